@@ -1,0 +1,150 @@
+/*
+ * mv_b200.h — C ABI of the B200-native (sm_100a) hot path of myrtle-vision's quantised ViT
+ * training step.  Plain pointers and sizes only; no torch types.  Every entry point
+ *   - works on caller-owned device buffers (no allocation inside),
+ *   - is ordered on the CUDA stream passed as the last argument (a cudaStream_t cast to void*),
+ *   - never synchronises the host,
+ *   - returns 0 on success, non-zero on error with the message in mv_last_error().
+ *
+ * Reference interfaces replaced (paths relative to the myrtle-vision repository):
+ *   B2, the fake-quant operator boundary:
+ *     src/myrtle_vision/utils/quantize.py:47-72  qtorch.quant.Quantizer(FloatingPoint|FixedPoint..)
+ *     src/myrtle_vision/utils/quantize.py:84     quant(X.data.float())  -> quant_cuda.float_quantize_nearest(a, man, exp)
+ *     QPyTorch 0.3.0 pybind surface (third-party, setup.py:10): float_quantize_{nearest,stochastic},
+ *     fixed_point_quantize_{nearest,stochastic}[_mask], block_quantize_{nearest,stochastic}
+ *   the torch/ATen ops under ViT.forward (src/myrtle_vision/models/vit.py:267-320):
+ *     torch.nn.qat.Linear.forward  (F.linear(x, weight_fake_quant(W), b) + activation_post_process)
+ *     nn.LayerNorm (:37), nn.GELU (:49), Attention.forward (:84-99), Residual.forward (:26-27)
+ *   and their autograd backward (straight-through quantisers, utils/quantize.py:87-89).
+ */
+#ifndef MV_B200_H
+#define MV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element container types */
+#define MV_F32 0
+#define MV_F16 1
+#define MV_BF16 2
+
+/* rounding modes (qtorch: "nearest" / "stochastic") */
+#define MV_ROUND_NEAREST 0
+#define MV_ROUND_STOCHASTIC 1
+
+const char* mv_last_error(void);
+int mv_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t mv_launch_count(void);
+
+/* ---------------------------------------------------------------- fake-quant (B2)
+ * qtorch.quant.float_quantize(x, exp, man, rounding)   [quant_cuda.float_quantize_*]
+ * in: fp32 [n]; out: container out_dtype [n] (MV_F32, or MV_F16 when the format fits fp16:
+ * exp<=5, man<=10).  Stochastic rounding: element i uses word (i&3) of
+ * Philox4x32-10(key=seed, counter={i>>2, offset}).  in == out is allowed for MV_F32. */
+int mv_float_quantize(const float* in, void* out, int out_dtype, int64_t n, int exp_bits,
+                      int man_bits, int rounding, uint64_t seed, uint64_t offset, void* stream);
+
+/* qtorch.quant.fixed_point_quantize(x, wl, fl, clamp, symmetric, rounding)
+ * mask (nullable): uint8 [n], 1 where the value was clamped (the *_mask variants; they always
+ * clamp).  Stochastic: r = (philox word >> 8) * 2^-24 in [0,1). */
+int mv_fixed_point_quantize(const float* in, float* out, uint8_t* mask, int64_t n, int wl, int fl,
+                            int clamp, int symmetric, int rounding, uint64_t seed,
+                            uint64_t offset, void* stream);
+
+/* qtorch.quant.block_quantize(x, wl, dim, rounding).  The tensor is viewed as
+ * [outer, dsize, inner] with `dim` the middle axis; whole_tensor != 0 means dim = -1 (one block).
+ * workspace: max(dsize,1) floats of scratch. */
+int mv_block_quantize(const float* in, float* out, float* workspace, int64_t outer, int64_t dsize,
+                      int64_t inner, int whole_tensor, int wl, int rounding, uint64_t seed,
+                      uint64_t offset, void* stream);
+
+/* debug: dump the 32-bit random stream the stochastic kernels consume for elements [0,n) */
+int mv_philox_bits(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* weight_fake_quant for a Linear weight W fp32 [rows, cols] (torch.nn.qat.Linear.forward):
+ * writes q(W) into `out` [rows, cols] and, if out_t != NULL, q(W)^T into out_t [cols, rows]
+ * (the dgrad operand).  Container out_dtype: MV_F16 (exp<=5) or MV_F32. */
+int mv_quantize_weight(const float* w, void* out, void* out_t, int out_dtype, int rows, int cols,
+                       int exp_bits, int man_bits, void* stream);
+
+/* ---------------------------------------------------------------- GEMM (tcgen05 / TMA)
+ * C[M,N] = A * B^T over K, fp32 accumulate in TMEM, fused epilogue.
+ *   a_major/b_major = 0: operand stored [M|N, K] row-major (K contiguous)   — forward, dgrad
+ *                   = 1: operand stored [K, M|N] row-major (M|N contiguous) — wgrad (dY^T, X^T)
+ *   a_dtype == b_dtype: MV_F16 or MV_BF16 (kind::f16; the hardware rejects f16 x bf16) or MV_F32 (kind::tf32)
+ * Epilogue, in this order (each optional):
+ *   acc (+ bias[n]) -> q_out -> [EPI_GELU: save u; acc = gelu(acc)] -> [EPI_DGELU: acc *= gelu'(u)]
+ *   -> (+ residual[m,n]) -> q_res -> store out (out_dtype) and out2 (out2_dtype)
+ *   accumulate != 0: out (fp32) += acc with red.global.add (split-K wgrad); bias/residual/q ignored.
+ */
+#define MV_EPI_NONE 0
+#define MV_EPI_GELU 1   /* aux (fp16 [M, ld_aux]) receives u = q_out(acc+bias); out = q_res(gelu(u)) */
+#define MV_EPI_DGELU 2  /* acc *= gelu'(aux[m,n]) */
+#define MV_EPI_EMBED 3  /* patch embedding: out row = (m / rows_per_img) * (rows_per_img+1) + 1 + m % rows_per_img,
+                           residual indexed by [1 + m % rows_per_img, n] (the resized pos-embedding) */
+
+typedef struct {
+    int M, N, K;
+    const void* A; int lda; int a_dtype; int a_major;
+    const void* B; int ldb; int b_dtype; int b_major;
+    const float* bias;            /* [N] or NULL */
+    const float* residual; int ld_res;   /* fp32 [M, ld_res] or NULL */
+    void* aux; int ld_aux;        /* fp16, see MV_EPI_* */
+    void* out; int ld_out; int out_dtype;
+    void* out2; int ld_out2; int out2_dtype;   /* optional second copy (e.g. bf16 for backward) */
+    int epilogue;
+    int q_out_exp, q_out_man;     /* exp == 0: identity */
+    int q_res_exp, q_res_man;
+    int accumulate;               /* split-K atomic accumulation into fp32 `out` */
+    int rows_per_img;             /* MV_EPI_EMBED */
+} mv_gemm_args;
+
+int mv_gemm(const mv_gemm_args* args, void* stream);
+
+
+/* ---------------------------------------------------------------- LayerNorm + quant (warp-shuffle)
+ * y = q_post(LN(q_in(x); gamma, beta)) : Sequential(QuantStub, nn.LayerNorm) followed by the next
+ * Linear's QuantStub (models/vit.py:37-41; utils/quantize.py:215-220).  One warp per row.
+ * y container: MV_F16 (formats that fit fp16) or MV_F32.  mean/rstd (fp32 [rows]) are saved for backward. */
+int mv_layernorm_q_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, void* y,
+                       int64_t ld_y, int y_dtype, float* mean, float* rstd, int rows, int D, float eps,
+                       int q_in_exp, int q_in_man, int q_post_exp, int q_post_man, void* stream);
+/* dx = LN'(dy; q_in(x)) + dres (dres nullable); dx_f16 (nullable) gets an fp16 copy of dx (the next
+ * GEMM operand).  dgamma/dbeta/dbias_prev (fp32 [D], nullable) are ACCUMULATED (+=): sum dy*xhat,
+ * sum dy, sum dx. */
+int mv_layernorm_q_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* dres,
+                       int64_t ld_dres, const float* gamma, const float* mean, const float* rstd,
+                       float* dx, int64_t ld_dx, void* dx_f16, int64_t ld_lp, float* dgamma,
+                       float* dbeta, float* dbias_prev, int rows, int D, int q_in_exp, int q_in_man,
+                       void* stream);
+/* out[c] += sum_r in[r,c]   (bias gradients); in_dtype MV_F16 or MV_F32 */
+int mv_colsum(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out, void* stream);
+/* img NCHW fp32 -> q(patches) [B*(H/P)*(W/P), P*P*C], (ph,pw,c) minor order (models/vit.py:271-275) */
+int mv_patchify_q(const float* img, void* out, int out_dtype, int B, int C, int H, int W, int P,
+                  int q_exp, int q_man, void* stream);
+/* x[b,0,:] = q(q(cls) + pos_q[0,:]) for every image b (models/vit.py:283-310) */
+int mv_cls_rows(const float* cls, const float* pos_q, float* x, int B, int n_tokens, int D, int q_exp,
+                int q_man, void* stream);
+/* fp32 -> fp16 (saturating) / bf16 copy of n elements (n % 4 == 0) */
+int mv_convert_f32(const float* in, void* out, int out_dtype, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- attention (tcgen05, flash-style)
+ * Attention.forward's (q @ k^T) * scale -> softmax -> @ v -> transpose/reshape (models/vit.py:87-97).
+ * qkv: fp16 [B*N, 3*H*64] as written by the to_qkv GEMM (q | k | v, 64 columns per head).
+ * out:  [B*N, H*64] container out_dtype, each value through q_out (the to_out QuantStub).
+ * lse:  fp32 [B, H, N], log2-domain log-sum-exp of the scaled scores (saved for backward). */
+int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float* lse, int B, int H, int N,
+                     float scale, int q_out_exp, int q_out_man, void* stream);
+/* autograd backward of the above.  o: the saved forward output (fp16), d_o: fp16 gradient w.r.t. it,
+ * delta: fp32 [B,H,N] scratch, dqkv: fp16 [B*N, 3*H*64] (dq | dk | dv).  Deterministic (no atomics). */
+int mv_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
+                     void* dqkv, int B, int H, int N, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MV_B200_H */

@@ -1,0 +1,503 @@
+// attention.cu — fused softmax attention forward/backward on tcgen05 (north-star kernel (b)).
+//
+// Replaces Attention.forward's  (q @ k^T) * scale -> softmax -> @ v -> transpose/reshape
+// (src/myrtle_vision/models/vit.py:87-97) and its autograd backward.  Scores and
+// probabilities live only in TMEM / shared memory: the reference's two [B,h,N,N] fp32
+// tensors per layer never reach HBM.  Head dim is fixed at 64 (models/vit.py:178).
+//
+// Layout: qkv fp16 [B*N, 3*D] exactly as the to_qkv GEMM writes it (q | k | v, heads contiguous,
+// 64 columns each), read through one 3-D TMA map {3D, N, B} so rows past N are zero-filled
+// instead of running into the next image.  Output / gradients use the same token-major layout,
+// which is what the next GEMM consumes ("transpose(1,2).reshape" is free).
+//
+//   warp 0     TMA producer           warp 1     tcgen05.mma issuer (+ TMEM alloc)
+//   warps 2-5  one thread per query row (TMEM lane): softmax / dS math, epilogue
+//
+// Forward:  S = Q K^T (TMEM) -> online softmax in registers -> P (fp16) to swizzled smem ->
+//           O_j = P V (TMEM) -> rescale-accumulate in registers -> q_out -> fp16 store.
+//           Saves L = m + log2(l) (log2 domain) per row for the backward.
+// Backward: two passes, no atomics, deterministic:
+//   KV pass (CTA = key block):  dV += P^T dO,  dK += dS^T Q       (MN-major A operands)
+//   Q  pass (CTA = query block): dQ += dS K
+//   with P = exp2(S*c - L), dS = P * (dP - Delta) * scale, dP = dO V^T, Delta = rowsum(dO*O).
+#include "common.cuh"
+#include "quant_dev.cuh"
+#include "../../include/mv_b200.h"
+
+namespace mv {
+
+extern int64_t g_launches;
+
+constexpr int kAttThreads = 192;
+constexpr int kTile = 16384;          // 128 rows x 128 B
+constexpr uint32_t kIdescS = make_idesc(0, 0, 0, 0, 128, 128);     // A K-major, B K-major, N=128
+constexpr uint32_t kIdescPV = make_idesc(0, 0, 0, 1, 128, 64);     // A K-major, B MN-major, N=64
+constexpr uint32_t kIdescTT = make_idesc(0, 0, 1, 1, 128, 64);     // A MN-major, B MN-major, N=64
+
+__device__ __forceinline__ float sat16f(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// write 32 consecutive fp16 columns [c32*32, c32*32+32) of row r into a [128 x 128-col] operand
+// stored as two K-major SW128 sub-tiles of 64 columns (16 KB each)
+__device__ __forceinline__ void store_p_chunk(uint8_t* tile_base, int r, int c32, const uint32_t (&w)[16]) {
+    uint8_t* sub = tile_base + (c32 >> 1) * kTile + r * 128;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int chunk = ((c32 & 1) * 4 + t) ^ (r & 7);
+        *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(w[4 * t], w[4 * t + 1], w[4 * t + 2], w[4 * t + 3]);
+    }
+}
+
+struct AttnFwdDev {
+    int B, H, N, D;
+    float scale_log2;
+    void* out; int out_dtype; int ld_out;
+    FloatFmt q_out;
+    float* lse;
+};
+
+__global__ void __launch_bounds__(kAttThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + kTile;                 // [2 stages][K, V]
+    uint8_t* sP = smem + 5 * kTile;              // 2 sub-tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTile);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;                // [2]
+    uint64_t* kv_empty = bars + 3;               // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;
+    uint64_t* o_full = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.N + 127) / 128;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, kTile);
+            tma_load_3d(sQ, &tmap_qkv, q_full, h * 64, q0, b);
+            for (int j = 0; j < nblk; j++) {
+                const int st = j & 1;
+                mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
+                tma_load_3d(sKV + st * 2 * kTile, &tmap_qkv, &kv_full[st], p.D + h * 64, j * 128, b);
+                tma_load_3d(sKV + st * 2 * kTile + kTile, &tmap_qkv, &kv_full[st], 2 * p.D + h * 64, j * 128, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+            mbar_wait(q_full, 0);
+            auto issue_s = [&](int j) {
+                const int st = j & 1;
+                mbar_wait(&kv_full[st], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t aK = smem_u32(sKV + st * 2 * kTile);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    umma_f16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024),
+                             make_smem_desc_sw128(aK + k * 32, 16, 1024), kIdescS, k > 0);
+                umma_commit(s_full);
+            };
+            issue_s(0);
+            for (int j = 0; j < nblk; j++) {
+                const int st = j & 1;
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+                const uint32_t aV = smem_u32(sKV + st * 2 * kTile + kTile);
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    umma_f16(tO, make_smem_desc_sw128(aP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+                             make_smem_desc_sw128(aV + k * 2048, 8192, 1024), kIdescPV, k > 0);
+                umma_commit(o_full);
+                umma_commit(&kv_empty[st]);
+                if (j + 1 < nblk) issue_s(j + 1);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const int qrow = q0 + r;
+        const uint32_t lane_off = uint32_t(quad * 32) << 16;
+        float m = -INFINITY, l = 0.f;
+        float o[64];
+#pragma unroll
+        for (int i = 0; i < 64; i++) o[i] = 0.f;
+        for (int j = 0; j < nblk; j++) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            const int kbase = j * 128;
+            // pass 1: row max of the scaled scores
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; c++) {
+                uint32_t s[32];
+                tmem_ld_32x32(tS + lane_off + c * 32, s);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 32; t++)
+                    if (kbase + c * 32 + t < p.N) mx = fmaxf(mx, __uint_as_float(s[t]));
+            }
+            const float m_new = fmaxf(m, mx * p.scale_log2);
+            const float alpha = exp2f(m - m_new);          // m = -inf on the first block -> 0
+            float psum = 0.f;
+            // pass 2: P = exp2(s*c - m_new) -> fp16 -> swizzled smem (A operand of P.V)
+#pragma unroll 1
+            for (int c = 0; c < 4; c++) {
+                uint32_t s[32];
+                tmem_ld_32x32(tS + lane_off + c * 32, s);
+                tmem_ld_wait();
+                uint32_t w[16];
+#pragma unroll
+                for (int t = 0; t < 16; t++) {
+                    const int k0 = kbase + c * 32 + 2 * t;
+                    float p0 = k0 < p.N ? exp2f(__uint_as_float(s[2 * t]) * p.scale_log2 - m_new) : 0.f;
+                    float p1 = k0 + 1 < p.N ? exp2f(__uint_as_float(s[2 * t + 1]) * p.scale_log2 - m_new) : 0.f;
+                    // accumulate the row sum from the fp16-rounded values the MMA will see
+                    const __half2 hp = __floats2half2_rn(p0, p1);
+                    const float2 fp = __half22float2(hp);
+                    psum += fp.x + fp.y;
+                    w[t] = *reinterpret_cast<const uint32_t*>(&hp);
+                }
+                store_p_chunk(sP, r, c, w);
+            }
+            l = l * alpha + psum;
+            m = m_new;
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+            // O_j = P V_j ; accumulate with rescale
+            mbar_wait(o_full, j & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                uint32_t v[32];
+                tmem_ld_32x32(tO + lane_off + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 32; t++) o[c * 32 + t] = o[c * 32 + t] * alpha + __uint_as_float(v[t]);
+            }
+            tc_fence_before();
+        }
+        if (qrow < p.N) {
+            const float inv = 1.0f / l;
+            const int64_t grow = int64_t(b) * p.N + qrow;
+            if (p.lse != nullptr) p.lse[(int64_t(b) * p.H + h) * p.N + qrow] = m + log2f(l);
+#pragma unroll
+            for (int i = 0; i < 64; i++) o[i] = fq_nearest(o[i] * inv, p.q_out);
+            if (p.out_dtype == MV_F16) {
+                __half* dst = reinterpret_cast<__half*>(p.out) + grow * p.ld_out + h * 64;
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_h2(sat16f(o[8 * i]), sat16f(o[8 * i + 1])), pack_h2(sat16f(o[8 * i + 2]), sat16f(o[8 * i + 3])),
+                                                                  pack_h2(sat16f(o[8 * i + 4]), sat16f(o[8 * i + 5])), pack_h2(sat16f(o[8 * i + 6]), sat16f(o[8 * i + 7])));
+            } else {
+                float* dst = reinterpret_cast<float*>(p.out) + grow * p.ld_out + h * 64;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    reinterpret_cast<float4*>(dst)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem_base); }
+}
+
+// Delta[b,h,n] = sum_d dO[bn, h*64+d] * O[bn, h*64+d]
+__global__ void attn_delta_kernel(const __half* __restrict__ dO, const __half* __restrict__ O,
+                                  float* __restrict__ delta, int B, int H, int N, int D) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;     // (row, head)
+    if (i >= int64_t(B) * N * H) return;
+    const int64_t row = i / H; const int h = int(i % H);
+    const uint4* a = reinterpret_cast<const uint4*>(dO + row * D + h * 64);
+    const uint4* c = reinterpret_cast<const uint4*>(O + row * D + h * 64);
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const uint4 x = a[t], y = c[t];
+        const __half2* xh = reinterpret_cast<const __half2*>(&x);
+        const __half2* yh = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float2 fx = __half22float2(xh[u]), fy = __half22float2(yh[u]);
+            s += fx.x * fy.x + fx.y * fy.y;
+        }
+    }
+    const int b = int(row / N), n = int(row % N);
+    delta[(int64_t(b) * H + h) * N + n] = s;
+}
+
+struct AttnBwdDev {
+    int B, H, N, D;
+    float scale_log2, scale;
+    const float* lse;
+    const float* delta;
+    __half* dqkv; int ld_dqkv;
+};
+
+// kModeKV = true : CTA owns key block blockIdx.x; loops over query blocks; emits dK, dV.
+// kModeKV = false: CTA owns query block blockIdx.x; loops over key blocks;  emits dQ.
+template <bool kModeKV>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                const AttnBwdDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sR0 = smem;                       // resident: K_j (KV) | Q_i (Q)
+    uint8_t* sR1 = smem + kTile;               // resident: V_j (KV) | dO_i (Q)
+    uint8_t* sRing = smem + 2 * kTile;         // [2 stages][X, Y]: (Q_i, dO_i) (KV) | (K_j, V_j) (Q)
+    uint8_t* sdS = smem + 6 * kTile;           // dS fp16, two 64-column sub-tiles
+    uint8_t* sP = smem + 8 * kTile;            // P fp16 (KV mode only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (kModeKV ? 10 : 8) * kTile);
+    uint64_t* res_full = bars;
+    uint64_t* ring_full = bars + 1;            // [2]
+    uint64_t* ring_empty = bars + 3;           // [2]
+    uint64_t* sdp_full = bars + 5;
+    uint64_t* pds_full = bars + 6;
+    uint64_t* pds_empty = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.N + 127) / 128;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+        tma_prefetch_desc(&tmap_do);
+        mbar_init(res_full, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
+        mbar_init(sdp_full, 1); mbar_init(pds_full, 4); mbar_init(pds_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tdP = tmem_base + 128, tAcc0 = tmem_base + 256, tAcc1 = tmem_base + 320;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(res_full, 2 * kTile);
+            if (kModeKV) {
+                tma_load_3d(sR0, &tmap_qkv, res_full, p.D + h * 64, blk0, b);        // K_j
+                tma_load_3d(sR1, &tmap_qkv, res_full, 2 * p.D + h * 64, blk0, b);    // V_j
+            } else {
+                tma_load_3d(sR0, &tmap_qkv, res_full, h * 64, blk0, b);              // Q_i
+                tma_load_3d(sR1, &tmap_do, res_full, h * 64, blk0, b);               // dO_i
+            }
+            for (int it = 0; it < nblk; it++) {
+                const int st = it & 1;
+                mbar_wait(&ring_empty[st], ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&ring_full[st], 2 * kTile);
+                uint8_t* x = sRing + st * 2 * kTile;
+                if (kModeKV) {
+                    tma_load_3d(x, &tmap_qkv, &ring_full[st], h * 64, it * 128, b);             // Q_i
+                    tma_load_3d(x + kTile, &tmap_do, &ring_full[st], h * 64, it * 128, b);      // dO_i
+                } else {
+                    tma_load_3d(x, &tmap_qkv, &ring_full[st], p.D + h * 64, it * 128, b);       // K_j
+                    tma_load_3d(x + kTile, &tmap_qkv, &ring_full[st], 2 * p.D + h * 64, it * 128, b);   // V_j
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t aR0 = smem_u32(sR0), aR1 = smem_u32(sR1), adS = smem_u32(sdS), aP = smem_u32(sP);
+            mbar_wait(res_full, 0);
+            for (int it = 0; it < nblk; it++) {
+                const int st = it & 1;
+                mbar_wait(&ring_full[st], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t aX = smem_u32(sRing + st * 2 * kTile), aY = aX + kTile;
+                // S = Q K^T ; dP = dO V^T   (all operands K-major over d)
+                const uint32_t aQ = kModeKV ? aX : aR0, aK = kModeKV ? aR0 : aX;
+                const uint32_t aDO = kModeKV ? aY : aR1, aV = kModeKV ? aR1 : aY;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    umma_f16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), kIdescS, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    umma_f16(tdP, make_smem_desc_sw128(aDO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), kIdescS, k > 0);
+                umma_commit(sdp_full);
+                mbar_wait(pds_full, it & 1);
+                tc_fence_after();
+                if (kModeKV) {
+                    // dV[keys, d] += P^T dO : A = P as MN-major (M = keys), B = dO as MN-major (N = d); K = 128 q rows
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        umma_f16(tAcc0, make_smem_desc_sw128(aP + k * 2048, kTile, 1024),
+                                 make_smem_desc_sw128(aDO + k * 2048, 8192, 1024), kIdescTT, (it > 0 || k > 0));
+                    // dK[keys, d] += dS^T Q
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        umma_f16(tAcc1, make_smem_desc_sw128(adS + k * 2048, kTile, 1024),
+                                 make_smem_desc_sw128(aQ + k * 2048, 8192, 1024), kIdescTT, (it > 0 || k > 0));
+                } else {
+                    // dQ[q, d] += dS K : A = dS K-major over keys, B = K_j as MN-major (N = d); K = 128 keys
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        umma_f16(tAcc0, make_smem_desc_sw128(adS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+                                 make_smem_desc_sw128(aK + k * 2048, 8192, 1024), kIdescPV, (it > 0 || k > 0));
+                }
+                umma_commit(&ring_empty[st]);
+                umma_commit(pds_empty);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_off = uint32_t(quad * 32) << 16;
+        for (int it = 0; it < nblk; it++) {
+            // thread row = query row of the current q block
+            const int qrow = (kModeKV ? it * 128 : blk0) + r;
+            const int kbase = kModeKV ? blk0 : it * 128;
+            const bool q_ok = qrow < p.N;
+            float L = 0.f, dl = 0.f;
+            if (q_ok) {
+                const int64_t si = (int64_t(b) * p.H + h) * p.N + qrow;
+                L = p.lse[si]; dl = p.delta[si];
+            }
+            mbar_wait(sdp_full, it & 1);
+            tc_fence_after();
+            mbar_wait(pds_empty, (it & 1) ^ 1);       // previous iteration's MMAs are done with sP / sdS
+#pragma unroll 1
+            for (int c = 0; c < 4; c++) {
+                uint32_t s[32], dp[32];
+                tmem_ld_32x32(tS + lane_off + c * 32, s);
+                tmem_ld_32x32(tdP + lane_off + c * 32, dp);
+                tmem_ld_wait();
+                uint32_t wp[16], wd[16];
+#pragma unroll
+                for (int t = 0; t < 16; t++) {
+                    float pv[2], dv[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const bool ok = q_ok && (kbase + c * 32 + 2 * t + u < p.N);
+                        const float pe = ok ? exp2f(__uint_as_float(s[2 * t + u]) * p.scale_log2 - L) : 0.f;
+                        pv[u] = pe;
+                        dv[u] = ok ? sat16f(pe * (__uint_as_float(dp[2 * t + u]) - dl) * p.scale) : 0.f;
+                    }
+                    wp[t] = pack_h2(pv[0], pv[1]);
+                    wd[t] = pack_h2(dv[0], dv[1]);
+                }
+                store_p_chunk(sdS, r, c, wd);
+                if (kModeKV) store_p_chunk(sP, r, c, wp);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pds_full);
+        }
+        // all accumulating MMAs of the last iteration have retired
+        mbar_wait(pds_empty, (nblk - 1) & 1);
+        tc_fence_after();
+        const int orow = blk0 + r;              // key row (KV mode) or query row (Q mode)
+        for (int a = 0; a < (kModeKV ? 2 : 1); a++) {
+            uint32_t v[32];
+            // KV: acc0 = dV -> columns 2D + h*64 ; acc1 = dK -> columns D + h*64.  Q: acc0 = dQ -> h*64
+            const int col = kModeKV ? ((a == 0 ? 2 : 1) * p.D + h * 64) : h * 64;
+            __half* dst = p.dqkv + (int64_t(b) * p.N + orow) * p.ld_dqkv + col;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                tmem_ld_32x32((a == 0 ? tAcc0 : tAcc1) + lane_off + c * 32, v);
+                tmem_ld_wait();
+                if (orow < p.N) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        reinterpret_cast<uint4*>(dst + c * 32)[i] =
+                            make_uint4(pack_h2(sat16f(__uint_as_float(v[8 * i])), sat16f(__uint_as_float(v[8 * i + 1]))),
+                                       pack_h2(sat16f(__uint_as_float(v[8 * i + 2])), sat16f(__uint_as_float(v[8 * i + 3]))),
+                                       pack_h2(sat16f(__uint_as_float(v[8 * i + 4])), sat16f(__uint_as_float(v[8 * i + 5]))),
+                                       pack_h2(sat16f(__uint_as_float(v[8 * i + 6])), sat16f(__uint_as_float(v[8 * i + 7]))));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+
+constexpr int kAttnFwdSmem = 7 * kTile + 1024 + 256;
+constexpr int kAttnBwdKVSmem = 10 * kTile + 1024 + 256;
+constexpr int kAttnBwdQSmem = 8 * kTile + 1024 + 256;
+
+}  // namespace mv
+
+using namespace mv;
+
+extern "C" int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float* lse, int B, int H, int N,
+                                float scale, int q_out_exp, int q_out_man, void* stream) {
+    MV_CHECK(B > 0 && H > 0 && N > 0 && qkv && out, "mv_attention_fwd: bad arguments");
+    MV_CHECK(out_dtype == MV_F16 || out_dtype == MV_F32, "mv_attention_fwd: bad output container");
+    const int D = H * 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwdSmem));
+        attr_done = true;
+    }
+    CUtensorMap tm;
+    if (make_tmap_3d(&tm, qkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 128, 1)) return 1;
+    AttnFwdDev p;
+    p.B = B; p.H = H; p.N = N; p.D = D;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.out = out; p.out_dtype = out_dtype; p.ld_out = D;
+    p.q_out = FloatFmt{q_out_exp, q_out_man};
+    p.lse = lse;
+    dim3 grid((N + 127) / 128, H, B);
+    attn_fwd_kernel<<<grid, kAttThreads, kAttnFwdSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "attention fwd launch");
+}
+
+extern "C" int mv_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
+                                void* dqkv, int B, int H, int N, float scale, void* stream) {
+    MV_CHECK(B > 0 && H > 0 && N > 0 && qkv && o && d_o && lse && delta && dqkv, "mv_attention_bwd: bad arguments");
+    const int D = H * 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdKVSmem));
+        MV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdQSmem));
+        attr_done = true;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUtensorMap tq, td;
+    if (make_tmap_3d(&tq, qkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 128, 1)) return 1;
+    if (make_tmap_3d(&td, d_o, MV_F16, D, N, B, D, uint64_t(N) * D, 64, 128, 1)) return 1;
+    const int64_t nrh = int64_t(B) * N * H;
+    attn_delta_kernel<<<unsigned((nrh + 255) / 256), 256, 0, st>>>((const __half*)d_o, (const __half*)o, delta, B, H, N, D);
+    g_launches++;
+    AttnBwdDev p;
+    p.B = B; p.H = H; p.N = N; p.D = D;
+    p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+    p.lse = lse; p.delta = delta;
+    p.dqkv = reinterpret_cast<__half*>(dqkv); p.ld_dqkv = 3 * D;
+    dim3 grid((N + 127) / 128, H, B);
+    attn_bwd_kernel<true><<<grid, kAttThreads, kAttnBwdKVSmem, st>>>(tq, td, p);
+    g_launches++;
+    attn_bwd_kernel<false><<<grid, kAttThreads, kAttnBwdQSmem, st>>>(tq, td, p);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "attention bwd launch");
+}

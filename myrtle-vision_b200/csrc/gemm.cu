@@ -1,0 +1,392 @@
+// gemm.cu — persistent, warp-specialised tcgen05 GEMM with fused fake-quant epilogues
+// (north-star kernel class (b)).  C[M,N] = A * B^T over K, fp32 accumulation in TMEM.
+//
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled tiles, 6-stage mbarrier ring)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma; owns the TMEM allocation)
+//   warps 2..5  epilogue       (tcgen05.ld 32 lanes x 32 columns; bias / quant / GELU / residual)
+//
+// TMEM holds two 128x128 fp32 accumulators so the epilogue of tile i overlaps the MMAs of
+// tile i+1.  Operands are the *exact* fp16 containers of the fake-quantised tensors (or
+// tf32-in-fp32 for the TF32 format), so products are exact and only the fp32 accumulation
+// order differs from the reference's F.linear (torch.nn.qat.Linear.forward).
+// Both K-major and MN-major operands are supported through the UMMA shared-memory
+// descriptors, which lets wgrad (dW = dY^T X) read dY and X in their natural layouts.
+#include "common.cuh"
+#include "quant_dev.cuh"
+#include "../../include/mv_b200.h"
+
+namespace mv {
+
+extern int64_t g_launches;
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int kStages = 6;
+constexpr int kTileBytes = BM * 128;                  // one operand tile per stage: 16 KB
+constexpr int kStageBytes = 2 * kTileBytes;
+constexpr int kGemmThreads = 192;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmDev {
+    int M, N, K;
+    int m_tiles, n_tiles, splits, kb_total, kb_per_split;
+    int a_major, b_major;
+    uint32_t idesc;
+    const float* bias;
+    const float* residual; int ld_res;
+    __half* aux; int ld_aux;
+    void* out; int ld_out; int out_dtype;
+    void* out2; int ld_out2; int out2_dtype;
+    int epilogue;
+    FloatFmt q_out, q_res;
+    int accumulate;
+    int rows_per_img;
+};
+
+__device__ __forceinline__ float gelu_exact(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+template <typename T> __device__ __forceinline__ void store_row32(T* dst, const float (&v)[32]);
+template <> __device__ __forceinline__ void store_row32<float>(float* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+template <> __device__ __forceinline__ void store_row32<__half>(__half* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        __half2 h0 = __floats2half2_rn(sat16(v[8 * j + 0]), sat16(v[8 * j + 1]));
+        __half2 h1 = __floats2half2_rn(sat16(v[8 * j + 2]), sat16(v[8 * j + 3]));
+        __half2 h2 = __floats2half2_rn(sat16(v[8 * j + 4]), sat16(v[8 * j + 5]));
+        __half2 h3 = __floats2half2_rn(sat16(v[8 * j + 6]), sat16(v[8 * j + 7]));
+        reinterpret_cast<uint4*>(dst)[j] =
+            make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                       *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+    }
+}
+template <> __device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+        reinterpret_cast<uint4*>(dst)[j] =
+            make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                       *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+    }
+}
+
+__device__ __forceinline__ void store_out(void* base, int dtype, int64_t row, int ld, int col,
+                                          const float (&v)[32], bool vec_ok, int ncols_valid) {
+    if (dtype == MV_F32) {
+        float* p = reinterpret_cast<float*>(base) + row * ld + col;
+        if (vec_ok) store_row32<float>(p, v);
+        else for (int j = 0; j < 32; j++) if (j < ncols_valid) p[j] = v[j];
+    } else if (dtype == MV_F16) {
+        __half* p = reinterpret_cast<__half*>(base) + row * ld + col;
+        if (vec_ok) store_row32<__half>(p, v);
+        else for (int j = 0; j < 32; j++) if (j < ncols_valid) p[j] = __float2half_rn(sat16(v[j]));
+    } else {
+        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + row * ld + col;
+        if (vec_ok) store_row32<__nv_bfloat16>(p, v);
+        else for (int j = 0; j < 32; j++) if (j < ncols_valid) p[j] = __float2bfloat16_rn(v[j]);
+    }
+}
+
+// kEsz: operand element size (2: f16/bf16, kind::f16; 4: tf32-in-fp32, kind::tf32)
+template <int kEsz>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const GemmDev p) {
+    constexpr int BK = 128 / kEsz;             // elements of K per stage (one 128-byte swizzle row)
+    constexpr int UMMA_K = 32 / kEsz;          // K elements per tcgen05.mma
+    constexpr int kMnChunk = 128 / kEsz;       // MN elements per 128-byte row (MN-major tiles)
+    constexpr int kMnBoxBytes = BK * 128;      // one MN-major TMA box: BK k-rows of 128 bytes
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_units = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const int split = u % p.splits;
+                const int tile = u / p.splits;
+                const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kStageBytes;
+                    uint8_t* sb = sa + kTileBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                    if (p.a_major == 0) {
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BM / kMnChunk; c++)
+                            tma_load_2d(sa + c * kMnBoxBytes, &tmap_a, &full_bar[stage], m0 + c * kMnChunk, kb * BK);
+                    }
+                    if (p.b_major == 0) {
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BN / kMnChunk; c++)
+                            tma_load_2d(sb + c * kMnBoxBytes, &tmap_b, &full_bar[stage], n0 + c * kMnChunk, kb * BK);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            // K-major: 8-row groups 1024 B apart, K advance = 32 B inside the swizzled row.
+            // MN-major: 128-byte rows are k-slices; 8 k-rows per 1024 B group (SBO), next 64/32
+            // MN elements one TMA box further (LBO); K advance = UMMA_K rows.
+            const uint32_t a_lbo = p.a_major ? kMnBoxBytes : 16, b_lbo = p.b_major ? kMnBoxBytes : 16;
+            const uint32_t a_kstep = p.a_major ? UMMA_K * 128 : 32, b_kstep = p.b_major ? UMMA_K * 128 : 32;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const int split = u % p.splits;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sb = sa + kTileBytes;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+                        const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+                        if (kEsz == 2) umma_f16(tmem_d, adesc, bdesc, p.idesc, accum);
+                        else umma_tf32(tmem_d, adesc, bdesc, p.idesc, accum);
+                    }
+                    umma_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);                  // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int split = u % p.splits;
+            const int tile = u / p.splits;
+            const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int m = m0 + quad * 32 + lane;
+            const bool row_ok = m < p.M;
+            int64_t orow = m, rrow = m;
+            if (p.epilogue == MV_EPI_EMBED) {
+                const int img = m / p.rows_per_img, pi = m % p.rows_per_img;
+                orow = int64_t(img) * (p.rows_per_img + 1) + 1 + pi;
+                rrow = 1 + pi;
+            }
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32, r);
+                tmem_ld_wait();
+                const int n = n0 + c * 32;
+                if (!row_ok || n >= p.N) continue;
+                const int nvalid = min(32, p.N - n);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+                if (p.accumulate) {
+                    float* o = reinterpret_cast<float*>(p.out) + int64_t(m) * p.ld_out + n;
+                    if (split == 0 && p.bias != nullptr) {
+                        // (bias only makes sense for non-split use; kept for completeness)
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j++) if (j < nvalid) atomicAdd(o + j, v[j]);
+                    continue;
+                }
+                const bool full = nvalid == 32;
+                if (p.bias != nullptr) {
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; j++) if (j < nvalid) v[j] += __ldg(p.bias + n + j);
+                    }
+                }
+                if (p.q_out.exp_bits) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = float_quantize_elem<false>(v[j], 0u, p.q_out.exp_bits, p.q_out.man_bits);
+                }
+                if (p.epilogue == MV_EPI_GELU) {
+                    __half* up = p.aux + int64_t(m) * p.ld_aux + n;
+                    if (full && (p.ld_aux & 7) == 0) store_row32<__half>(up, v);
+                    else for (int j = 0; j < 32; j++) if (j < nvalid) up[j] = __float2half_rn(v[j]);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = gelu_exact(v[j]);
+                } else if (p.epilogue == MV_EPI_DGELU) {
+                    const __half* up = p.aux + int64_t(m) * p.ld_aux + n;
+                    if (full && (p.ld_aux & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint4 w = *reinterpret_cast<const uint4*>(up + 8 * j);
+                            const __half2* h = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const float2 f = __half22float2(h[q]);
+                                v[8 * j + 2 * q] *= gelu_grad(f.x);
+                                v[8 * j + 2 * q + 1] *= gelu_grad(f.y);
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < 32; j++) if (j < nvalid) v[j] *= gelu_grad(__half2float(up[j]));
+                    }
+                }
+                if (p.residual != nullptr) {
+                    const float* rp = p.residual + rrow * p.ld_res + n;
+                    if (full && (p.ld_res & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const float4 b = *reinterpret_cast<const float4*>(rp + 4 * j);
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; j++) if (j < nvalid) v[j] += rp[j];
+                    }
+                }
+                if (p.q_res.exp_bits) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = float_quantize_elem<false>(v[j], 0u, p.q_res.exp_bits, p.q_res.man_bits);
+                }
+                const int esz_o = p.out_dtype == MV_F32 ? 4 : 2;
+                const bool vec_o = full && ((p.ld_out * esz_o) % 16 == 0);
+                store_out(p.out, p.out_dtype, orow, p.ld_out, n, v, vec_o, nvalid);
+                if (p.out2 != nullptr) {
+                    const int esz_2 = p.out2_dtype == MV_F32 ? 4 : 2;
+                    const bool vec_2 = full && ((p.ld_out2 * esz_2) % 16 == 0);
+                    store_out(p.out2, p.out2_dtype, orow, p.ld_out2, n, v, vec_2, nvalid);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * BN>(tmem_base);
+    }
+}
+
+}  // namespace mv
+
+using namespace mv;
+
+extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
+    MV_CHECK(a != nullptr, "mv_gemm: null args");
+    MV_CHECK(a->M > 0 && a->N > 0 && a->K > 0, "mv_gemm: bad shape %dx%dx%d", a->M, a->N, a->K);
+    MV_CHECK(a->A && a->B && a->out, "mv_gemm: null operand");
+    const bool tf32 = a->a_dtype == MV_F32;
+    MV_CHECK(a->a_dtype == a->b_dtype, "mv_gemm: A and B must share one element type (tcgen05 kind::f16 rejects f16 x bf16)");
+    const int esz = tf32 ? 4 : 2;
+    const int BK = 128 / esz;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        attr_done = true;
+    }
+    if (a->accumulate) MV_CHECK(a->out_dtype == MV_F32, "mv_gemm: accumulate needs an fp32 output");
+    if (a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU) MV_CHECK(a->aux != nullptr, "mv_gemm: GELU epilogues need aux");
+    if (a->epilogue == MV_EPI_EMBED) MV_CHECK(a->rows_per_img > 0, "mv_gemm: EMBED epilogue needs rows_per_img");
+
+    CUtensorMap ta, tb;
+    // K-major operand [rows = M|N, cols = K]: box = 128 rows x 128 B of K.
+    // MN-major operand stored [K, M|N]: box = BK k-rows x 128 B of M|N.
+    if (a->a_major == 0) { if (make_tmap_2d(&ta, a->A, a->a_dtype, a->M, a->K, a->lda, BM, BK)) return 1; }
+    else                 { if (make_tmap_2d(&ta, a->A, a->a_dtype, a->K, a->M, a->lda, BK, 128 / esz)) return 1; }
+    if (a->b_major == 0) { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->N, a->K, a->ldb, BN, BK)) return 1; }
+    else                 { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->K, a->N, a->ldb, BK, 128 / esz)) return 1; }
+
+    GemmDev p;
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.m_tiles = (a->M + BM - 1) / BM;
+    p.n_tiles = (a->N + BN - 1) / BN;
+    p.kb_total = (a->K + BK - 1) / BK;
+    int splits = 1;
+    if (a->accumulate) {
+        const int tiles = p.m_tiles * p.n_tiles;
+        splits = kNumSMs / tiles;
+        if (splits < 1) splits = 1;
+        if (splits > p.kb_total) splits = p.kb_total;
+    }
+    p.kb_per_split = (p.kb_total + splits - 1) / splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.a_major = a->a_major; p.b_major = a->b_major;
+    const int afmt = tf32 ? 2 : (a->a_dtype == MV_BF16 ? 1 : 0);
+    const int bfmt = tf32 ? 2 : (a->b_dtype == MV_BF16 ? 1 : 0);
+    p.idesc = make_idesc(afmt, bfmt, a->a_major, a->b_major, BM, BN);
+    p.bias = a->bias; p.residual = a->residual; p.ld_res = a->ld_res;
+    p.aux = reinterpret_cast<__half*>(a->aux); p.ld_aux = a->ld_aux;
+    p.out = a->out; p.ld_out = a->ld_out; p.out_dtype = a->out_dtype;
+    p.out2 = a->out2; p.ld_out2 = a->ld_out2; p.out2_dtype = a->out2_dtype;
+    p.epilogue = a->epilogue;
+    p.q_out = FloatFmt{a->q_out_exp, a->q_out_man};
+    p.q_res = FloatFmt{a->q_res_exp, a->q_res_man};
+    p.accumulate = a->accumulate;
+    p.rows_per_img = a->rows_per_img;
+
+    const int units = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = units < kNumSMs ? units : kNumSMs;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (tf32) gemm_kernel<4><<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tb, p);
+    else gemm_kernel<2><<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tb, p);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "gemm launch");
+}

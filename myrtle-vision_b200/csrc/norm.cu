@@ -1,0 +1,398 @@
+// norm.cu — warp-shuffle LayerNorm forward/backward fused with its fake-quantisers, plus the
+// small memory-bound helpers of the step (north-star kernel class (c)).
+//
+// Forward (one warp per token row, row held in registers, 128-bit accesses):
+//     y = q_post( LN( q_in(x) ; gamma, beta ) )      -> fp16 / fp32 container
+// which is the reference's Sequential(QuantStub, LayerNorm) followed by the next Linear's
+// QuantStub (src/myrtle_vision/models/vit.py:37-41, utils/quantize.py:215-220, Appendix A of
+// SURVEY.md); q is idempotent so LN-output quant (FP16_16) and the next stub collapse.
+// Backward (straight-through quantisers, utils/quantize.py:87-89):
+//     dx = LN'(dy; q_in(x)) + dres,   dgamma += sum dy*xhat,   dbeta += sum dy,
+//     dbias_prev += sum dx   (bias gradient of the Linear that produced the residual stream)
+// HBM traffic per element: fwd 4 B read + 2 B write (fp16 container); bwd 12 B read + 6 B write.
+#include "common.cuh"
+#include "quant_dev.cuh"
+#include "../../include/mv_b200.h"
+
+namespace mv {
+
+extern int64_t g_launches;
+
+constexpr int kLnWarps = 8;
+constexpr int kLnMaxVec = 8;     // float4 per lane: D <= 32*4*8 = 1024
+
+__device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ gamma,
+              const float* __restrict__ beta, OutT* __restrict__ y, int64_t ld_y,
+              float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int D, float eps,
+              FloatFmt q_in, FloatFmt q_post) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec = D >> 2;
+    float4 g[NV], b[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const int c = lane + 32 * i;
+        if (c < nvec) {
+            g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+            b[i] = __ldg(reinterpret_cast<const float4*>(beta) + c);
+        }
+    }
+    for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
+        const float4* xr = reinterpret_cast<const float4*>(x + int64_t(row) * ld_x);
+        float4 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                v[i] = __ldcs(xr + c);
+                v[i].x = fq_nearest(v[i].x, q_in); v[i].y = fq_nearest(v[i].y, q_in);
+                v[i].z = fq_nearest(v[i].z, q_in); v[i].w = fq_nearest(v[i].w, q_in);
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+        }
+        const float mean = warp_sum(s) / float(D);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+                ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(ss) / float(D) + eps);
+        if (lane == 0 && mean_out != nullptr) { mean_out[row] = mean; rstd_out[row] = rstd; }
+        OutT* yr = y + int64_t(row) * ld_y;
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                float4 o;
+                o.x = fq_nearest((v[i].x - mean) * rstd * g[i].x + b[i].x, q_post);
+                o.y = fq_nearest((v[i].y - mean) * rstd * g[i].y + b[i].y, q_post);
+                o.z = fq_nearest((v[i].z - mean) * rstd * g[i].z + b[i].z, q_post);
+                o.w = fq_nearest((v[i].w - mean) * rstd * g[i].w + b[i].w, q_post);
+                if (sizeof(OutT) == 4) {
+                    reinterpret_cast<float4*>(yr)[c] = o;
+                } else {
+                    __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+                    reinterpret_cast<uint2*>(yr)[c] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                }
+            }
+        }
+    }
+}
+
+// dy: fp32 [rows, D] gradient w.r.t. the LN output; dres: fp32 [rows, D] gradient flowing
+// along the residual connection (nullable); dx (fp32) and dx_lp (fp16, nullable) receive
+// LN'(dy) + dres.  Column sums are accumulated per lane over the warp's rows, reduced across
+// the CTA in shared memory and added to global memory with one atomic per column per CTA.
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x, int64_t ld_x,
+              const float* __restrict__ dres, int64_t ld_dres, const float* __restrict__ gamma,
+              const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+              float* __restrict__ dx, int64_t ld_dx, __half* __restrict__ dx_lp, int64_t ld_lp,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias_prev,
+              int rows, int D, FloatFmt q_in) {
+    extern __shared__ float red[];      // [kLnWarps][D] reused for the three column sums
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec = D >> 2;
+    float4 g[NV], acc_g[NV], acc_b[NV], acc_p[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const int c = lane + 32 * i;
+        if (c < nvec) g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        acc_g[i] = make_float4(0, 0, 0, 0); acc_b[i] = acc_g[i]; acc_p[i] = acc_g[i];
+    }
+    for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        const float4* xr = reinterpret_cast<const float4*>(x + int64_t(row) * ld_x);
+        const float4* dyr = reinterpret_cast<const float4*>(dy + int64_t(row) * ld_dy);
+        float4 xh[NV], gy[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                float4 xv = __ldcs(xr + c);
+                const float4 d = __ldcs(dyr + c);
+                xv.x = (fq_nearest(xv.x, q_in) - mean) * rstd; xv.y = (fq_nearest(xv.y, q_in) - mean) * rstd;
+                xv.z = (fq_nearest(xv.z, q_in) - mean) * rstd; xv.w = (fq_nearest(xv.w, q_in) - mean) * rstd;
+                xh[i] = xv;
+                acc_g[i].x += d.x * xv.x; acc_g[i].y += d.y * xv.y; acc_g[i].z += d.z * xv.z; acc_g[i].w += d.w * xv.w;
+                acc_b[i].x += d.x; acc_b[i].y += d.y; acc_b[i].z += d.z; acc_b[i].w += d.w;
+                gy[i] = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+                s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+                s2 += (gy[i].x * xv.x + gy[i].y * xv.y) + (gy[i].z * xv.z + gy[i].w * xv.w);
+            }
+        }
+        const float m1 = warp_sum(s1) / float(D), m2 = warp_sum(s2) / float(D);
+        float* dxr = dx + int64_t(row) * ld_dx;
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                float4 o;
+                o.x = rstd * (gy[i].x - m1 - xh[i].x * m2); o.y = rstd * (gy[i].y - m1 - xh[i].y * m2);
+                o.z = rstd * (gy[i].z - m1 - xh[i].z * m2); o.w = rstd * (gy[i].w - m1 - xh[i].w * m2);
+                if (dres != nullptr) {
+                    const float4 r = __ldcs(reinterpret_cast<const float4*>(dres + int64_t(row) * ld_dres) + c);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                acc_p[i].x += o.x; acc_p[i].y += o.y; acc_p[i].z += o.z; acc_p[i].w += o.w;
+                reinterpret_cast<float4*>(dxr)[c] = o;
+                if (dx_lp != nullptr) {
+                    __half2 lo = __floats2half2_rn(sat16(o.x), sat16(o.y)), hi = __floats2half2_rn(sat16(o.z), sat16(o.w));
+                    reinterpret_cast<uint2*>(dx_lp + int64_t(row) * ld_lp)[c] =
+                        make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                }
+            }
+        }
+    }
+    // CTA-level column reduction, one quantity at a time
+    for (int which = 0; which < 3; which++) {
+        float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias_prev);
+        if (dst == nullptr) continue;       // uniform across the CTA
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                const float4 a = which == 0 ? acc_g[i] : (which == 1 ? acc_b[i] : acc_p[i]);
+                reinterpret_cast<float4*>(red + warp * D)[c] = a;
+            }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < D; c += blockDim.x) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kLnWarps; w++) s += red[w * D + c];
+            atomicAdd(dst + c, s);
+        }
+    }
+}
+
+// out[c] += sum_r in[r, c]   (bias gradients of to_qkv / net.0 from their fp16 dY)
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ in, int64_t ld, int rows, int cols, float* __restrict__ out) {
+    // block: 32 column-pairs x 8 row lanes; each thread owns 2 adjacent columns
+    __shared__ float2 sm[8][33];
+    const int cp = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;
+    float2 acc = make_float2(0.f, 0.f);
+    if (2 * cp < cols) {
+        for (int r = blockIdx.y * 8 + ry; r < rows; r += gridDim.y * 8) {
+            if (sizeof(T) == 2) {
+                const __half2 v = *reinterpret_cast<const __half2*>(
+                    reinterpret_cast<const __half*>(in) + int64_t(r) * ld + 2 * cp);
+                const float2 f = __half22float2(v);
+                acc.x += f.x; acc.y += f.y;
+            } else {
+                const float2 f = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(in) + int64_t(r) * ld + 2 * cp);
+                acc.x += f.x; acc.y += f.y;
+            }
+        }
+    }
+    sm[ry][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (ry == 0 && 2 * cp < cols) {
+        float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { s.x += sm[j][threadIdx.x].x; s.y += sm[j][threadIdx.x].y; }
+        atomicAdd(out + 2 * cp, s.x);
+        atomicAdd(out + 2 * cp + 1, s.y);
+    }
+}
+
+// patchify + input quant:  img NCHW fp32 -> patches [B*gh*gw, p*p*C] with (ph, pw, c) minor
+// order (src/myrtle_vision/models/vit.py:271-275), each value through q_in, fp16/fp32 container.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, OutT* __restrict__ out, int B, int C, int H, int W,
+                int P, FloatFmt q_in) {
+    // one CTA per (b, patch row gy): reads C x P rows of W contiguous floats, coalesced
+    const int gw = W / P, gh = H / P;
+    const int b = blockIdx.x / gh, gy = blockIdx.x % gh;
+    const int pdim = P * P * C;
+    const int total = C * P * W;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int w = i % W;
+        const int ph = (i / W) % P;
+        const int c = i / (W * P);
+        const float v = fq_nearest(__ldcs(img + ((int64_t(b) * C + c) * H + gy * P + ph) * W + w), q_in);
+        const int gx = w / P, pw = w % P;
+        const int64_t o = (int64_t(b) * gh * gw + gy * gw + gx) * pdim + (ph * P + pw) * C + c;
+        if (sizeof(OutT) == 4) reinterpret_cast<float*>(out)[o] = v;
+        else reinterpret_cast<__half*>(out)[o] = __float2half_rn(v);
+    }
+}
+
+// scatter-add of the patch gradient back to NCHW is never needed (images need no grad).
+
+// cls rows: x[b, 0, :] = q_ff( q_ff(cls) + pos_q[0, :] )   (vit.py:283-310, FP16_16 quantises
+// the cat and the add; other formats pass q_ff = identity)
+__global__ void cls_row_kernel(const float* __restrict__ cls, const float* __restrict__ pos_q,
+                               float* __restrict__ x, int B, int n_tokens, int D, FloatFmt q_ff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * D) return;
+    const int b = i / D, d = i % D;
+    const float v = fq_nearest(fq_nearest(cls[d], q_ff) + pos_q[d], q_ff);
+    x[(int64_t(b) * n_tokens) * D + d] = v;
+}
+
+// fp32 -> bf16 / fp16 conversion (gradient operand copies)
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+convert_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t n4) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(in) + i);
+        uint2 u;
+        if (sizeof(OutT) == 2 && std::is_same<OutT, __nv_bfloat16>::value) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            u = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        } else {
+            __half2 lo = __floats2half2_rn(sat16(v.x), sat16(v.y)), hi = __floats2half2_rn(sat16(v.z), sat16(v.w));
+            u = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+        reinterpret_cast<uint2*>(out)[i] = u;
+    }
+}
+
+template <int NV>
+static int launch_ln_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, void* y,
+                         int64_t ld_y, int y_dtype, float* mean, float* rstd, int rows, int D,
+                         float eps, FloatFmt q_in, FloatFmt q_post, cudaStream_t st) {
+    int grid = (rows + kLnWarps - 1) / kLnWarps;
+    const int cap = kNumSMs * 8;
+    if (grid > cap) grid = cap;
+    if (y_dtype == MV_F16)
+        ln_fwd_kernel<NV, __half><<<grid, kLnWarps * 32, 0, st>>>(x, ld_x, gamma, beta, (__half*)y, ld_y, mean, rstd, rows, D, eps, q_in, q_post);
+    else
+        ln_fwd_kernel<NV, float><<<grid, kLnWarps * 32, 0, st>>>(x, ld_x, gamma, beta, (float*)y, ld_y, mean, rstd, rows, D, eps, q_in, q_post);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "ln fwd launch");
+}
+
+template <int NV>
+static int launch_ln_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* dres,
+                         int64_t ld_dres, const float* gamma, const float* mean, const float* rstd,
+                         float* dx, int64_t ld_dx, void* dx_lp, int64_t ld_lp, float* dgamma, float* dbeta,
+                         float* dbias_prev, int rows, int D, FloatFmt q_in, cudaStream_t st) {
+    int grid = (rows + kLnWarps - 1) / kLnWarps;
+    const int cap = kNumSMs * 4;
+    if (grid > cap) grid = cap;
+    const size_t smem = size_t(kLnWarps) * D * sizeof(float);
+    ln_bwd_kernel<NV><<<grid, kLnWarps * 32, smem, st>>>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx,
+                                                        (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "ln bwd launch");
+}
+
+}  // namespace mv
+
+using namespace mv;
+
+extern "C" int mv_layernorm_q_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta,
+                                  void* y, int64_t ld_y, int y_dtype, float* mean, float* rstd, int rows,
+                                  int D, float eps, int q_in_exp, int q_in_man, int q_post_exp,
+                                  int q_post_man, void* stream) {
+    MV_CHECK(rows >= 0 && D > 0 && D % 4 == 0 && D <= 128 * kLnMaxVec, "mv_layernorm_q_fwd: D=%d unsupported (multiple of 4, <= %d)", D, 128 * kLnMaxVec);
+    MV_CHECK(ld_x % 4 == 0 && ld_y % 4 == 0, "mv_layernorm_q_fwd: row pitches must be multiples of 4 elements");
+    MV_CHECK(y_dtype == MV_F16 || y_dtype == MV_F32, "mv_layernorm_q_fwd: bad output container");
+    if (rows == 0) return 0;
+    const FloatFmt qi{q_in_exp, q_in_man}, qp{q_post_exp, q_post_man};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nv = (D / 4 + 31) / 32;
+    switch (nv) {
+        case 1: return launch_ln_fwd<1>(x, ld_x, gamma, beta, y, ld_y, y_dtype, mean, rstd, rows, D, eps, qi, qp, st);
+        case 2: return launch_ln_fwd<2>(x, ld_x, gamma, beta, y, ld_y, y_dtype, mean, rstd, rows, D, eps, qi, qp, st);
+        case 3: return launch_ln_fwd<3>(x, ld_x, gamma, beta, y, ld_y, y_dtype, mean, rstd, rows, D, eps, qi, qp, st);
+        case 4: return launch_ln_fwd<4>(x, ld_x, gamma, beta, y, ld_y, y_dtype, mean, rstd, rows, D, eps, qi, qp, st);
+        case 5: case 6: return launch_ln_fwd<6>(x, ld_x, gamma, beta, y, ld_y, y_dtype, mean, rstd, rows, D, eps, qi, qp, st);
+        default: return launch_ln_fwd<8>(x, ld_x, gamma, beta, y, ld_y, y_dtype, mean, rstd, rows, D, eps, qi, qp, st);
+    }
+}
+
+extern "C" int mv_layernorm_q_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x,
+                                  const float* dres, int64_t ld_dres, const float* gamma, const float* mean,
+                                  const float* rstd, float* dx, int64_t ld_dx, void* dx_bf16, int64_t ld_lp,
+                                  float* dgamma, float* dbeta, float* dbias_prev, int rows, int D,
+                                  int q_in_exp, int q_in_man, void* stream) {
+    MV_CHECK(rows >= 0 && D > 0 && D % 4 == 0 && D <= 128 * kLnMaxVec, "mv_layernorm_q_bwd: D=%d unsupported", D);
+    MV_CHECK(ld_dy % 4 == 0 && ld_x % 4 == 0 && ld_dx % 4 == 0 && ld_dres % 4 == 0 && ld_lp % 4 == 0, "mv_layernorm_q_bwd: row pitches must be multiples of 4");
+    if (rows == 0) return 0;
+    const FloatFmt qi{q_in_exp, q_in_man};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nv = (D / 4 + 31) / 32;
+    switch (nv) {
+        case 1: return launch_ln_bwd<1>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        case 2: return launch_ln_bwd<2>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        case 3: return launch_ln_bwd<3>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        case 4: return launch_ln_bwd<4>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        case 5: case 6: return launch_ln_bwd<6>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        default: return launch_ln_bwd<8>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+    }
+}
+
+extern "C" int mv_colsum(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out, void* stream) {
+    MV_CHECK(rows >= 0 && cols > 0 && cols % 2 == 0 && ld % 2 == 0, "mv_colsum: cols/ld must be even");
+    if (rows == 0) return 0;
+    int gy = (rows + 8 * 64 - 1) / (8 * 64);
+    if (gy > 512) gy = 512;
+    if (gy < 1) gy = 1;
+    dim3 grid((cols / 2 + 31) / 32, gy);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (in_dtype == MV_F16) colsum_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, ld, rows, cols, out);
+    else if (in_dtype == MV_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)in, ld, rows, cols, out);
+    else MV_CHECK(false, "mv_colsum: dtype must be f16 or f32");
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "colsum launch");
+}
+
+extern "C" int mv_patchify_q(const float* img, void* out, int out_dtype, int B, int C, int H, int W, int P,
+                             int q_exp, int q_man, void* stream) {
+    MV_CHECK(B > 0 && C > 0 && P > 0 && H % P == 0 && W % P == 0, "mv_patchify_q: image dims must be divisible by the patch size");
+    const FloatFmt q{q_exp, q_man};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = B * (H / P);
+    if (out_dtype == MV_F16) patchify_kernel<__half><<<grid, 256, 0, st>>>(img, (__half*)out, B, C, H, W, P, q);
+    else if (out_dtype == MV_F32) patchify_kernel<float><<<grid, 256, 0, st>>>(img, (float*)out, B, C, H, W, P, q);
+    else MV_CHECK(false, "mv_patchify_q: bad container");
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "patchify launch");
+}
+
+extern "C" int mv_cls_rows(const float* cls, const float* pos_q, float* x, int B, int n_tokens, int D,
+                           int q_exp, int q_man, void* stream) {
+    const FloatFmt q{q_exp, q_man};
+    const int n = B * D;
+    cls_row_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(cls, pos_q, x, B, n_tokens, D, q);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "cls rows launch");
+}
+
+extern "C" int mv_convert_f32(const float* in, void* out, int out_dtype, int64_t n, void* stream) {
+    MV_CHECK(n % 4 == 0, "mv_convert_f32: n must be a multiple of 4");
+    if (n == 0) return 0;
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (out_dtype == MV_BF16) convert_kernel<__nv_bfloat16><<<int(blocks), 256, 0, st>>>(in, (__nv_bfloat16*)out, n4);
+    else if (out_dtype == MV_F16) convert_kernel<__half><<<int(blocks), 256, 0, st>>>(in, (__half*)out, n4);
+    else MV_CHECK(false, "mv_convert_f32: bad dtype");
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "convert launch");
+}

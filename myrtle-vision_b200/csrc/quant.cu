@@ -1,0 +1,339 @@
+// quant.cu — standalone fake-quantisation kernels (north-star kernel class (a)).
+// HBM-bound bit manipulation on float words: 128-bit coalesced accesses, 4 independent
+// vector loads in flight per thread, streaming cache policy, counter-based Philox RNG.
+// Algorithmic traffic: 8 B/element (fp32 -> fp32), 6 B/element (fp32 -> fp16 container).
+//
+// Replaces QPyTorch 0.3.0 quant_cuda.{float,fixed_point,block}_quantize_* as invoked from
+// src/myrtle_vision/utils/quantize.py:84 (reference), which moves >= 12 B/element
+// (zeros_like memset + scalar load + scalar store).
+#include "common.cuh"
+#include "quant_dev.cuh"
+#include "../../include/mv_b200.h"
+
+namespace mv {
+
+extern int64_t g_launches;
+
+constexpr int kQThreads = 256;
+constexpr int kQUnroll = 4;
+
+template <typename T> struct Vec4Store;
+template <> struct Vec4Store<float> {
+    static __device__ __forceinline__ void st(float* p, float4 v) {
+        __stcs(reinterpret_cast<float4*>(p), v);
+    }
+};
+template <> struct Vec4Store<__half> {
+    static __device__ __forceinline__ void st(__half* p, float4 v) {
+        __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        __stcs(reinterpret_cast<uint2*>(p), u);
+    }
+};
+template <typename T> __device__ __forceinline__ T cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
+
+struct FixedParams {
+    float scale_up, scale_down, t_min, t_max;
+    int clamp;
+};
+
+// MODE 0: float_quantize ; MODE 1: fixed_point_quantize
+template <int MODE, bool STOCH, typename OutT>
+__global__ void __launch_bounds__(kQThreads)
+quant_vec_kernel(const float* __restrict__ in, OutT* __restrict__ out, uint8_t* __restrict__ mask,
+                 int64_t n, int exp_bits, int man_bits, FixedParams fp, uint64_t seed,
+                 uint64_t offset) {
+    const int64_t n4 = n >> 2;
+    const int64_t stride = int64_t(gridDim.x) * kQThreads * kQUnroll;
+    for (int64_t base = int64_t(blockIdx.x) * kQThreads * kQUnroll + threadIdx.x; base < n4;
+         base += stride) {
+        float4 v[kQUnroll];
+#pragma unroll
+        for (int j = 0; j < kQUnroll; j++) {
+            const int64_t i = base + int64_t(j) * kQThreads;
+            if (i < n4) v[j] = __ldcs(reinterpret_cast<const float4*>(in) + i);
+        }
+#pragma unroll
+        for (int j = 0; j < kQUnroll; j++) {
+            const int64_t i = base + int64_t(j) * kQThreads;
+            if (i >= n4) continue;
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (STOCH) r = philox4x32_10(seed, uint64_t(i), offset);
+            float4 o;
+            if (MODE == 0) {
+                o.x = float_quantize_elem<STOCH>(v[j].x, r.x, exp_bits, man_bits);
+                o.y = float_quantize_elem<STOCH>(v[j].y, r.y, exp_bits, man_bits);
+                o.z = float_quantize_elem<STOCH>(v[j].z, r.z, exp_bits, man_bits);
+                o.w = float_quantize_elem<STOCH>(v[j].w, r.w, exp_bits, man_bits);
+            } else {
+                const bool cl = fp.clamp != 0 && mask == nullptr;
+                float4 u;
+                u.x = fixed_quantize_elem(v[j].x, STOCH ? bits_to_uniform(r.x) : 0.5f, fp.scale_up, fp.scale_down, fp.t_min, fp.t_max, cl);
+                u.y = fixed_quantize_elem(v[j].y, STOCH ? bits_to_uniform(r.y) : 0.5f, fp.scale_up, fp.scale_down, fp.t_min, fp.t_max, cl);
+                u.z = fixed_quantize_elem(v[j].z, STOCH ? bits_to_uniform(r.z) : 0.5f, fp.scale_up, fp.scale_down, fp.t_min, fp.t_max, cl);
+                u.w = fixed_quantize_elem(v[j].w, STOCH ? bits_to_uniform(r.w) : 0.5f, fp.scale_up, fp.scale_down, fp.t_min, fp.t_max, cl);
+                if (mask != nullptr) {
+                    uchar4 m;
+                    m.x = (u.x < fp.t_min || u.x > fp.t_max); m.y = (u.y < fp.t_min || u.y > fp.t_max);
+                    m.z = (u.z < fp.t_min || u.z > fp.t_max); m.w = (u.w < fp.t_min || u.w > fp.t_max);
+                    reinterpret_cast<uchar4*>(mask)[i] = m;
+                    u.x = fminf(fmaxf(u.x, fp.t_min), fp.t_max); u.y = fminf(fmaxf(u.y, fp.t_min), fp.t_max);
+                    u.z = fminf(fmaxf(u.z, fp.t_min), fp.t_max); u.w = fminf(fmaxf(u.w, fp.t_min), fp.t_max);
+                }
+                o = u;
+            }
+            Vec4Store<OutT>::st(out + 4 * i, o);
+        }
+    }
+}
+
+// scalar path: tails (n % 4) and unaligned buffers.  Element index i keeps its RNG word.
+template <int MODE, bool STOCH, typename OutT>
+__global__ void quant_scalar_kernel(const float* __restrict__ in, OutT* __restrict__ out,
+                                    uint8_t* __restrict__ mask, int64_t begin, int64_t n,
+                                    int exp_bits, int man_bits, FixedParams fp, uint64_t seed,
+                                    uint64_t offset) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = begin + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t r = 0;
+        if (STOCH) {
+            const uint4 w = philox4x32_10(seed, uint64_t(i >> 2), offset);
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+            r = ws[i & 3];
+        }
+        float o;
+        if (MODE == 0) {
+            o = float_quantize_elem<STOCH>(in[i], r, exp_bits, man_bits);
+        } else {
+            const bool cl = fp.clamp != 0 && mask == nullptr;
+            o = fixed_quantize_elem(in[i], STOCH ? bits_to_uniform(r) : 0.5f, fp.scale_up,
+                                    fp.scale_down, fp.t_min, fp.t_max, cl);
+            if (mask != nullptr) {
+                mask[i] = (o < fp.t_min || o > fp.t_max);
+                o = fminf(fmaxf(o, fp.t_min), fp.t_max);
+            }
+        }
+        out[i] = cvt_out<OutT>(o);
+    }
+}
+
+static inline int grid_for(int64_t work_items, int per_block) {
+    int64_t blocks = (work_items + per_block - 1) / per_block;
+    const int64_t cap = int64_t(kNumSMs) * 8;   // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return int(blocks);
+}
+
+template <int MODE, bool STOCH, typename OutT>
+static int launch_quant(const float* in, OutT* out, uint8_t* mask, int64_t n, int exp_bits,
+                        int man_bits, FixedParams fp, uint64_t seed, uint64_t offset,
+                        cudaStream_t st) {
+    if (n == 0) return 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(OutT)) == 0) &&
+                         (mask == nullptr || reinterpret_cast<uintptr_t>(mask) % 4 == 0);
+    int64_t done = 0;
+    if (aligned && n >= 4) {
+        const int64_t n4 = n >> 2;
+        quant_vec_kernel<MODE, STOCH, OutT><<<grid_for(n4, kQThreads * kQUnroll), kQThreads, 0, st>>>(
+            in, out, mask, n, exp_bits, man_bits, fp, seed, offset);
+        g_launches++;
+        done = n4 << 2;
+    }
+    if (done < n) {
+        quant_scalar_kernel<MODE, STOCH, OutT><<<grid_for(n - done, 256), 256, 0, st>>>(
+            in, out, mask, done, n, exp_bits, man_bits, fp, seed, offset);
+        g_launches++;
+    }
+    return check_cuda(cudaGetLastError(), "quant launch");
+}
+
+// ------------------------------------------------------------------ block quantize
+__global__ void absmax_whole_kernel(const float* __restrict__ in, int64_t n, uint32_t* __restrict__ mx) {
+    float m = 0.f;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        m = fmaxf(m, fabsf(in[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float sm[32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) atomicMax(mx, __float_as_uint(m));   // non-negative floats order as uints
+    }
+}
+// one block per (outer index u, dim index d) slab of `inner` contiguous elements
+__global__ void absmax_dim_kernel(const float* __restrict__ in, int64_t dsize, int64_t inner,
+                                  uint32_t* __restrict__ mx) {
+    const int64_t slab = blockIdx.x;
+    const int64_t d = slab % dsize;
+    const float* p = in + slab * inner;
+    float m = 0.f;
+    for (int64_t i = threadIdx.x; i < inner; i += blockDim.x) m = fmaxf(m, fabsf(p[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(mx + d, __float_as_uint(m));
+}
+// inner == 1 (dim is the last axis): threads across d (coalesced), loop over outer
+__global__ void absmax_lastdim_kernel(const float* __restrict__ in, int64_t outer, int64_t dsize,
+                                      uint32_t* __restrict__ mx) {
+    const int64_t d = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (d >= dsize) return;
+    float m = 0.f;
+    for (int64_t u = blockIdx.y; u < outer; u += gridDim.y) m = fmaxf(m, fabsf(in[u * dsize + d]));
+    atomicMax(mx + d, __float_as_uint(m));
+}
+template <bool STOCH>
+__global__ void block_quant_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                   const float* __restrict__ mx, int64_t n, int64_t dsize,
+                                   int64_t inner, int whole, int wl, uint64_t seed,
+                                   uint64_t offset) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float m = whole ? mx[0] : mx[(i / inner) % dsize];
+        uint32_t r = 0;
+        if (STOCH) {
+            const uint4 w = philox4x32_10(seed, uint64_t(i >> 2), offset);
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+            r = ws[i & 3];
+        }
+        out[i] = block_quantize_elem<STOCH>(in[i], m, r, wl);
+    }
+}
+
+__global__ void philox_dump_kernel(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint4 w = philox4x32_10(seed, uint64_t(i >> 2), offset);
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        out[i] = ws[i & 3];
+    }
+}
+
+// --------------------------------------------------------- weight quant (+ transpose)
+// 32x32 tiles through shared memory so both q(W) and q(W)^T are written coalesced.
+template <typename OutT>
+__global__ void quant_weight_kernel(const float* __restrict__ w, OutT* __restrict__ out,
+                                    OutT* __restrict__ out_t, int rows, int cols, int exp_bits,
+                                    int man_bits) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (r < rows && c < cols) {
+            v = w[int64_t(r) * cols + c];
+            if (exp_bits > 0) v = float_quantize_elem<false>(v, 0u, exp_bits, man_bits);
+            out[int64_t(r) * cols + c] = cvt_out<OutT>(v);
+        }
+        tile[j][threadIdx.x] = v;
+    }
+    if (out_t == nullptr) return;
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out_t[int64_t(c) * rows + r] = cvt_out<OutT>(tile[threadIdx.x][j]);
+    }
+}
+
+}  // namespace mv
+
+using namespace mv;
+
+extern "C" int mv_float_quantize(const float* in, void* out, int out_dtype, int64_t n, int exp_bits,
+                                 int man_bits, int rounding, uint64_t seed, uint64_t offset,
+                                 void* stream) {
+    MV_CHECK(n >= 0, "mv_float_quantize: negative n");
+    MV_CHECK(exp_bits >= 1 && exp_bits <= 8, "mv_float_quantize: exp_bits %d not in [1,8]", exp_bits);
+    MV_CHECK(man_bits >= 1 && man_bits <= 22, "mv_float_quantize: man_bits %d not in [1,22]", man_bits);
+    MV_CHECK(n == 0 || (in && out), "mv_float_quantize: null buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FixedParams fp{};
+    if (out_dtype == MV_F32) {
+        return rounding == MV_ROUND_STOCHASTIC
+                   ? launch_quant<0, true, float>(in, (float*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st)
+                   : launch_quant<0, false, float>(in, (float*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st);
+    }
+    MV_CHECK(out_dtype == MV_F16, "mv_float_quantize: unsupported out_dtype %d", out_dtype);
+    MV_CHECK(exp_bits <= 5 && man_bits <= 10,
+             "mv_float_quantize: (exp=%d, man=%d) is not exactly representable in an fp16 container",
+             exp_bits, man_bits);
+    return rounding == MV_ROUND_STOCHASTIC
+               ? launch_quant<0, true, __half>(in, (__half*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st)
+               : launch_quant<0, false, __half>(in, (__half*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st);
+}
+
+extern "C" int mv_fixed_point_quantize(const float* in, float* out, uint8_t* mask, int64_t n, int wl,
+                                       int fl, int clamp, int symmetric, int rounding,
+                                       uint64_t seed, uint64_t offset, void* stream) {
+    MV_CHECK(n >= 0, "mv_fixed_point_quantize: negative n");
+    MV_CHECK(wl >= 1 && wl <= 32 && fl >= -100 && fl <= 100, "mv_fixed_point_quantize: bad wl/fl %d/%d", wl, fl);
+    MV_CHECK(n == 0 || (in && out), "mv_fixed_point_quantize: null buffer");
+    FixedParams fp;
+    fp.scale_up = ldexpf(1.0f, fl);
+    fp.scale_down = ldexpf(1.0f, -fl);
+    fp.t_min = -ldexpf(1.0f, wl - fl - 1);
+    fp.t_max = -fp.t_min - ldexpf(1.0f, -fl);
+    if (symmetric) fp.t_min = fp.t_min + ldexpf(1.0f, -fl);
+    fp.clamp = clamp;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return rounding == MV_ROUND_STOCHASTIC
+               ? launch_quant<1, true, float>(in, out, mask, n, 0, 0, fp, seed, offset, st)
+               : launch_quant<1, false, float>(in, out, mask, n, 0, 0, fp, seed, offset, st);
+}
+
+extern "C" int mv_block_quantize(const float* in, float* out, float* workspace, int64_t outer,
+                                 int64_t dsize, int64_t inner, int whole_tensor, int wl,
+                                 int rounding, uint64_t seed, uint64_t offset, void* stream) {
+    const int64_t n = outer * dsize * inner;
+    MV_CHECK(n >= 0 && wl >= 1 && wl <= 22, "mv_block_quantize: bad arguments");
+    if (n == 0) return 0;
+    MV_CHECK(in && out && workspace, "mv_block_quantize: null buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t* mx = reinterpret_cast<uint32_t*>(workspace);
+    const int64_t nblk = whole_tensor ? 1 : dsize;
+    MV_CUDA(cudaMemsetAsync(mx, 0, sizeof(uint32_t) * nblk, st));
+    if (whole_tensor) {
+        absmax_whole_kernel<<<grid_for(n, 256 * 8), 256, 0, st>>>(in, n, mx);
+    } else if (inner == 1) {
+        dim3 grid((unsigned)((dsize + 255) / 256), (unsigned)(outer < 64 ? outer : 64));
+        absmax_lastdim_kernel<<<grid, 256, 0, st>>>(in, outer, dsize, mx);
+    } else {
+        MV_CHECK(outer * dsize < (int64_t(1) << 31), "mv_block_quantize: too many slabs");
+        absmax_dim_kernel<<<(unsigned)(outer * dsize), 128, 0, st>>>(in, dsize, inner, mx);
+    }
+    g_launches++;
+    if (rounding == MV_ROUND_STOCHASTIC)
+        block_quant_kernel<true><<<grid_for(n, 256 * 4), 256, 0, st>>>(in, out, workspace, n, dsize, inner, whole_tensor, wl, seed, offset);
+    else
+        block_quant_kernel<false><<<grid_for(n, 256 * 4), 256, 0, st>>>(in, out, workspace, n, dsize, inner, whole_tensor, wl, seed, offset);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "block quant launch");
+}
+
+extern "C" int mv_philox_bits(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+    if (n <= 0) return 0;
+    philox_dump_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, offset);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "philox dump launch");
+}
+
+extern "C" int mv_quantize_weight(const float* w, void* out, void* out_t, int out_dtype, int rows,
+                                  int cols, int exp_bits, int man_bits, void* stream) {
+    MV_CHECK(rows > 0 && cols > 0 && w && out, "mv_quantize_weight: bad arguments");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (out_dtype == MV_F16) {
+        MV_CHECK(exp_bits >= 1 && exp_bits <= 5 && man_bits <= 10, "mv_quantize_weight: format does not fit fp16");
+        quant_weight_kernel<__half><<<grid, block, 0, st>>>(w, (__half*)out, (__half*)out_t, rows, cols, exp_bits, man_bits);
+    } else {
+        MV_CHECK(out_dtype == MV_F32, "mv_quantize_weight: unsupported container");
+        quant_weight_kernel<float><<<grid, block, 0, st>>>(w, (float*)out, (float*)out_t, rows, cols, exp_bits, man_bits);
+    }
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "quant weight launch");
+}

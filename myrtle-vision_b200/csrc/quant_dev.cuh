@@ -1,0 +1,102 @@
+// quant_dev.cuh — per-element fake-quantisation arithmetic shared by the standalone kernels
+// and by the fused prologues/epilogues (GEMM, LayerNorm, GELU, attention).
+//
+// Bit-for-bit the algorithm of QPyTorch 0.3.0's float/fixed/block kernels that myrtle-vision
+// invokes at src/myrtle_vision/utils/quantize.py:84 (formats built at :47-72); the algorithm
+// is written down in SURVEY.md Appendix B and checked against oracle/quant_oracle.c.
+#pragma once
+#include <stdint.h>
+
+namespace mv {
+
+struct FloatFmt {
+    int exp_bits;   // 0 => identity
+    int man_bits;
+};
+
+__device__ __forceinline__ uint32_t round_bits_nearest(uint32_t t, int man_bits) {
+    const uint32_t mask = (1u << (23 - man_bits)) - 1u;
+    return (t + (1u << (22 - man_bits))) & ~mask;
+}
+__device__ __forceinline__ uint32_t round_bits_stochastic(uint32_t t, uint32_t r, int man_bits) {
+    const uint32_t mask = (1u << (23 - man_bits)) - 1u;
+    return (t + (r & mask)) & ~mask;
+}
+
+// float_quantize for one element.  kStochastic selects round_bitwise_stochastic with the
+// element's 32 random bits `r`.
+template <bool kStochastic>
+__device__ __forceinline__ float float_quantize_elem(float a, uint32_t r, int exp_bits,
+                                                     int man_bits) {
+    const uint32_t target = __float_as_uint(a);
+    const int target_exp = int((target << 1) >> 24) - 127;
+    const int min_exp = -((1 << (exp_bits - 1)) - 2);
+    if (target_exp < min_exp) {
+        // below the lowest normal binade: shift up to it, round there, shift back
+        const uint32_t shift_bits = (uint32_t(127 + min_exp) << 23) | (target & 0x80000000u);
+        const float shift = __uint_as_float(shift_bits);
+        const float val = __fadd_rn(a, shift);
+        const uint32_t vb = __float_as_uint(val);
+        const uint32_t qb =
+            kStochastic ? round_bits_stochastic(vb, r, man_bits) : round_bits_nearest(vb, man_bits);
+        return __fsub_rn(__uint_as_float(qb), shift);
+    }
+    uint32_t q = kStochastic ? round_bits_stochastic(target, r, man_bits)
+                             : round_bits_nearest(target, man_bits);
+    // clip_exponent: the top exponent code is not used for finite values -> saturate to +-max
+    const int e = int((q << 1) >> 24);
+    const int max_e = (1 << (exp_bits - 1)) - 1 + 127;
+    if (q != 0u && e > max_e) {
+        const uint32_t max_man = (0x007FFFFFu >> (23 - man_bits)) << (23 - man_bits);
+        q = (target & 0x80000000u) | (uint32_t(max_e) << 23) | max_man;
+    }
+    return __uint_as_float(q);
+}
+
+__device__ __forceinline__ float fq_nearest(float a, FloatFmt f) {
+    return f.exp_bits == 0 ? a : float_quantize_elem<false>(a, 0u, f.exp_bits, f.man_bits);
+}
+
+// fixed_point_quantize for one element: floor(a * 2^fl + r) * 2^-fl, then clamp.
+// Nearest passes r = 0.5 (QPyTorch's CUDA kernel: ties toward +inf).
+__device__ __forceinline__ float fixed_quantize_elem(float a, float r, float scale_up,
+                                                     float scale_down, float t_min, float t_max,
+                                                     bool clamp) {
+    float v = floorf(__fadd_rn(__fmul_rn(a, scale_up), r));
+    v = __fmul_rn(v, scale_down);
+    if (clamp) v = fminf(fmaxf(v, t_min), t_max);
+    return v;
+}
+
+// block_quantize for one element given the block's max |a|
+template <bool kStochastic>
+__device__ __forceinline__ float block_quantize_elem(float a, float max_entry, uint32_t r, int wl) {
+    const uint32_t max_exp = ((__float_as_uint(max_entry) << 1) >> 24) << 23;
+    const float base = __fmul_rn(6.0f, __uint_as_float(max_exp));
+    const float t = __fadd_rn(a, base);
+    const uint32_t tb = __float_as_uint(t);
+    const uint32_t qb = kStochastic ? round_bits_stochastic(tb, r, wl) : round_bits_nearest(tb, wl);
+    return __fsub_rn(__uint_as_float(qb), base);
+}
+
+// Philox4x32-10 counter RNG: element i consumes word (i & 3) of
+// philox(key = seed, counter = {lo(i>>2), hi(i>>2), lo(offset), hi(offset)}).
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr, uint64_t offset) {
+    uint32_t c0 = uint32_t(ctr), c1 = uint32_t(ctr >> 32), c2 = uint32_t(offset),
+             c3 = uint32_t(offset >> 32);
+    uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float bits_to_uniform(uint32_t b) {
+    return float(b >> 8) * (1.0f / 16777216.0f);
+}
+
+}  // namespace mv

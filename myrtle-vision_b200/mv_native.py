@@ -1,0 +1,314 @@
+"""ctypes binding of the C-ABI CUDA library (include/mv_b200.h).
+
+There is no CPU fallback: every wrapper requires CUDA tensors and raises if the library is
+missing or a call fails.  PyTorch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "csrc", "libmv_b200.so")
+_lib = None
+
+F32, F16, BF16 = 0, 1, 2
+ROUND_NEAREST, ROUND_STOCHASTIC = 0, 1
+EPI_NONE, EPI_GELU, EPI_DGELU, EPI_EMBED = 0, 1, 2, 3
+
+_DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+
+class MvError(RuntimeError):
+    pass
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("M", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int),
+        ("A", ctypes.c_void_p), ("lda", ctypes.c_int), ("a_dtype", ctypes.c_int), ("a_major", ctypes.c_int),
+        ("B", ctypes.c_void_p), ("ldb", ctypes.c_int), ("b_dtype", ctypes.c_int), ("b_major", ctypes.c_int),
+        ("bias", ctypes.c_void_p),
+        ("residual", ctypes.c_void_p), ("ld_res", ctypes.c_int),
+        ("aux", ctypes.c_void_p), ("ld_aux", ctypes.c_int),
+        ("out", ctypes.c_void_p), ("ld_out", ctypes.c_int), ("out_dtype", ctypes.c_int),
+        ("out2", ctypes.c_void_p), ("ld_out2", ctypes.c_int), ("out2_dtype", ctypes.c_int),
+        ("epilogue", ctypes.c_int),
+        ("q_out_exp", ctypes.c_int), ("q_out_man", ctypes.c_int),
+        ("q_res_exp", ctypes.c_int), ("q_res_man", ctypes.c_int),
+        ("accumulate", ctypes.c_int),
+        ("rows_per_img", ctypes.c_int),
+    ]
+
+
+def so_path():
+    return _SO
+
+
+def lib():
+    """Load libmv_b200.so (built in-tree by csrc/build.py).  Fails loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise MvError(
+                "CUDA extension %s is missing: run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (there is no CPU fallback)" % _SO)
+        _lib = ctypes.CDLL(_SO)
+        _lib.mv_last_error.restype = ctypes.c_char_p
+        _lib.mv_launch_count.restype = ctypes.c_int64
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise MvError("%s failed: %s" % (what, lib().mv_last_error().decode()))
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise MvError("myrtle-vision_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def launch_count():
+    return int(lib().mv_launch_count())
+
+
+# ------------------------------------------------------------------ fake-quant
+def float_quantize(x, exp, man, rounding="nearest", seed=0, offset=0, out=None,
+                   out_dtype=torch.float32):
+    _need_cuda(x)
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    rc = lib().mv_float_quantize(_ptr(x), _ptr(out), _DT[out.dtype], ctypes.c_int64(x.numel()),
+                                 int(exp), int(man),
+                                 ROUND_STOCHASTIC if rounding == "stochastic" else ROUND_NEAREST,
+                                 ctypes.c_uint64(seed), ctypes.c_uint64(offset), _stream())
+    _check(rc, "mv_float_quantize")
+    return out
+
+
+def fixed_point_quantize(x, wl, fl, clamp=True, symmetric=False, rounding="nearest", seed=0,
+                         offset=0, with_mask=False):
+    _need_cuda(x)
+    x = x.contiguous().float()
+    out = torch.empty_like(x)
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if with_mask else None
+    rc = lib().mv_fixed_point_quantize(_ptr(x), _ptr(out), _ptr(mask), ctypes.c_int64(x.numel()),
+                                       int(wl), int(fl), int(bool(clamp)), int(bool(symmetric)),
+                                       ROUND_STOCHASTIC if rounding == "stochastic" else ROUND_NEAREST,
+                                       ctypes.c_uint64(seed), ctypes.c_uint64(offset), _stream())
+    _check(rc, "mv_fixed_point_quantize")
+    return (out, mask) if with_mask else out
+
+
+def block_quantize(x, wl, dim=-1, rounding="nearest", seed=0, offset=0):
+    _need_cuda(x)
+    x = x.contiguous().float()
+    out = torch.empty_like(x)
+    if dim is None or dim < 0:
+        outer, dsize, inner, whole = 1, 1, x.numel(), 1
+    else:
+        shape = list(x.shape)
+        outer = 1
+        for s in shape[:dim]:
+            outer *= s
+        dsize = shape[dim]
+        inner = 1
+        for s in shape[dim + 1:]:
+            inner *= s
+        whole = 0
+    ws = torch.empty(max(dsize, 1), dtype=torch.float32, device=x.device)
+    rc = lib().mv_block_quantize(_ptr(x), _ptr(out), _ptr(ws), ctypes.c_int64(outer),
+                                 ctypes.c_int64(dsize), ctypes.c_int64(inner), whole, int(wl),
+                                 ROUND_STOCHASTIC if rounding == "stochastic" else ROUND_NEAREST,
+                                 ctypes.c_uint64(seed), ctypes.c_uint64(offset), _stream())
+    _check(rc, "mv_block_quantize")
+    return out
+
+
+def philox_bits(n, seed, offset=0, device="cuda"):
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    _check(lib().mv_philox_bits(_ptr(out), ctypes.c_int64(n), ctypes.c_uint64(seed),
+                                ctypes.c_uint64(offset), _stream()), "mv_philox_bits")
+    return out
+
+
+def quantize_weight(w, exp, man, out_dtype=torch.float16, transpose=True, out=None, out_t=None):
+    _need_cuda(w)
+    assert w.dim() == 2 and w.dtype == torch.float32 and w.is_contiguous()
+    rows, cols = w.shape
+    if out is None:
+        out = torch.empty(rows, cols, dtype=out_dtype, device=w.device)
+    if transpose and out_t is None:
+        out_t = torch.empty(cols, rows, dtype=out_dtype, device=w.device)
+    rc = lib().mv_quantize_weight(_ptr(w), _ptr(out), _ptr(out_t) if transpose else None,
+                                  _DT[out.dtype], rows, cols, int(exp), int(man), _stream())
+    _check(rc, "mv_quantize_weight")
+    return out, out_t
+
+
+# ------------------------------------------------------------------------ GEMM
+def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out2=None,
+         epilogue=EPI_NONE, q_out=None, q_res=None, accumulate=False, rows_per_img=0,
+         M=None, N=None, K=None):
+    """out[M,N] = A . B^T over K with the fused epilogue of mv_gemm (include/mv_b200.h).
+    a_major/b_major = 0: operand is [M|N, K] (K contiguous); 1: operand is [K, M|N]."""
+    _need_cuda(A, B, out)
+    assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1
+    if M is None:
+        M = A.shape[0] if a_major == 0 else A.shape[1]
+    if K is None:
+        K = A.shape[1] if a_major == 0 else A.shape[0]
+    if N is None:
+        N = B.shape[0] if b_major == 0 else B.shape[1]
+    a = GemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.A, a.lda, a.a_dtype, a.a_major = A.data_ptr(), A.stride(0), _DT[A.dtype], a_major
+    a.B, a.ldb, a.b_dtype, a.b_major = B.data_ptr(), B.stride(0), _DT[B.dtype], b_major
+    a.bias = bias.data_ptr() if bias is not None else None
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(-1) == 1
+        a.residual, a.ld_res = residual.data_ptr(), residual.stride(-2)
+    if aux is not None:
+        assert aux.dtype == torch.float16
+        a.aux, a.ld_aux = aux.data_ptr(), aux.stride(-2)
+    a.out, a.ld_out, a.out_dtype = out.data_ptr(), out.stride(-2), _DT[out.dtype]
+    if out2 is not None:
+        a.out2, a.ld_out2, a.out2_dtype = out2.data_ptr(), out2.stride(-2), _DT[out2.dtype]
+    a.epilogue = epilogue
+    if q_out:
+        a.q_out_exp, a.q_out_man = q_out
+    if q_res:
+        a.q_res_exp, a.q_res_man = q_res
+    a.accumulate = int(bool(accumulate))
+    a.rows_per_img = rows_per_img
+    _check(lib().mv_gemm(ctypes.byref(a), _stream()), "mv_gemm")
+    return out
+
+
+# ------------------------------------------------------------- LayerNorm & helpers
+def _fmt(f):
+    return (int(f[0]), int(f[1])) if f else (0, 0)
+
+
+def layernorm_q_fwd(x, gamma, beta, *, q_in=None, q_post=None, out_dtype=torch.float16, eps=1e-5,
+                    save_stats=True):
+    _need_cuda(x, gamma, beta)
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    assert x2.dtype == torch.float32 and x2.stride(1) == 1
+    rows = x2.shape[0]
+    y = torch.empty(rows, D, dtype=out_dtype, device=x.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    qi, qp = _fmt(q_in), _fmt(q_post)
+    rc = lib().mv_layernorm_q_fwd(_ptr(x2), ctypes.c_int64(x2.stride(0)), _ptr(gamma), _ptr(beta),
+                                  _ptr(y), ctypes.c_int64(D), _DT[out_dtype], _ptr(mean), _ptr(rstd),
+                                  rows, D, ctypes.c_float(eps), qi[0], qi[1], qp[0], qp[1], _stream())
+    _check(rc, "mv_layernorm_q_fwd")
+    return y.reshape(x.shape), mean, rstd
+
+
+def layernorm_q_bwd(dy, x, gamma, mean, rstd, *, dres=None, q_in=None, dgamma=None, dbeta=None,
+                    dbias_prev=None, want_f16=True, dx=None, dx_f16=None):
+    _need_cuda(dy, x)
+    D = x.shape[-1]
+    x2, dy2 = x.reshape(-1, D), dy.reshape(-1, D)
+    rows = x2.shape[0]
+    assert dy2.dtype == torch.float32 and x2.dtype == torch.float32
+    if dx is None:
+        dx = torch.empty(rows, D, dtype=torch.float32, device=x.device)
+    if want_f16 and dx_f16 is None:
+        dx_f16 = torch.empty(rows, D, dtype=torch.float16, device=x.device)
+    dres2 = dres.reshape(-1, D) if dres is not None else None
+    qi = _fmt(q_in)
+    rc = lib().mv_layernorm_q_bwd(_ptr(dy2), ctypes.c_int64(dy2.stride(0)), _ptr(x2),
+                                  ctypes.c_int64(x2.stride(0)), _ptr(dres2),
+                                  ctypes.c_int64(dres2.stride(0) if dres2 is not None else D),
+                                  _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx),
+                                  ctypes.c_int64(dx.stride(0)), _ptr(dx_f16), ctypes.c_int64(D),
+                                  _ptr(dgamma), _ptr(dbeta), _ptr(dbias_prev), rows, D, qi[0], qi[1],
+                                  _stream())
+    _check(rc, "mv_layernorm_q_bwd")
+    return dx, dx_f16
+
+
+def colsum(x2d, out):
+    _need_cuda(x2d, out)
+    assert x2d.dim() == 2 and x2d.stride(1) == 1 and out.dtype == torch.float32
+    rc = lib().mv_colsum(_ptr(x2d), _DT[x2d.dtype], ctypes.c_int64(x2d.stride(0)), x2d.shape[0],
+                         x2d.shape[1], _ptr(out), _stream())
+    _check(rc, "mv_colsum")
+    return out
+
+
+def patchify_q(img, patch, q_in=None, out_dtype=torch.float16):
+    _need_cuda(img)
+    img = img.contiguous().float()
+    B, C, H, W = img.shape
+    out = torch.empty(B * (H // patch) * (W // patch), patch * patch * C, dtype=out_dtype,
+                      device=img.device)
+    q = _fmt(q_in)
+    _check(lib().mv_patchify_q(_ptr(img), _ptr(out), _DT[out_dtype], B, C, H, W, patch, q[0], q[1],
+                               _stream()), "mv_patchify_q")
+    return out
+
+
+def cls_rows(cls, pos_q, x, B, n_tokens, D, q_ff=None):
+    q = _fmt(q_ff)
+    _check(lib().mv_cls_rows(_ptr(cls), _ptr(pos_q), _ptr(x), B, n_tokens, D, q[0], q[1], _stream()),
+           "mv_cls_rows")
+
+
+def convert_f32(x, out_dtype=torch.float16, out=None):
+    _need_cuda(x)
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    _check(lib().mv_convert_f32(_ptr(x), _ptr(out), _DT[out.dtype], ctypes.c_int64(x.numel()),
+                                _stream()), "mv_convert_f32")
+    return out
+
+
+# ------------------------------------------------------------------- attention
+def attention_fwd(qkv, B, H, N, *, scale=0.125, q_out=None, out_dtype=torch.float16, out=None,
+                  lse=None):
+    """qkv fp16 [B*N, 3*H*64] -> out [B*N, H*64] = q_out(softmax(q k^T * scale) v), lse [B,H,N]."""
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.float16 and qkv.is_contiguous() and qkv.shape == (B * N, 3 * H * 64)
+    if out is None:
+        out = torch.empty(B * N, H * 64, dtype=out_dtype, device=qkv.device)
+    if lse is None:
+        lse = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
+    q = _fmt(q_out)
+    rc = lib().mv_attention_fwd(_ptr(qkv), _ptr(out), _DT[out.dtype], _ptr(lse), B, H, N,
+                                ctypes.c_float(scale), q[0], q[1], _stream())
+    _check(rc, "mv_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, o, d_o, lse, B, H, N, *, scale=0.125, dqkv=None, delta=None):
+    """d_o fp16 [B*N, D] -> dqkv fp16 [B*N, 3D] (dq | dk | dv)."""
+    _need_cuda(qkv, o, d_o, lse)
+    assert qkv.dtype == torch.float16 and o.dtype == torch.float16 and d_o.dtype == torch.float16
+    assert o.is_contiguous() and d_o.is_contiguous() and qkv.is_contiguous()
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    if delta is None:
+        delta = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
+    rc = lib().mv_attention_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(delta), _ptr(dqkv), B,
+                                H, N, ctypes.c_float(scale), _stream())
+    _check(rc, "mv_attention_bwd")
+    return dqkv
