@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — train images/s of the quantised ViT fwd+bwd step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                          # the reference's CPU path
+
+Workload (BASELINE.json configs[1]): ViT-Small (D=384, L=12, h=6,
+M=1536, patch 16), classification, 45 classes, 256x256x3 synthetic RESISC45-shaped images,
+q_format FP16_32, batch 256 per GPU, random-init weights.  One step = zero_grad -> forward ->
+CrossEntropy -> backward (+ NCCL gradient all-reduce for N > 1), the span the reference times
+in classification/train.py:239-264.  Weak scaling: 256 images per GPU.
+
+Prints ONE JSON line (rank 0).  `value` has inputs resident in HBM; `e2e` copies every step's
+batch from pinned host memory and reads the loss back.  `roofline` describes the dominant kernel
+class of the step, timed with CUDA events inside the timed region; `cpu_baseline` times the
+oracle port of the reference (stock PyTorch CPU ops + the C restatement of QPyTorch quant_cpu)
+on a bounded sample on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "myrtle-vision_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+ARCH = dict(dim=384, depth=12, heads=6, mlp_dim=1536)
+IMAGE, PATCH, CLASSES = 256, 16, 45
+METRIC = "train images/sec, quantised ViT fwd+bwd"
+
+
+def flops_per_image(n_tokens, dim, depth, mlp, classes, patch_dim=768):
+    fwd = 2 * (n_tokens - 1) * patch_dim * dim + depth * (
+        2 * n_tokens * (3 * dim * dim + dim * dim + 2 * dim * mlp) + 4 * n_tokens * n_tokens * dim
+    ) + 2 * dim * classes
+    return 3 * fwd
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_port_throughput(batch, steps, warmup, q_format):
+    """The reference's CPU path restated (oracle/vit_oracle.py): img/s of zero_grad -> fwd -> CE ->
+    bwd on `batch` images per step, all host threads torch wants to use."""
+    import torch
+    from oracle import vit_oracle
+    torch.manual_seed(1234)
+    P = vit_oracle.init_params(decoder="classification", num_classes=CLASSES, seed=1234, **ARCH)
+    g = torch.Generator().manual_seed(1234)
+    img = torch.randn(batch, 3, IMAGE, IMAGE, generator=g).clamp(-1, 1)
+    tgt = torch.randint(0, CLASSES, (batch,), generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        vit_oracle.train_step(P, img, tgt, decoder="classification", heads=ARCH["heads"], q_format=q_format)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return batch / mean, mean * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 8
+    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 1))
+    ips, ms, threads = cpu_port_throughput(batch, steps, warmup, args.q_format)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (fake-quantised to fp16 values)", "data": "synthetic",
+        "config": {"workload": "ViT-Small cls 256x256 q_format=%s, CPU sample batch %d" % (args.q_format, batch)},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": "%d steps of batch %d (same model/input shape), host cores=%d" % (steps, batch, os.cpu_count())},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    import mv_native
+    from myrtle_vision.models.vit import ViT
+    from myrtle_vision.utils.parallel import DataParallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(1234)
+    model = ViT(decoder="classification", image_size=IMAGE, patch_size=PATCH, num_classes=CLASSES,
+                q_format=args.q_format, **ARCH).to(dev).train()
+    net = DataParallel(model) if world > 1 else model
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [(torch.randn(B, 3, IMAGE, IMAGE, generator=g).clamp(-1, 1).pin_memory(),
+             torch.randint(0, CLASSES, (B,), generator=g).pin_memory()) for _ in range(2)]
+    resident = [(a.to(dev), b.to(dev)) for a, b in host]
+
+    def step(img, y):
+        model.zero_grad(set_to_none=True)
+        loss = F.cross_entropy(net(img), y)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(args.warmup):
+        step(*resident[i % 2])
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    mv_native.enable_timing(rank == 0 and not args.no_kernel_timing)
+    barrier()
+    n0 = mv_native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(*resident[i % 2])
+    e1.record()
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = mv_native.launch_count() - n0
+    kern = mv_native.timing_summary()
+    mv_native.enable_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2 (e2e): every step copies its batch from pinned host memory (prefetched one
+    # step ahead on a copy stream) and reads the loss back to the host
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1])) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            bufs[s][0].copy_(host[s][0], non_blocking=True)
+            bufs[s][1].copy_(host[s][1], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    for s in range(2):
+        consumed[s].record()
+    barrier()
+    t_e2e0 = torch.cuda.Event(enable_timing=True); t_e2e1 = torch.cuda.Event(enable_timing=True)
+    t_e2e0.record()
+    prefetch(0)
+    loss_host = 0.0
+    for i in range(args.steps):
+        s = i % 2
+        if i + 1 < args.steps:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[s])
+        loss = step(*bufs[s])
+        consumed[s].record()
+        loss_host = loss.item()                       # device -> host read of the step result
+    t_e2e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t_e2e0.elapsed_time(t_e2e1) / args.steps)
+    h2d = B * 3 * IMAGE * IMAGE * 4 + B * 8
+    d2h = 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+        peaks = json.load(f) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    n_tok = (IMAGE // PATCH) ** 2 + 1
+    M, D, Mm, H, L = B * n_tok, ARCH["dim"], ARCH["mlp_dim"], ARCH["heads"], ARCH["depth"]
+    gemm_fwd_flops = 2.0 * M * (768 * D + L * (3 * D * D + D * D + 2 * D * Mm))
+    alg = {   # algorithmic work per STEP of each kernel class
+        "gemm_fwd": ("tensor", gemm_fwd_flops),
+        "gemm_dgrad": ("tensor", 2.0 * M * L * (3 * D * D + D * D + 2 * D * Mm)),
+        "gemm_wgrad": ("tensor", gemm_fwd_flops),
+        "attn_fwd": ("tensor", L * 4.0 * B * H * n_tok * n_tok * 64),
+        "attn_bwd": ("tensor", L * 10.0 * B * H * n_tok * n_tok * 64),
+        "ln_fwd": ("hbm", 2 * L * M * D * 6.0),
+        "ln_bwd": ("hbm", 2 * L * M * D * 18.0),
+        "colsum": ("hbm", L * M * (Mm + 3 * D) * 2.0),
+    }
+    breakdown, roofline = {}, None
+    if kern:
+        top = max(kern.items(), key=lambda kv: kv[1][1])[0]
+        for name, (cnt, tot) in sorted(kern.items(), key=lambda kv: -kv[1][1]):
+            breakdown[name] = {"launches_per_step": cnt / args.steps, "ms_per_step": tot / args.steps}
+        bound, work = alg[top]
+        per_launch = work / (kern[top][0] / args.steps)
+        avg_ms = kern[top][1] / kern[top][0]
+        if bound == "tensor":
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            ach = per_launch / avg_ms / 1e9
+            unit = "TFLOP/s"
+        else:
+            peak = peaks.get("hbm_gbs", 6650.0)
+            ach = per_launch / avg_ms / 1e6
+            unit = "GB/s"
+        roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+                    "frac": ach / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json (sustained)" if peaks else "fallback",
+                    "avg_launch_ms": avg_ms}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, ms_cpu, threads = cpu_port_throughput(8, 2, 1, args.q_format)
+        cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": "2 timed steps of batch 8, same model and image shape (%.0f ms/step), host cpu_count=%d"
+                         % (ms_cpu, os.cpu_count())}
+
+    value = world * B / ms_step * 1e3
+    fl = flops_per_image(n_tok, D, L, Mm, CLASSES)
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16 operands (exact fake-quant containers), f32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": "ViT-Small cls 256x256x3, 45 classes, q_format=%s, batch %d/GPU, fwd+CE+bwd%s"
+                               % (args.q_format, B, " + NCCL grad all-reduce" if world > 1 else ""),
+                   "global_batch": world * B, "parallelism": "dp%d" % world,
+                   "l2": "per-step working set (~11 GB of activations) >> 126 MB L2; two alternating input batches"},
+        "clocks": clocks,
+        "e2e": {"value": world * B / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "last_loss": loss_host},
+        "gpu_launches": launches,
+        "model_tflops": value * fl / 1e12,
+        "roofline": roofline,
+        "kernels": breakdown,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--q-format", default="FP16_32", choices=["FP16_32", "FP16_16"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

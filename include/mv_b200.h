@@ -84,8 +84,8 @@ int mv_quantize_weight(const float* w, void* out, void* out_t, int out_dtype, in
 #define MV_EPI_NONE 0
 #define MV_EPI_GELU 1   /* aux (fp16 [M, ld_aux]) receives u = q_out(acc+bias); out = q_res(gelu(u)) */
 #define MV_EPI_DGELU 2  /* acc *= gelu'(aux[m,n]) */
-#define MV_EPI_EMBED 3  /* patch embedding: out row = (m / rows_per_img) * (rows_per_img+1) + 1 + m % rows_per_img,
-                           residual indexed by [1 + m % rows_per_img, n] (the resized pos-embedding) */
+/* rows_per_img > 0 (any epilogue): the residual is indexed by [m % rows_per_img, n] — the resized
+ * positional embedding broadcast over the batch (models/vit.py:305-310). */
 
 typedef struct {
     int M, N, K;
@@ -100,7 +100,7 @@ typedef struct {
     int q_out_exp, q_out_man;     /* exp == 0: identity */
     int q_res_exp, q_res_man;
     int accumulate;               /* split-K atomic accumulation into fp32 `out` */
-    int rows_per_img;             /* MV_EPI_EMBED */
+    int rows_per_img;             /* residual row = m % rows_per_img when > 0 */
 } mv_gemm_args;
 
 int mv_gemm(const mv_gemm_args* args, void* stream);
@@ -123,9 +123,11 @@ int mv_layernorm_q_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t l
                        void* stream);
 /* out[c] += sum_r in[r,c]   (bias gradients); in_dtype MV_F16 or MV_F32 */
 int mv_colsum(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out, void* stream);
-/* img NCHW fp32 -> q(patches) [B*(H/P)*(W/P), P*P*C], (ph,pw,c) minor order (models/vit.py:271-275) */
+/* img NCHW fp32 -> q(patches) [B*(H/P)*(W/P), P*P*C], (ph,pw,c) minor order (models/vit.py:271-275).
+ * cls_slot != 0: each image gets one extra leading all-zero row (the class-token slot), so patch rows
+ * line up 1:1 with token rows [B*N, .] for the embedding GEMM and its wgrad. */
 int mv_patchify_q(const float* img, void* out, int out_dtype, int B, int C, int H, int W, int P,
-                  int q_exp, int q_man, void* stream);
+                  int q_exp, int q_man, int cls_slot, void* stream);
 /* x[b,0,:] = q(q(cls) + pos_q[0,:]) for every image b (models/vit.py:283-310) */
 int mv_cls_rows(const float* cls, const float* pos_q, float* x, int B, int n_tokens, int D, int q_exp,
                 int q_man, void* stream);

@@ -219,12 +219,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tc_fence_after();
             const int m = m0 + quad * 32 + lane;
             const bool row_ok = m < p.M;
-            int64_t orow = m, rrow = m;
-            if (p.epilogue == MV_EPI_EMBED) {
-                const int img = m / p.rows_per_img, pi = m % p.rows_per_img;
-                orow = int64_t(img) * (p.rows_per_img + 1) + 1 + pi;
-                rrow = 1 + pi;
-            }
+            const int64_t orow = m;
+            const int64_t rrow = p.rows_per_img > 0 ? (m % p.rows_per_img) : m;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; c++) {
                 uint32_t r[32];
@@ -344,7 +340,6 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     }
     if (a->accumulate) MV_CHECK(a->out_dtype == MV_F32, "mv_gemm: accumulate needs an fp32 output");
     if (a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU) MV_CHECK(a->aux != nullptr, "mv_gemm: GELU epilogues need aux");
-    if (a->epilogue == MV_EPI_EMBED) MV_CHECK(a->rows_per_img > 0, "mv_gemm: EMBED epilogue needs rows_per_img");
 
     CUtensorMap ta, tb;
     // K-major operand [rows = M|N, cols = K]: box = 128 rows x 128 B of K.

@@ -220,19 +220,26 @@ colsum_kernel(const T* __restrict__ in, int64_t ld, int rows, int cols, float* _
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, OutT* __restrict__ out, int B, int C, int H, int W,
-                int P, FloatFmt q_in) {
+                int P, FloatFmt q_in, int cls_slot) {
     // one CTA per (b, patch row gy): reads C x P rows of W contiguous floats, coalesced
     const int gw = W / P, gh = H / P;
     const int b = blockIdx.x / gh, gy = blockIdx.x % gh;
     const int pdim = P * P * C;
     const int total = C * P * W;
+    const int64_t rows_per_img = int64_t(gh) * gw + cls_slot;
+    if (cls_slot && gy == 0) {          // row b*N + 0 is the (zero) slot of the class token
+        for (int i = threadIdx.x; i < pdim; i += blockDim.x) {
+            if (sizeof(OutT) == 4) reinterpret_cast<float*>(out)[int64_t(b) * rows_per_img * pdim + i] = 0.f;
+            else reinterpret_cast<__half*>(out)[int64_t(b) * rows_per_img * pdim + i] = __float2half_rn(0.f);
+        }
+    }
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int w = i % W;
         const int ph = (i / W) % P;
         const int c = i / (W * P);
         const float v = fq_nearest(__ldcs(img + ((int64_t(b) * C + c) * H + gy * P + ph) * W + w), q_in);
         const int gx = w / P, pw = w % P;
-        const int64_t o = (int64_t(b) * gh * gw + gy * gw + gx) * pdim + (ph * P + pw) * C + c;
+        const int64_t o = (int64_t(b) * rows_per_img + cls_slot + gy * gw + gx) * pdim + (ph * P + pw) * C + c;
         if (sizeof(OutT) == 4) reinterpret_cast<float*>(out)[o] = v;
         else reinterpret_cast<__half*>(out)[o] = __float2half_rn(v);
     }
@@ -362,13 +369,13 @@ extern "C" int mv_colsum(const void* in, int in_dtype, int64_t ld, int rows, int
 }
 
 extern "C" int mv_patchify_q(const float* img, void* out, int out_dtype, int B, int C, int H, int W, int P,
-                             int q_exp, int q_man, void* stream) {
+                             int q_exp, int q_man, int cls_slot, void* stream) {
     MV_CHECK(B > 0 && C > 0 && P > 0 && H % P == 0 && W % P == 0, "mv_patchify_q: image dims must be divisible by the patch size");
     const FloatFmt q{q_exp, q_man};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = B * (H / P);
-    if (out_dtype == MV_F16) patchify_kernel<__half><<<grid, 256, 0, st>>>(img, (__half*)out, B, C, H, W, P, q);
-    else if (out_dtype == MV_F32) patchify_kernel<float><<<grid, 256, 0, st>>>(img, (float*)out, B, C, H, W, P, q);
+    if (out_dtype == MV_F16) patchify_kernel<__half><<<grid, 256, 0, st>>>(img, (__half*)out, B, C, H, W, P, q, cls_slot ? 1 : 0);
+    else if (out_dtype == MV_F32) patchify_kernel<float><<<grid, 256, 0, st>>>(img, (float*)out, B, C, H, W, P, q, cls_slot ? 1 : 0);
     else MV_CHECK(false, "mv_patchify_q: bad container");
     g_launches++;
     return check_cuda(cudaGetLastError(), "patchify launch");

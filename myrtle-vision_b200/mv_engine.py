@@ -1,0 +1,225 @@
+"""Fused sm_100a execution of the quantised ViT encoder (patch embedding + transformer blocks).
+
+Host-side orchestration only: every arithmetic step is a kernel of libmv_b200.so called through
+the C ABI (include/mv_b200.h).  Replaces the module-by-module execution of
+src/myrtle_vision/models/vit.py:267-314 (ViT.forward up to the decoder) and its autograd
+backward, with the fake-quantisers of SURVEY.md Appendix A folded into the neighbouring kernels:
+
+  forward, per block (H = the input/weight format, o = Linear/LN output format, f = FloatFunctional
+  format; o and f are identity except in FP16_16):
+    xn1  = H(LN(H(x)))                                   mv_layernorm_q_fwd      -> fp16
+    qkv  = o(xn1 . H(Wqkv)^T + b)                        mv_gemm                 -> fp16
+    att  = H(softmax(q k^T / 8) v)                       mv_attention_fwd        -> fp16
+    x1   = f(o(att . H(Wo)^T + b) + x)                   mv_gemm (+residual)     -> fp32
+    xn2  = H(LN(H(x1)))                                  mv_layernorm_q_fwd      -> fp16
+    u,h  = o(xn2 . H(W1)^T + b),  H(gelu(u))             mv_gemm (GELU epilogue) -> fp16, fp16
+    x2   = f(o(h . H(W2)^T + b) + x1)                    mv_gemm (+residual)     -> fp32
+  backward: straight-through quantisers (utils/quantize.py:87-89); dgrad / wgrad on the same GEMM
+  kernel (wgrad reads dY and X in place as MN-major operands, split-K red.add into a flat fp32
+  gradient buffer), GELU' in the dgrad epilogue, LN backward fused with the residual-gradient add,
+  the fp16 operand copy and the bias-gradient column sums.
+
+Gradients travel as fp16 tensor-core operands scaled by a power of two S chosen on the device from
+the incoming gradient (the reference itself trains under GradScaler(65536), classification/
+train.py:167); parameter gradients are un-scaled in fp32 before they are returned.
+"""
+import torch
+
+import mv_native as mv
+
+
+class EngineConfig:
+    def __init__(self, dim, heads, mlp_dim, depth, patch, plan):
+        self.dim, self.heads, self.mlp_dim, self.depth, self.patch, self.plan = (
+            dim, heads, mlp_dim, depth, patch, plan)
+
+
+PER_LAYER = 12   # ln1.w ln1.b qkv.w qkv.b out.w out.b ln2.w ln2.b fc1.w fc1.b fc2.w fc2.b
+
+
+class EncoderEngine:
+    def __init__(self, cfg, params):
+        """params: [pe.w, pe.b] + PER_LAYER tensors per block, all fp32 CUDA nn.Parameters."""
+        self.cfg = cfg
+        self.params = list(params)
+        assert len(self.params) == 2 + PER_LAYER * cfg.depth
+        plan = cfg.plan
+        if plan.inp != (5, 10):
+            raise NotImplementedError(
+                "the fused tcgen05 path currently covers the fp16-operand formats (FP16_32, "
+                "FP16_16); q_format with input format %r is not wired yet" % (plan.inp,))
+        if cfg.dim != cfg.heads * 64:
+            raise ValueError("dim must equal heads * 64 (dim_head is fixed at 64, models/vit.py:178)")
+        self.fmt = plan.inp
+        self.dev = self.params[0].device
+        self._wq = None
+        self._wq_versions = None
+        sizes = [p.numel() for p in self.params]
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + ((s + 3) // 4) * 4)
+        self.gflat = torch.zeros(self.offsets[-1], dtype=torch.float32, device=self.dev)
+        self.gviews = [self.gflat[self.offsets[i]:self.offsets[i] + sizes[i]].view_as(p)
+                       for i, p in enumerate(self.params)]
+        self.reducer = None      # set by parallel.DataParallel: called with flat gradient slices
+
+    # ------------------------------------------------------------------ weights
+    def _weight_indices(self):
+        idx = [0]
+        for l in range(self.cfg.depth):
+            base = 2 + PER_LAYER * l
+            idx += [base + 2, base + 4, base + 8, base + 10]
+        return idx
+
+    def quantised_weights(self):
+        """weight_fake_quant of every Linear (torch.nn.qat.Linear.forward re-quantises each step):
+        fp16 q(W) [out,in] for forward and q(W)^T [in,out] for dgrad; cached on parameter versions."""
+        idx = self._weight_indices()
+        versions = tuple(self.params[i]._version for i in idx) + tuple(
+            self.params[i].data_ptr() for i in idx)
+        if self._wq is not None and versions == self._wq_versions:
+            return self._wq
+        wq = {}
+        for i in idx:
+            w = self.params[i].detach()
+            old = self._wq.get(i) if self._wq else None
+            q, qt = mv.quantize_weight(w, self.fmt[0], self.fmt[1], out=old[0] if old else None,
+                                       out_t=old[1] if old else None)
+            wq[i] = (q, qt)
+        self._wq, self._wq_versions = wq, versions
+        return wq
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, img, pos_full, cls_token, save):
+        cfg, plan, fmt = self.cfg, self.cfg.plan, self.fmt
+        B, C, Hh, Ww = img.shape
+        P = cfg.patch
+        N = (Hh // P) * (Ww // P) + 1
+        M, D, Mm, H = B * N, cfg.dim, cfg.mlp_dim, cfg.heads
+        prm = [p.detach() for p in self.params]
+        wq = self.quantised_weights()
+        f16 = torch.float16
+        dev = img.device
+
+        patches = mv.patchify_q(img, P, q_in=fmt, cls_slot=True)            # [M, P*P*C], zero cls rows
+        x = torch.empty(M, D, dtype=torch.float32, device=dev)
+        pos32 = pos_full.detach().reshape(N, D).contiguous()
+        mv.gemm(patches, wq[0][0], x, bias=prm[1], q_out=plan.out, residual=pos32, q_res=plan.ff,
+                rows_per_img=N)
+        mv.cls_rows(cls_token.detach().reshape(D).contiguous(), pos32, x, B, N, D, q_ff=plan.ff)
+
+        saved = {"B": B, "N": N, "patches": patches, "layers": []} if save else None
+        for l in range(cfg.depth):
+            b0 = 2 + PER_LAYER * l
+            xn1, mean1, rstd1 = mv.layernorm_q_fwd(x, prm[b0], prm[b0 + 1], q_in=fmt, q_post=fmt)
+            qkv = torch.empty(M, 3 * D, dtype=f16, device=dev)
+            mv.gemm(xn1, wq[b0 + 2][0], qkv, bias=prm[b0 + 3], q_out=plan.out)
+            att, lse = mv.attention_fwd(qkv, B, H, N, scale=0.125, q_out=fmt)
+            x1 = torch.empty(M, D, dtype=torch.float32, device=dev)
+            mv.gemm(att, wq[b0 + 4][0], x1, bias=prm[b0 + 5], q_out=plan.out, residual=x,
+                    q_res=plan.ff)
+            xn2, mean2, rstd2 = mv.layernorm_q_fwd(x1, prm[b0 + 6], prm[b0 + 7], q_in=fmt, q_post=fmt)
+            u = torch.empty(M, Mm, dtype=f16, device=dev)
+            h = torch.empty(M, Mm, dtype=f16, device=dev)
+            mv.gemm(xn2, wq[b0 + 8][0], h, bias=prm[b0 + 9], q_out=plan.out, aux=u,
+                    epilogue=mv.EPI_GELU, q_res=fmt)
+            x2 = torch.empty(M, D, dtype=torch.float32, device=dev)
+            mv.gemm(h, wq[b0 + 10][0], x2, bias=prm[b0 + 11], q_out=plan.out, residual=x1,
+                    q_res=plan.ff)
+            if save:
+                saved["layers"].append((x, xn1, mean1, rstd1, qkv, att, lse, x1, xn2, mean2, rstd2, u, h))
+            x = x2
+        return x.view(B, N, D), saved
+
+    # ----------------------------------------------------------------- backward
+    def backward(self, saved, gx):
+        cfg, fmt = self.cfg, self.fmt
+        B, N = saved["B"], saved["N"]
+        M, D, Mm, H = B * N, cfg.dim, cfg.mlp_dim, cfg.heads
+        prm = [p.detach() for p in self.params]
+        wq = self.quantised_weights()
+        g = self.gviews
+        dev = gx.device
+        f16 = torch.float16
+
+        # power-of-two gradient scale chosen on the device (no host sync)
+        gx = gx.reshape(M, D)
+        amax = gx.abs().amax().clamp_min(1e-30)
+        S = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).clamp(2.0 ** -60, 2.0 ** 60)
+        dx = gx * S
+        dx_h = mv.convert_f32(dx, f16)
+        self.gflat.zero_()
+        last = cfg.depth - 1
+        mv.colsum(dx, g[2 + PER_LAYER * last + 11].view(-1))               # fc2 bias of the last block
+
+        for l in range(last, -1, -1):
+            b0 = 2 + PER_LAYER * l
+            x, xn1, mean1, rstd1, qkv, att, lse, x1, xn2, mean2, rstd2, u, h = saved["layers"][l]
+            # ---- FeedForward
+            du = torch.empty(M, Mm, dtype=f16, device=dev)
+            mv.gemm(dx_h, wq[b0 + 10][1], du, aux=u, epilogue=mv.EPI_DGELU)
+            mv.gemm(dx_h, h, g[b0 + 10], a_major=1, b_major=1, accumulate=True)
+            dxn2 = torch.empty(M, D, dtype=torch.float32, device=dev)
+            mv.gemm(du, wq[b0 + 8][1], dxn2, tag="dgrad")
+            mv.gemm(du, xn2, g[b0 + 8], a_major=1, b_major=1, accumulate=True)
+            mv.colsum(du, g[b0 + 9].view(-1))
+            del du
+            dx1, dx1_h = mv.layernorm_q_bwd(dxn2, x1, prm[b0 + 6], mean2, rstd2, dres=dx, q_in=fmt,
+                                            dgamma=g[b0 + 6], dbeta=g[b0 + 7], dbias_prev=g[b0 + 5])
+            # ---- Attention
+            datt = torch.empty(M, D, dtype=f16, device=dev)
+            mv.gemm(dx1_h, wq[b0 + 4][1], datt, tag="dgrad")
+            mv.gemm(dx1_h, att, g[b0 + 4], a_major=1, b_major=1, accumulate=True)
+            dqkv = mv.attention_bwd(qkv, att, datt, lse, B, H, N, scale=0.125)
+            dxn1 = dxn2      # reuse
+            mv.gemm(dqkv, wq[b0 + 2][1], dxn1, tag="dgrad")
+            mv.gemm(dqkv, xn1, g[b0 + 2], a_major=1, b_major=1, accumulate=True)
+            mv.colsum(dqkv, g[b0 + 3].view(-1))
+            prev_bias = g[b0 - 1] if l > 0 else None                       # fc2 bias of block l-1
+            dx, dx_h = mv.layernorm_q_bwd(dxn1, x, prm[b0], mean1, rstd1, dres=dx1, q_in=fmt,
+                                          dgamma=g[b0], dbeta=g[b0 + 1], dbias_prev=prev_bias,
+                                          dx=dx, dx_f16=dx_h)
+            if self.reducer is not None:
+                lo, hi = self.offsets[b0], self.offsets[b0 + PER_LAYER]
+                self.reducer.reduce_slice(self.gflat[lo:hi], 1.0 / S)
+        # ---- patch embedding: dW = dx^T patches (cls rows of `patches` are zero)
+        mv.gemm(dx_h, saved["patches"], g[0], a_major=1, b_major=1, accumulate=True)
+        dpos = torch.zeros(N * D, dtype=torch.float32, device=dev)
+        mv.colsum(dx.view(B, N * D), dpos)
+        dpos = dpos.view(1, N, D)
+        g[1].copy_(dpos[0, 1:].sum(0))                                     # bias: patch rows only
+        inv = 1.0 / S
+        if self.reducer is not None:
+            self.reducer.reduce_slice(self.gflat[:self.offsets[2]], inv)
+            self.reducer.wait()
+        else:
+            self.gflat.mul_(inv)
+        dpos = dpos * inv
+        dcls = dpos[:, 0:1, :].clone()
+        # hand autograd its own copy: self.gflat is reused (zeroed) by the next backward
+        out = self.gflat.clone()
+        grads = [out[self.offsets[i]:self.offsets[i] + p.numel()].view_as(p)
+                 for i, p in enumerate(self.params)]
+        return dpos, dcls, grads
+
+
+class EncoderFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, img, pos_full, cls_token, *params):
+        need = any(ctx.needs_input_grad)      # False under torch.no_grad() / eval without grads
+        with torch.no_grad():
+            x, saved = engine.forward(img, pos_full, cls_token, save=need)
+        ctx.engine, ctx.saved = engine, saved
+        return x
+
+    @staticmethod
+    def backward(ctx, gx):
+        engine, saved = ctx.engine, ctx.saved
+        if saved is None:
+            raise RuntimeError("backward through an encoder forward that ran without grad")
+        if engine.reducer is not None:
+            engine.reducer.queue_finalize()
+        with torch.no_grad():
+            dpos, dcls, g = engine.backward(saved, gx.contiguous())
+        ctx.saved = None
+        return (None, None, dpos, dcls) + tuple(g)

@@ -14,7 +14,7 @@ _lib = None
 
 F32, F16, BF16 = 0, 1, 2
 ROUND_NEAREST, ROUND_STOCHASTIC = 0, 1
-EPI_NONE, EPI_GELU, EPI_DGELU, EPI_EMBED = 0, 1, 2, 3
+EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
 
 _DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -62,6 +62,40 @@ def lib():
 def _check(rc, what):
     if rc != 0:
         raise MvError("%s failed: %s" % (what, lib().mv_last_error().decode()))
+
+
+# Optional per-kernel-class CUDA-event timing (bench.py's roofline leg).  Off by default.
+_TIMERS = None
+
+
+def enable_timing(on=True):
+    global _TIMERS
+    _TIMERS = {} if on else None
+
+
+def timing_summary():
+    """{class: (launches, total_ms)} — call after torch.cuda.synchronize()."""
+    out = {}
+    for name, evs in (_TIMERS or {}).items():
+        out[name] = (len(evs), sum(a.elapsed_time(b) for a, b in evs))
+    return out
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _TIMERS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _TIMERS is not None:
+            self.e1.record()
+            _TIMERS.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
 
 
 def _stream():
@@ -162,7 +196,7 @@ def quantize_weight(w, exp, man, out_dtype=torch.float16, transpose=True, out=No
 # ------------------------------------------------------------------------ GEMM
 def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out2=None,
          epilogue=EPI_NONE, q_out=None, q_res=None, accumulate=False, rows_per_img=0,
-         M=None, N=None, K=None):
+         M=None, N=None, K=None, tag=None):
     """out[M,N] = A . B^T over K with the fused epilogue of mv_gemm (include/mv_b200.h).
     a_major/b_major = 0: operand is [M|N, K] (K contiguous); 1: operand is [K, M|N]."""
     _need_cuda(A, B, out)
@@ -194,7 +228,10 @@ def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None,
         a.q_res_exp, a.q_res_man = q_res
     a.accumulate = int(bool(accumulate))
     a.rows_per_img = rows_per_img
-    _check(lib().mv_gemm(ctypes.byref(a), _stream()), "mv_gemm")
+    kind = "gemm_wgrad" if accumulate else ("gemm_dgrad" if epilogue == EPI_DGELU or tag == "dgrad"
+                                            else "gemm_fwd")
+    with _timed(kind):
+        _check(lib().mv_gemm(ctypes.byref(a), _stream()), "mv_gemm")
     return out
 
 
@@ -214,9 +251,10 @@ def layernorm_q_fwd(x, gamma, beta, *, q_in=None, q_post=None, out_dtype=torch.f
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     qi, qp = _fmt(q_in), _fmt(q_post)
-    rc = lib().mv_layernorm_q_fwd(_ptr(x2), ctypes.c_int64(x2.stride(0)), _ptr(gamma), _ptr(beta),
-                                  _ptr(y), ctypes.c_int64(D), _DT[out_dtype], _ptr(mean), _ptr(rstd),
-                                  rows, D, ctypes.c_float(eps), qi[0], qi[1], qp[0], qp[1], _stream())
+    with _timed("ln_fwd"):
+        rc = lib().mv_layernorm_q_fwd(_ptr(x2), ctypes.c_int64(x2.stride(0)), _ptr(gamma), _ptr(beta),
+                                      _ptr(y), ctypes.c_int64(D), _DT[out_dtype], _ptr(mean), _ptr(rstd),
+                                      rows, D, ctypes.c_float(eps), qi[0], qi[1], qp[0], qp[1], _stream())
     _check(rc, "mv_layernorm_q_fwd")
     return y.reshape(x.shape), mean, rstd
 
@@ -234,13 +272,14 @@ def layernorm_q_bwd(dy, x, gamma, mean, rstd, *, dres=None, q_in=None, dgamma=No
         dx_f16 = torch.empty(rows, D, dtype=torch.float16, device=x.device)
     dres2 = dres.reshape(-1, D) if dres is not None else None
     qi = _fmt(q_in)
-    rc = lib().mv_layernorm_q_bwd(_ptr(dy2), ctypes.c_int64(dy2.stride(0)), _ptr(x2),
-                                  ctypes.c_int64(x2.stride(0)), _ptr(dres2),
-                                  ctypes.c_int64(dres2.stride(0) if dres2 is not None else D),
-                                  _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx),
-                                  ctypes.c_int64(dx.stride(0)), _ptr(dx_f16), ctypes.c_int64(D),
-                                  _ptr(dgamma), _ptr(dbeta), _ptr(dbias_prev), rows, D, qi[0], qi[1],
-                                  _stream())
+    with _timed("ln_bwd"):
+        rc = lib().mv_layernorm_q_bwd(_ptr(dy2), ctypes.c_int64(dy2.stride(0)), _ptr(x2),
+                                      ctypes.c_int64(x2.stride(0)), _ptr(dres2),
+                                      ctypes.c_int64(dres2.stride(0) if dres2 is not None else D),
+                                      _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx),
+                                      ctypes.c_int64(dx.stride(0)), _ptr(dx_f16), ctypes.c_int64(D),
+                                      _ptr(dgamma), _ptr(dbeta), _ptr(dbias_prev), rows, D, qi[0], qi[1],
+                                      _stream())
     _check(rc, "mv_layernorm_q_bwd")
     return dx, dx_f16
 
@@ -248,21 +287,22 @@ def layernorm_q_bwd(dy, x, gamma, mean, rstd, *, dres=None, q_in=None, dgamma=No
 def colsum(x2d, out):
     _need_cuda(x2d, out)
     assert x2d.dim() == 2 and x2d.stride(1) == 1 and out.dtype == torch.float32
-    rc = lib().mv_colsum(_ptr(x2d), _DT[x2d.dtype], ctypes.c_int64(x2d.stride(0)), x2d.shape[0],
-                         x2d.shape[1], _ptr(out), _stream())
+    with _timed("colsum"):
+        rc = lib().mv_colsum(_ptr(x2d), _DT[x2d.dtype], ctypes.c_int64(x2d.stride(0)), x2d.shape[0],
+                             x2d.shape[1], _ptr(out), _stream())
     _check(rc, "mv_colsum")
     return out
 
 
-def patchify_q(img, patch, q_in=None, out_dtype=torch.float16):
+def patchify_q(img, patch, q_in=None, out_dtype=torch.float16, cls_slot=False):
     _need_cuda(img)
     img = img.contiguous().float()
     B, C, H, W = img.shape
-    out = torch.empty(B * (H // patch) * (W // patch), patch * patch * C, dtype=out_dtype,
-                      device=img.device)
+    rows = B * ((H // patch) * (W // patch) + (1 if cls_slot else 0))
+    out = torch.empty(rows, patch * patch * C, dtype=out_dtype, device=img.device)
     q = _fmt(q_in)
     _check(lib().mv_patchify_q(_ptr(img), _ptr(out), _DT[out_dtype], B, C, H, W, patch, q[0], q[1],
-                               _stream()), "mv_patchify_q")
+                               int(bool(cls_slot)), _stream()), "mv_patchify_q")
     return out
 
 
@@ -293,8 +333,9 @@ def attention_fwd(qkv, B, H, N, *, scale=0.125, q_out=None, out_dtype=torch.floa
     if lse is None:
         lse = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
     q = _fmt(q_out)
-    rc = lib().mv_attention_fwd(_ptr(qkv), _ptr(out), _DT[out.dtype], _ptr(lse), B, H, N,
-                                ctypes.c_float(scale), q[0], q[1], _stream())
+    with _timed("attn_fwd"):
+        rc = lib().mv_attention_fwd(_ptr(qkv), _ptr(out), _DT[out.dtype], _ptr(lse), B, H, N,
+                                    ctypes.c_float(scale), q[0], q[1], _stream())
     _check(rc, "mv_attention_fwd")
     return out, lse
 
@@ -308,7 +349,8 @@ def attention_bwd(qkv, o, d_o, lse, B, H, N, *, scale=0.125, dqkv=None, delta=No
         dqkv = torch.empty_like(qkv)
     if delta is None:
         delta = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
-    rc = lib().mv_attention_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(delta), _ptr(dqkv), B,
-                                H, N, ctypes.c_float(scale), _stream())
+    with _timed("attn_bwd"):
+        rc = lib().mv_attention_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(delta), _ptr(dqkv), B,
+                                    H, N, ctypes.c_float(scale), _stream())
     _check(rc, "mv_attention_bwd")
     return dqkv

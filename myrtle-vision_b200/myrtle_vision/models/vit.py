@@ -1,0 +1,257 @@
+"""B200-native Vision Transformer with myrtle-vision's constructor and outputs.
+
+Drop-in for src/myrtle_vision/models/vit.py of the reference: `ViT(decoder=..., image_size=...,
+patch_size=..., num_classes=..., dim=..., depth=..., heads=..., mlp_dim=..., q_format=...)`,
+`.forward(img[B,3,H,W])`, `.convert()`, `.quantizer.prepare_qat(...)`; identical parameter names,
+shapes, initial values for a given torch seed, and state_dict keys per q_format.
+
+The modules below only *hold parameters* under the reference's names.  forward() does not call
+them: the patch embedding and the transformer blocks run as fused sm_100a kernels through
+mv_engine.EncoderFunction (C ABI: include/mv_b200.h), and only the tiny decoder heads, the
+positional-embedding resize and the loss stay in PyTorch.  There is no CPU execution path.
+"""
+from typing import Optional, Union
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+import mv_engine
+import mv_native
+from myrtle_vision.utils.quantize import ModelQuantizer, QFormat
+
+MIN_NUM_PATCHES = 16
+
+
+class Residual(nn.Module):
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
+class PreNorm(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, hidden_dim, dropout=0.0):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
+                                 nn.Linear(hidden_dim, dim), nn.Dropout(dropout))
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0.0):
+        super().__init__()
+        inner_dim = dim_head * heads
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=True)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout))
+
+
+class Transformer(nn.Module):
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        for _ in range(depth):
+            # construction order (Attention, LayerNorm, FeedForward, LayerNorm) fixes the RNG
+            # stream so that a torch seed yields the reference's initial weights
+            attn = Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout)
+            first = Residual(PreNorm(dim, attn))
+            ff = FeedForward(dim, mlp_dim, dropout=dropout)
+            second = Residual(PreNorm(dim, ff))
+            self.layers.append(nn.Sequential(first, second))
+
+
+class ClassificationDecoder(nn.Module):
+    def __init__(self, dim, num_classes):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.linear = nn.Linear(dim, num_classes)
+
+
+class SegmentationDecoder(nn.Module):
+    def __init__(self, dim, num_classes, image_size, patch_size):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.linear = nn.Linear(dim, num_classes)
+        self.upsample = nn.Upsample(size=image_size, mode="bilinear")
+        self.image_size_in_patches = image_size // patch_size
+
+
+class DetectionDecoder(nn.Module):
+    def __init__(self, in_dim, num_classes, num_det_tokens):
+        super().__init__()
+        self.class_embed = nn.Linear(in_dim, num_classes + 1)   # +1 for no-class
+        self.bbox_embed = nn.Linear(in_dim, 4)
+        self.num_det_tokens = num_det_tokens
+
+
+class _STEQuant(torch.autograd.Function):
+    """float_quantize (nearest) on the GPU with a straight-through backward."""
+
+    @staticmethod
+    def forward(ctx, x, exp, man):
+        return mv_native.float_quantize(x.detach(), exp, man).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None
+
+
+def _fq(x, fmt):
+    return x if fmt is None else _STEQuant.apply(x, fmt[0], fmt[1])
+
+
+def _unwrap(module):
+    """The parameter-holding module behind an optional Sequential(QuantStubSlot, module)."""
+    if isinstance(module, nn.Sequential) and len(module) == 2 and not isinstance(
+            module[1], (nn.Dropout,)):
+        return module[1]
+    return module
+
+
+class ViT(nn.Module):
+    def __init__(
+        self,
+        *,
+        decoder: str,
+        image_size: int,
+        patch_size: int,
+        num_classes: int,
+        dim: int,
+        depth: int,
+        heads: int,
+        mlp_dim: int,
+        pool: str = "cls",
+        channels: int = 3,
+        dim_head: int = 64,
+        dropout: float = 0.0,
+        emb_dropout: float = 0.0,
+        num_det_tokens: int = 100,
+        profile: bool = False,
+        q_format: Optional[Union[str, QFormat]] = None,
+    ):
+        super().__init__()
+        assert image_size % patch_size == 0, "Image dimensions must be divisible by the patch size."
+        num_patches = (image_size // patch_size) ** 2
+        patch_dim = channels * patch_size ** 2
+        assert num_patches > MIN_NUM_PATCHES, (
+            f"your number of patches ({num_patches}) is way too small for attention to be "
+            f"effective (at least 16). Try decreasing your patch size")
+        assert decoder in {"classification", "segmentation", "detection"}, \
+            "decoder must be either classification, segmentation, or detection"
+        self.patch_size = patch_size
+        self.task = decoder
+        self.profile = profile
+        self.heads, self.dim, self.mlp_dim, self.depth = heads, dim, mlp_dim, depth
+        self.dim_head = dim_head
+        self.dropout_p, self.emb_dropout_p = dropout, emb_dropout
+
+        # the positional embedding is stored at 14x14 and resized on the fly (vit.py:216-218)
+        self.pos_embedding = nn.Parameter(torch.randn(1, 14 * 14 + 1, dim))
+        self.pos_embedding_det = nn.Parameter(torch.randn(1, num_det_tokens, dim))
+        self.patch_to_embedding = nn.Linear(patch_dim, dim)
+        self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.det_tokens = nn.Parameter(torch.randn(1, num_det_tokens, dim))
+        self.dropout = nn.Dropout(emb_dropout)
+        self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout)
+        if decoder == "classification":
+            self.decoder = ClassificationDecoder(dim, num_classes)
+        elif decoder == "segmentation":
+            self.decoder = SegmentationDecoder(dim, num_classes, image_size, patch_size)
+        else:
+            self.decoder = DetectionDecoder(dim, num_classes, num_det_tokens)
+
+        self._engine = None
+        self.quantizer = ModelQuantizer(self)
+        self.quantizer.prepare_qat(q_format if q_format is not None else QFormat.FP32)
+
+    # ------------------------------------------------------------------ plumbing
+    def _invalidate_engine(self):
+        self._engine = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._engine = None              # parameters may move (.to / .cuda / .half)
+        return super()._apply(fn, *args, **kwargs)
+
+    def _engine_params(self):
+        pe = _unwrap(self.patch_to_embedding)
+        params = [pe.weight, pe.bias]
+        for block in self.transformer.layers:
+            pre1, pre2 = block[0].fn, block[1].fn
+            ln1, ln2 = _unwrap(pre1.norm), _unwrap(pre2.norm)
+            qkv = _unwrap(pre1.fn.to_qkv)
+            out = _unwrap(pre1.fn.to_out[0])
+            fc1, fc2 = _unwrap(pre2.fn.net[0]), _unwrap(pre2.fn.net[3])
+            params += [ln1.weight, ln1.bias, qkv.weight, qkv.bias, out.weight, out.bias,
+                       ln2.weight, ln2.bias, fc1.weight, fc1.bias, fc2.weight, fc2.bias]
+        return params
+
+    def engine(self):
+        if self._engine is None:
+            cfg = mv_engine.EngineConfig(self.dim, self.heads, self.mlp_dim, self.depth,
+                                         self.patch_size, self.quantizer.plan)
+            self._engine = mv_engine.EncoderEngine(cfg, self._engine_params())
+        return self._engine
+
+    # ------------------------------------------------------------------- forward
+    def _pos_full(self, gh, gw):
+        """cls position + bicubic resize of the 14x14 grid (vit.py:292-302); FP16_16 quantises
+        the concatenation (FloatFunctional output)."""
+        ff = self.quantizer.plan.ff
+        pos_cls, pos = self.pos_embedding[:, 0:1, :], self.pos_embedding[:, 1:, :]
+        pos = pos.transpose(1, 2).view(1, -1, 14, 14)
+        pos = F.interpolate(pos, size=(gh, gw), mode="bicubic", align_corners=False)
+        pos = pos.view(1, -1, gh * gw).transpose(1, 2)
+        return _fq(torch.cat((pos_cls, pos), dim=1), ff)
+
+    def _linear(self, holder, x):
+        plan = self.quantizer.plan
+        lin = _unwrap(holder)
+        y = F.linear(_fq(x, plan.inp), _fq(lin.weight, plan.inp), lin.bias)
+        return _fq(y, plan.out)
+
+    def _norm(self, holder, x):
+        plan = self.quantizer.plan
+        ln = _unwrap(holder)
+        y = F.layer_norm(_fq(x, plan.inp), ln.normalized_shape, ln.weight, ln.bias, ln.eps)
+        return _fq(y, plan.out)
+
+    def _decode(self, x, img_hw):
+        dec = self.decoder
+        if self.task == "classification":                               # vit.py:335-342
+            return self._linear(dec.linear, self._norm(dec.norm, x[:, 0]))
+        if self.task == "segmentation":                                 # vit.py:359-374
+            y = self._linear(dec.linear, self._norm(dec.norm, x[:, 1:]))
+            b, hw, c = y.size()
+            y = y.transpose(1, 2).reshape(b, c, dec.image_size_in_patches, dec.image_size_in_patches)
+            return dec.upsample(y)
+        # detection (vit.py:389-396).  The reference's `self.decoder == "detection"` test is
+        # always False (the attribute holds a Module), so det tokens never enter the sequence and
+        # the heads read the last num_det_tokens *patch* tokens; reproduced here for parity.
+        t = x[:, -dec.num_det_tokens:, :]
+        return {"pred_logits": self._linear(dec.class_embed, t),
+                "pred_boxes": self._linear(dec.bbox_embed, t).sigmoid()}
+
+    def forward(self, img: torch.Tensor):
+        if not img.is_cuda:
+            raise RuntimeError("myrtle-vision_b200 runs on CUDA (sm_100a) only; there is no CPU "
+                               "fallback — move the model and the batch to a B200")
+        if self.training and (self.dropout_p > 0 or self.emb_dropout_p > 0):
+            raise NotImplementedError("dropout > 0 is not supported by the fused path "
+                                      "(all shipped configs use 0.0)")
+        b, c, h, w = img.shape
+        p = self.patch_size
+        engine = self.engine()
+        pos_full = self._pos_full(h // p, w // p)
+        x = mv_engine.EncoderFunction.apply(engine, img, pos_full, self.cls_token,
+                                            *engine.params)
+        return self._decode(x, (h, w))
+
+    def convert(self) -> None:
+        self.quantizer.convert()

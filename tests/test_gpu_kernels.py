@@ -1,0 +1,147 @@
+"""Floating-point kernels (tcgen05 GEMM + epilogues, LayerNorm, attention) vs a torch fp64
+reference of the same op on the same inputs.  Tolerances are written at each assert."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def relmax(a, b):
+    return ((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 45, 384), (1000, 384, 1536),
+                                   (2501 * 2, 1152, 384)])
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (1, 1), (1, 0), (0, 1)])
+def test_gemm_layouts(M, N, K, a_major, b_major):
+    import mv_native as mv
+    if (a_major and M % 8) or (b_major and N % 8):
+        pytest.skip("MN-major operands need a 16-byte row pitch")
+    torch.manual_seed(0)
+    A = torch.randn((K, M) if a_major else (M, K), device=dev).half()
+    B = torch.randn((K, N) if b_major else (N, K), device=dev).half()
+    out = torch.full((M, N), float("nan"), device=dev)
+    mv.gemm(A, B, out, a_major=a_major, b_major=b_major)
+    Af = A.double().t() if a_major else A.double()
+    Bf = B.double().t() if b_major else B.double()
+    # exact products, fp32 accumulation: 1e-5 of the largest entry
+    assert relmax(out, Af @ Bf.t()) < 1e-5
+
+
+def test_gemm_tf32_kmajor():
+    import mv_native as mv
+    torch.manual_seed(0)
+    A = torch.randn(256, 256, device=dev); B = torch.randn(128, 256, device=dev)
+    out = torch.empty(256, 128, device=dev)
+    mv.gemm(A, B, out)
+    assert relmax(out, A.double() @ B.double().t()) < 2e-3        # tf32 operand truncation
+
+
+def test_gemm_splitk_accumulate_and_epilogues():
+    import mv_native as mv
+    torch.manual_seed(1)
+    T, No, Ki = 8192, 384, 1536
+    dY = torch.randn(T, No, device=dev).half(); X = torch.randn(T, Ki, device=dev).half()
+    out = torch.zeros(No, Ki, device=dev)
+    mv.gemm(dY, X, out, a_major=1, b_major=1, accumulate=True)
+    assert relmax(out, dY.double().t() @ X.double()) < 1e-5
+    M, N, K = 514, 384, 384
+    A = torch.randn(M, K, device=dev).half(); B = (torch.randn(N, K, device=dev) * 0.05).half()
+    bias = torch.randn(N, device=dev); res = torch.randn(M, N, device=dev)
+    lin = A.double() @ B.double().t() + bias.double()
+    out = torch.empty(M, N, device=dev)
+    mv.gemm(A, B, out, bias=bias, residual=res)
+    assert relmax(out, lin + res.double()) < 1e-5
+    # q_out: quantise in the epilogue == standalone quant of the fp32 result (up to fp32 sum order)
+    outq = torch.empty(M, N, device=dev, dtype=torch.float16)
+    mv.gemm(A, B, outq, bias=bias, q_out=(5, 10))
+    want = mv.float_quantize(lin.float(), 5, 10)
+    assert ((outq.float() - want).abs() > 0).float().mean().item() < 2e-3      # rare 1-ulp flips only
+    assert relmax(outq, want) < 1e-3
+    u = torch.empty(M, N, device=dev, dtype=torch.float16); h = torch.empty_like(u)
+    mv.gemm(A, B, h, bias=bias, aux=u, epilogue=mv.EPI_GELU, q_res=(5, 10))
+    assert relmax(u, lin) < 1e-3 and relmax(h, F.gelu(lin)) < 1e-3
+    # DGELU epilogue: out = (A B^T) * gelu'(u)
+    d = torch.empty(M, N, device=dev, dtype=torch.float16)
+    mv.gemm(A, B, d, aux=u, epilogue=mv.EPI_DGELU)
+    uu = u.double().requires_grad_(True)
+    F.gelu(uu).sum().backward()
+    assert relmax(d, (A.double() @ B.double().t()) * uu.grad) < 2e-3
+    # residual broadcast over images (positional embedding)
+    pos = torch.randn(257, N, device=dev)
+    A2 = torch.randn(2 * 257, K, device=dev).half()
+    o2 = torch.empty(2 * 257, N, device=dev)
+    mv.gemm(A2, B, o2, bias=bias, residual=pos, rows_per_img=257)
+    assert relmax(o2, A2.double() @ B.double().t() + bias.double() + pos.double().repeat(2, 1)) < 1e-5
+
+
+def test_gemm_rejects_mixed_operand_types():
+    import mv_native as mv
+    A = torch.zeros(128, 64, device=dev).half(); B = torch.zeros(128, 64, device=dev).bfloat16()
+    with pytest.raises(mv.MvError, match="share one element type"):
+        mv.gemm(A, B, torch.empty(128, 128, device=dev))
+
+
+@pytest.mark.parametrize("D", [128, 192, 384, 768])
+def test_layernorm_q(D):
+    import mv_native as mv
+    torch.manual_seed(D)
+    rows = 1000
+    x = torch.randn(rows, D, device=dev) * 3
+    g = 1 + 0.1 * torch.randn(D, device=dev); b = 0.1 * torch.randn(D, device=dev)
+    y, mean, rstd = mv.layernorm_q_fwd(x, g, b, q_in=(5, 10), q_post=(5, 10))
+    xq = mv.float_quantize(x, 5, 10)
+    ref = mv.float_quantize(F.layer_norm(xq.double(), (D,), g.double(), b.double(), 1e-5).float(), 5, 10)
+    assert (y.float() - ref).abs().max().item() <= 2 ** -9 * ref.abs().max().item()   # <= 1 fp16 ulp
+    assert ((y.float() != ref).float().mean().item()) < 2e-3
+    y32, _, _ = mv.layernorm_q_fwd(x, g, b, out_dtype=torch.float32)
+    assert (y32 - F.layer_norm(x.double(), (D,), g.double(), b.double(), 1e-5).float()).abs().max() < 5e-6
+    dy = torch.randn(rows, D, device=dev); dres = torch.randn(rows, D, device=dev)
+    xr = xq.double().requires_grad_(True); gr = g.double().requires_grad_(True); br = b.double().requires_grad_(True)
+    F.layer_norm(xr, (D,), gr, br, 1e-5).backward(dy.double())
+    dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev); dp = torch.zeros(D, device=dev)
+    dx, dx16 = mv.layernorm_q_bwd(dy, x, g, mean, rstd, dres=dres, q_in=(5, 10), dgamma=dg, dbeta=db,
+                                  dbias_prev=dp)
+    want = xr.grad + dres.double()
+    assert relmax(dx, want) < 1e-6 and relmax(dx16, want) < 1e-3
+    assert relmax(dg, gr.grad) < 1e-5 and relmax(db, br.grad) < 1e-5 and relmax(dp, want.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,N", [(1, 1, 64), (1, 1, 128), (2, 2, 257), (2, 3, 197), (1, 2, 1000)])
+def test_attention_fwd_bwd(B, H, N):
+    import mv_native as mv
+    torch.manual_seed(N)
+    D = H * 64
+    qkv = torch.randn(B * N, 3 * D, device=dev).half()
+    out, lse = mv.attention_fwd(qkv, B, H, N)
+    x = qkv.double().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    q, k, v = [t.clone().requires_grad_(True) for t in (x[0], x[1], x[2])]
+    s = (q @ k.transpose(-2, -1)) * 0.125
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, D)
+    # fp16 probabilities on the tensor core: 2e-3 of the largest output
+    assert relmax(out, o) < 2e-3
+    assert (lse.double() - torch.logsumexp(s, -1) * 1.4426950408889634).abs().max() < 1e-3
+    do = torch.randn(B * N, D, device=dev).half()
+    o.backward(do.double())
+    dqkv = mv.attention_bwd(qkv, out, do, lse, B, H, N)
+    gq = dqkv.double().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    for got, ref in zip(gq, (q.grad, k.grad, v.grad)):
+        assert relmax(got, ref) < 3e-3
+    # quantised output variant is exactly the quantisation of the plain one (same accumulators)
+    outq, _ = mv.attention_fwd(qkv, B, H, N, q_out=(5, 10))
+    assert relmax(outq, o) < 2e-3
+
+
+def test_patchify_and_colsum():
+    import mv_native as mv
+    img = torch.randn(4, 3, 64, 96, device=dev)
+    pt = mv.patchify_q(img, 16, q_in=(5, 10))
+    ref = img.reshape(4, 3, 4, 16, 6, 16).permute(0, 2, 4, 3, 5, 1).reshape(4 * 24, 768).contiguous()
+    assert torch.equal(pt.float(), mv.float_quantize(ref, 5, 10))
+    pc = mv.patchify_q(img, 16, q_in=(5, 10), cls_slot=True).reshape(4, 25, 768)
+    assert torch.equal(pc[:, 1:].reshape(-1, 768), pt) and pc[:, 0].abs().max() == 0
+    a = torch.randn(8000, 1152, device=dev).half(); o = torch.zeros(1152, device=dev)
+    mv.colsum(a, o)
+    assert relmax(o, a.double().sum(0)) < 1e-5

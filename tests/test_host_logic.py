@@ -1,0 +1,126 @@
+"""Host-side mirror of the reference interface: constructors, quantisation config, state_dict
+keys, batch-size solver, config schema."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle.golden_cases import GOLD
+
+
+def make(decoder="classification", fmt="FP16_32", **kw):
+    from myrtle_vision.models.vit import ViT
+    args = dict(decoder=decoder, image_size=176 if decoder == "detection" else 80, patch_size=16,
+                num_classes=5, dim=128, depth=2, heads=2, mlp_dim=256, q_format=fmt)
+    args.update(kw)
+    return ViT(**args)
+
+
+@pytest.mark.parametrize("decoder", ["classification", "segmentation", "detection"])
+@pytest.mark.parametrize("fmt", ["FP32", "FP16_32", "TF32", "FP16_16"])
+def test_state_dict_keys_equal_the_reference(decoder, fmt):
+    with open(os.path.join(GOLD, "state_dict_keys.json")) as f:
+        keys = json.load(f)
+    assert list(make(decoder, fmt).state_dict().keys()) == keys["%s/%s" % (decoder, fmt)]
+
+
+def test_qformat_enum_and_errors():
+    from myrtle_vision.utils.quantize import ModelQuantizer, QFormat
+    assert [f.name for f in QFormat] == ["FP32", "PyTorchINT8", "FP16_16", "FP16_32", "TF32"]
+    assert int(QFormat.FP16_32) == 3
+    m = make(fmt="FP16_32")
+    with pytest.raises(ValueError, match="model already quantized"):
+        m.quantizer.prepare_qat("FP16_16")
+    m = make(fmt=None)                      # FP32 may be re-prepared, like the reference
+    m.quantizer.prepare_qat("FP16_32")
+    assert "patch_to_embedding.1.weight" in m.state_dict()
+    with pytest.raises(KeyError):
+        make(fmt="FP8")
+    with pytest.raises(NotImplementedError):
+        make(fmt="PyTorchINT8")
+
+
+def test_constructor_asserts():
+    with pytest.raises(AssertionError, match="divisible by the patch size"):
+        make(image_size=81)
+    with pytest.raises(AssertionError, match="way too small"):
+        make(image_size=64)
+    with pytest.raises(AssertionError, match="decoder must be"):
+        make(decoder="pose")
+
+
+def test_cpu_forward_fails_loudly():
+    with pytest.raises(RuntimeError, match="no CPU"):
+        make()(torch.zeros(1, 3, 80, 80))
+
+
+def test_engine_parameter_order_and_shapes():
+    m = make(fmt="FP16_16")
+    p = m._engine_params()
+    assert len(p) == 2 + 12 * 2
+    assert p[0].shape == (128, 768) and p[1].shape == (128,)
+    assert p[2 + 2].shape == (384, 128) and p[2 + 8].shape == (256, 128) and p[2 + 10].shape == (128, 256)
+    names = {id(v): k for k, v in m.named_parameters()}
+    assert names[id(p[2 + 12 + 4])] == "transformer.layers.1.0.fn.fn.to_out.0.1.weight"
+    # parameters that the reference leaves without gradient exist but are not engine-owned
+    assert "det_tokens" in dict(m.named_parameters())
+
+
+def test_same_seed_same_init_as_constructor_order():
+    torch.manual_seed(7)
+    a = make(fmt="FP32")
+    torch.manual_seed(7)
+    b = make(fmt="FP16_16")
+    from oracle.vit_oracle import canonical_key
+    sa = a.state_dict()
+    for k, v in b.state_dict().items():
+        assert torch.equal(v, sa[canonical_key(k)])
+
+
+def test_get_batch_sizes():
+    from myrtle_vision.utils.utils import get_batch_sizes
+    assert get_batch_sizes(32, 2, 64) == (32, 1)            # shipped vit_small.json point
+    assert get_batch_sizes(256, 8, 2048) == (256, 1)        # BASELINE config 3
+    assert get_batch_sizes(32, 1, 128) == (32, 4)
+    assert get_batch_sizes(32, 0, 64) == (32, 2)            # CPU: num_gpus == 0
+    assert get_batch_sizes(32, 4, 120) == (30, 1)           # best divisor below the target
+    assert get_batch_sizes(32, 4, 200) == (25, 2)
+    with pytest.raises(ValueError, match="not divisible by the number of GPUs"):
+        get_batch_sizes(32, 3, 64)
+
+
+def test_get_models_reads_the_reference_json_schema(tmp_path):
+    from myrtle_vision.utils.models import get_models
+    from myrtle_vision.utils.utils import parse_config
+    data = tmp_path / "data_config.json"
+    data.write_text(json.dumps({"number_of_classes": 45}))
+    cfg = {
+        "train_config": {"local_batch_size": 32, "global_batch_size": 64, "seed": 1234},
+        "data_config_path": str(data),
+        "dist_config": {"dist_backend": "nccl", "dist_url": "tcp://localhost:54321"},
+        "vit_config": {"decoder": "classification", "image_size": 224, "patch_size": 16,
+                       "embed_dim": 192, "depth": 2, "heads": 3, "mlp_dim": 768, "dropout": 0.0,
+                       "emb_dropout": 0.0, "q_format": "FP16_32"},
+    }
+    path = tmp_path / "train.json"
+    path.write_text(json.dumps(cfg))
+    vit, distiller = get_models(parse_config(str(path)))
+    assert distiller is None
+    assert vit.decoder.linear[1].weight.shape == (45, 192)
+    assert vit.quantizer.q_format.name == "FP16_32"
+
+
+def test_qtorch_facade_surface():
+    import qtorch
+    import qtorch.quant as qq
+    assert repr(qtorch.FloatingPoint(5, 10)) == "FloatingPoint (exponent=5, mantissa=10)"
+    with pytest.raises(AssertionError):
+        qtorch.FloatingPoint(9, 10)
+    for name in ("float_quantize", "fixed_point_quantize", "block_quantize", "quantizer", "Quantizer"):
+        assert hasattr(qq, name)
+    with pytest.raises(AssertionError, match="invalid rounding"):
+        qq.quantizer(forward_rounding="up")
+    import mv_native
+    with pytest.raises(mv_native.MvError, match="CUDA tensors"):
+        qq.float_quantize(torch.zeros(4), 5, 10, "nearest")
