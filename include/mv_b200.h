@@ -82,8 +82,8 @@ int mv_quantize_weight(const float* w, void* out, void* out_t, int out_dtype, in
  *   accumulate != 0: out (fp32) += acc with red.global.add (split-K wgrad); bias/residual/q ignored.
  */
 #define MV_EPI_NONE 0
-#define MV_EPI_GELU 1   /* aux (fp16 [M, ld_aux]) receives u = q_out(acc+bias); out = q_res(gelu(u)) */
-#define MV_EPI_DGELU 2  /* acc *= gelu'(aux[m,n]) */
+#define MV_EPI_GELU 1   /* u = q_out(acc+bias); out = q_res(gelu(u)); aux (fp16 [M, ld_aux]) receives gelu'(u) */
+#define MV_EPI_DGELU 2  /* acc *= aux[m,n]  (the gelu'(u) saved by the forward) */
 /* rows_per_img > 0 (any epilogue): the residual is indexed by [m % rows_per_img, n] — the resized
  * positional embedding broadcast over the batch (models/vit.py:305-310). */
 
@@ -101,6 +101,7 @@ typedef struct {
     int q_res_exp, q_res_man;
     int accumulate;               /* split-K atomic accumulation into fp32 `out` */
     int rows_per_img;             /* residual row = m % rows_per_img when > 0 */
+    int tile_n;                   /* 0 = auto; 128 forces 128-wide tiles (testing) */
 } mv_gemm_args;
 
 int mv_gemm(const mv_gemm_args* args, void* stream);

@@ -20,12 +20,15 @@ namespace mv {
 extern int64_t g_launches;
 
 constexpr int BM = 128;
-constexpr int BN = 128;
-constexpr int kStages = 6;
-constexpr int kTileBytes = BM * 128;                  // one operand tile per stage: 16 KB
-constexpr int kStageBytes = 2 * kTileBytes;
-constexpr int kGemmThreads = 192;
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kATileBytes = BM * 128;                 // A tile per stage: 128 rows x 128 B = 16 KB
+constexpr int kEpiWarps = 16;                         // four warps per TMEM lane quadrant
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+template <int BN> struct GemmCfg {
+    static constexpr int kBTileBytes = BN * 128;
+    static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+    static constexpr int kStages = BN == 128 ? 6 : 4;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 struct GemmDev {
     int M, N, K;
@@ -43,13 +46,12 @@ struct GemmDev {
     int rows_per_img;
 };
 
-__device__ __forceinline__ float gelu_exact(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
-__device__ __forceinline__ float gelu_grad(float x) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+// erf-GELU (nn.GELU default, models/vit.py:49) and its derivative from one erf evaluation
+__device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+    const float cdf = 0.5f + 0.5f * erff(x * 0.70710678118654752440f);
     const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    g = x * cdf;
+    dg = cdf + x * pdf;
 }
 
 template <typename T> __device__ __forceinline__ void store_row32(T* dst, const float (&v)[32]);
@@ -102,10 +104,13 @@ __device__ __forceinline__ void store_out(void* base, int dtype, int64_t row, in
 }
 
 // kEsz: operand element size (2: f16/bf16, kind::f16; 4: tf32-in-fp32, kind::tf32)
-template <int kEsz>
+template <int BN, int kEsz>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmDev p) {
+    constexpr int kStages = GemmCfg<BN>::kStages;
+    constexpr int kStageBytes = GemmCfg<BN>::kStageBytes;
+    constexpr int kTileBytes = kATileBytes;
     constexpr int BK = 128 / kEsz;             // elements of K per stage (one 128-byte swizzle row)
     constexpr int UMMA_K = 32 / kEsz;          // K elements per tcgen05.mma
     constexpr int kMnChunk = 128 / kEsz;       // MN elements per 128-byte row (MN-major tiles)
@@ -126,7 +131,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
@@ -160,7 +165,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                             tma_load_2d(sa + c * kMnBoxBytes, &tmap_a, &full_bar[stage], m0 + c * kMnChunk, kb * BK);
                     }
                     if (p.b_major == 0) {
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+#pragma unroll
+                        for (int c = 0; c < BN / 128; c++)
+                            tma_load_2d(sb + c * kATileBytes, &tmap_b, &full_bar[stage], kb * BK, n0 + c * 128);
                     } else {
 #pragma unroll
                         for (int c = 0; c < BN / kMnChunk; c++)
@@ -209,24 +216,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
     } else {
         // ================================ epilogue ====================================
-        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        // 16 warps: warp e covers TMEM lane quadrant (warp & 3) and column group (e >> 2) of the tile.
+        // Each epilogue warp is latency-bound (dependent math on one element set), so the step's
+        // elementwise work is spread over 4 warps per scheduler.
+        const int quad = warp & 3;
+        const int cgrp = (warp - 2) >> 2;
+        constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+        const int mode_out = fq_mode(p.q_out), mode_res = fq_mode(p.q_res);
         int acc = 0; uint32_t acc_phase = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-            const int split = u % p.splits;
             const int tile = u / p.splits;
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int m = m0 + quad * 32 + lane;
             const bool row_ok = m < p.M;
-            const int64_t orow = m;
             const int64_t rrow = p.rows_per_img > 0 ? (m % p.rows_per_img) : m;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
+            for (int c = 0; c < kColsPerWarp / 32; c++) {
+                const int col = cgrp * kColsPerWarp + c * 32;
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32, r);
+                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + col, r);
                 tmem_ld_wait();
-                const int n = n0 + c * 32;
+                const int n = n0 + col;
                 if (!row_ok || n >= p.N) continue;
                 const int nvalid = min(32, p.N - n);
                 float v[32];
@@ -234,9 +246,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
                 if (p.accumulate) {
                     float* o = reinterpret_cast<float*>(p.out) + int64_t(m) * p.ld_out + n;
-                    if (split == 0 && p.bias != nullptr) {
-                        // (bias only makes sense for non-split use; kept for completeness)
-                    }
 #pragma unroll
                     for (int j = 0; j < 32; j++) if (j < nvalid) atomicAdd(o + j, v[j]);
                     continue;
@@ -253,16 +262,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         for (int j = 0; j < 32; j++) if (j < nvalid) v[j] += __ldg(p.bias + n + j);
                     }
                 }
-                if (p.q_out.exp_bits) {
+                if (mode_out) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = float_quantize_elem<false>(v[j], 0u, p.q_out.exp_bits, p.q_out.man_bits);
+                    for (int j = 0; j < 32; j++) v[j] = fq_apply(v[j], mode_out, p.q_out);
                 }
                 if (p.epilogue == MV_EPI_GELU) {
-                    __half* up = p.aux + int64_t(m) * p.ld_aux + n;
-                    if (full && (p.ld_aux & 7) == 0) store_row32<__half>(up, v);
-                    else for (int j = 0; j < 32; j++) if (j < nvalid) up[j] = __float2half_rn(v[j]);
+                    // out = gelu(u); aux = gelu'(u) (all the backward needs)
+                    float d[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = gelu_exact(v[j]);
+                    for (int j = 0; j < 32; j++) gelu_both(v[j], v[j], d[j]);
+                    __half* up = p.aux + int64_t(m) * p.ld_aux + n;
+                    if (full && (p.ld_aux & 7) == 0) store_row32<__half>(up, d);
+                    else for (int j = 0; j < 32; j++) if (j < nvalid) up[j] = __float2half_rn(d[j]);
                 } else if (p.epilogue == MV_EPI_DGELU) {
                     const __half* up = p.aux + int64_t(m) * p.ld_aux + n;
                     if (full && (p.ld_aux & 7) == 0) {
@@ -273,12 +284,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
                                 const float2 f = __half22float2(h[q]);
-                                v[8 * j + 2 * q] *= gelu_grad(f.x);
-                                v[8 * j + 2 * q + 1] *= gelu_grad(f.y);
+                                v[8 * j + 2 * q] *= f.x;
+                                v[8 * j + 2 * q + 1] *= f.y;
                             }
                         }
                     } else {
-                        for (int j = 0; j < 32; j++) if (j < nvalid) v[j] *= gelu_grad(__half2float(up[j]));
+                        for (int j = 0; j < 32; j++) if (j < nvalid) v[j] *= __half2float(up[j]);
                     }
                 }
                 if (p.residual != nullptr) {
@@ -293,17 +304,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         for (int j = 0; j < 32; j++) if (j < nvalid) v[j] += rp[j];
                     }
                 }
-                if (p.q_res.exp_bits) {
+                if (mode_res) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = float_quantize_elem<false>(v[j], 0u, p.q_res.exp_bits, p.q_res.man_bits);
+                    for (int j = 0; j < 32; j++) v[j] = fq_apply(v[j], mode_res, p.q_res);
                 }
                 const int esz_o = p.out_dtype == MV_F32 ? 4 : 2;
                 const bool vec_o = full && ((p.ld_out * esz_o) % 16 == 0);
-                store_out(p.out, p.out_dtype, orow, p.ld_out, n, v, vec_o, nvalid);
+                store_out(p.out, p.out_dtype, m, p.ld_out, n, v, vec_o, nvalid);
                 if (p.out2 != nullptr) {
                     const int esz_2 = p.out2_dtype == MV_F32 ? 4 : 2;
                     const bool vec_2 = full && ((p.ld_out2 * esz_2) % 16 == 0);
-                    store_out(p.out2, p.out2_dtype, orow, p.ld_out2, n, v, vec_2, nvalid);
+                    store_out(p.out2, p.out2_dtype, m, p.ld_out2, n, v, vec_2, nvalid);
                 }
             }
             tc_fence_before();
@@ -334,10 +345,13 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     const int BK = 128 / esz;
     static bool attr_done = false;
     if (!attr_done) {
-        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmem));
         attr_done = true;
     }
+    // 128x256 tiles cut the L2->SM operand traffic per flop by a quarter; use them when N tiles evenly
+    const int BN = (!tf32 && a->N % 256 == 0 && a->tile_n != 128) ? 256 : 128;
     if (a->accumulate) MV_CHECK(a->out_dtype == MV_F32, "mv_gemm: accumulate needs an fp32 output");
     if (a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU) MV_CHECK(a->aux != nullptr, "mv_gemm: GELU epilogues need aux");
 
@@ -346,7 +360,7 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     // MN-major operand stored [K, M|N]: box = BK k-rows x 128 B of M|N.
     if (a->a_major == 0) { if (make_tmap_2d(&ta, a->A, a->a_dtype, a->M, a->K, a->lda, BM, BK)) return 1; }
     else                 { if (make_tmap_2d(&ta, a->A, a->a_dtype, a->K, a->M, a->lda, BK, 128 / esz)) return 1; }
-    if (a->b_major == 0) { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->N, a->K, a->ldb, BN, BK)) return 1; }
+    if (a->b_major == 0) { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->N, a->K, a->ldb, 128, BK)) return 1; }
     else                 { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->K, a->N, a->ldb, BK, 128 / esz)) return 1; }
 
     GemmDev p;
@@ -380,8 +394,9 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     const int units = p.m_tiles * p.n_tiles * p.splits;
     const int grid = units < kNumSMs ? units : kNumSMs;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (tf32) gemm_kernel<4><<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tb, p);
-    else gemm_kernel<2><<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tb, p);
+    if (tf32) gemm_kernel<128, 4><<<grid, kGemmThreads, GemmCfg<128>::kSmem, st>>>(ta, tb, p);
+    else if (BN == 256) gemm_kernel<256, 2><<<grid, kGemmThreads, GemmCfg<256>::kSmem, st>>>(ta, tb, p);
+    else gemm_kernel<128, 2><<<grid, kGemmThreads, GemmCfg<128>::kSmem, st>>>(ta, tb, p);
     g_launches++;
     return check_cuda(cudaGetLastError(), "gemm launch");
 }

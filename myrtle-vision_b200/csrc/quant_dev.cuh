@@ -57,6 +57,25 @@ __device__ __forceinline__ float fq_nearest(float a, FloatFmt f) {
     return f.exp_bits == 0 ? a : float_quantize_elem<false>(a, 0u, f.exp_bits, f.man_bits);
 }
 
+// Same result as float_quantize_elem<false>(a, 0, 5, 10), with a short path for the normal
+// fp16 range (the subnormal / zero branch is rare for activations and falls back).
+__device__ __forceinline__ float fq_half_fast(float a) {
+    const uint32_t t = __float_as_uint(a);
+    if (((t >> 23) & 0xFFu) < 113u) return float_quantize_elem<false>(a, 0u, 5, 10);
+    uint32_t q = (t + 0x1000u) & 0xFFFFE000u;
+    if ((q & 0x7FFFFFFFu) > 0x477FE000u) q = (t & 0x80000000u) | 0x477FE000u;
+    return __uint_as_float(q);
+}
+// quantiser selected once per kernel: 0 = identity, 1 = (5,10) fast path, 2 = generic
+__device__ __forceinline__ int fq_mode(FloatFmt f) {
+    return f.exp_bits == 0 ? 0 : ((f.exp_bits == 5 && f.man_bits == 10) ? 1 : 2);
+}
+__device__ __forceinline__ float fq_apply(float a, int mode, FloatFmt f) {
+    if (mode == 1) return fq_half_fast(a);
+    if (mode == 2) return float_quantize_elem<false>(a, 0u, f.exp_bits, f.man_bits);
+    return a;
+}
+
 // fixed_point_quantize for one element: floor(a * 2^fl + r) * 2^-fl, then clamp.
 // Nearest passes r = 0.5 (QPyTorch's CUDA kernel: ties toward +inf).
 __device__ __forceinline__ float fixed_quantize_elem(float a, float r, float scale_up,

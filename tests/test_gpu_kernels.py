@@ -13,7 +13,7 @@ def relmax(a, b):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 45, 384), (1000, 384, 1536),
-                                   (2501 * 2, 1152, 384)])
+                                   (2501 * 2, 1152, 384), (520, 1536, 384), (384, 256, 8192)])
 @pytest.mark.parametrize("a_major,b_major", [(0, 0), (1, 1), (1, 0), (0, 1)])
 def test_gemm_layouts(M, N, K, a_major, b_major):
     import mv_native as mv
@@ -60,14 +60,15 @@ def test_gemm_splitk_accumulate_and_epilogues():
     want = mv.float_quantize(lin.float(), 5, 10)
     assert ((outq.float() - want).abs() > 0).float().mean().item() < 6e-3      # rare 1-ulp flips only
     assert relmax(outq, want) < 1e-3
-    u = torch.empty(M, N, device=dev, dtype=torch.float16); h = torch.empty_like(u)
-    mv.gemm(A, B, h, bias=bias, aux=u, epilogue=mv.EPI_GELU, q_res=(5, 10))
-    assert relmax(u, lin) < 1e-3 and relmax(h, F.gelu(lin)) < 1e-3
-    # DGELU epilogue: out = (A B^T) * gelu'(u)
-    d = torch.empty(M, N, device=dev, dtype=torch.float16)
-    mv.gemm(A, B, d, aux=u, epilogue=mv.EPI_DGELU)
-    uu = u.double().requires_grad_(True)
+    gp = torch.empty(M, N, device=dev, dtype=torch.float16); h = torch.empty_like(gp)
+    mv.gemm(A, B, h, bias=bias, aux=gp, epilogue=mv.EPI_GELU, q_res=(5, 10))
+    uu = lin.clone().requires_grad_(True)
     F.gelu(uu).sum().backward()
+    # GELU epilogue: out = q(gelu(u)), aux = gelu'(u) saved for the backward
+    assert relmax(h, F.gelu(lin)) < 1e-3 and relmax(gp, uu.grad) < 1e-3
+    # DGELU epilogue: out = (A B^T) * aux
+    d = torch.empty(M, N, device=dev, dtype=torch.float16)
+    mv.gemm(A, B, d, aux=gp, epilogue=mv.EPI_DGELU)
     assert relmax(d, (A.double() @ B.double().t()) * uu.grad) < 2e-3
     # residual broadcast over images (positional embedding)
     pos = torch.randn(257, N, device=dev)

@@ -58,6 +58,9 @@ case(256, 256, 128, f32, f32, 1, 1)
 case(200, 45, 384, h, h, 0, 0)
 case(1000, 384, 1536, h, h, 0, 0)
 case(65792, 1152, 384, h, h, 0, 0)
+case(1000, 1536, 384, h, h, 0, 0)
+case(1000, 256, 384, h, h, 0, 0)
+case(512, 512, 4096, h, h, 1, 1)
 
 # split-K accumulate (wgrad shape): dW[N_out, K_in] = dY^T X
 def wgrad():
@@ -83,9 +86,10 @@ def epi():
     report("epi bias+q_out->f16", outh, want.double())
     u = torch.empty(M, N, device=dev, dtype=h); hh = torch.empty(M, N, device=dev, dtype=h)
     mv.gemm(A, B, hh, bias=bias, aux=u, epilogue=mv.EPI_GELU, q_res=(5, 10))
-    uu = (A.float() @ B.float().t() + bias)
-    report("epi gelu u", u, uu.double())
-    report("epi gelu h", hh, torch.nn.functional.gelu(uu).double())
+    uu = (A.double() @ B.double().t() + bias.double()).requires_grad_(True)
+    torch.nn.functional.gelu(uu).sum().backward()
+    report("epi gelu' (aux)", u, uu.grad)
+    report("epi gelu h", hh, torch.nn.functional.gelu(uu).detach())
 run("epi", epi)
 
 # timing of the flagship shapes
@@ -109,3 +113,49 @@ def bench(M, N, K, iters=20):
     print("   cuBLAS f16: %.3f ms  %.1f TFLOP/s" % (ms, 2.0*M*N*K/ms/1e9), flush=True)
 for shp in [(65792, 1152, 384), (65792, 384, 384), (65792, 1536, 384), (65792, 384, 1536), (8192, 8192, 8192)]:
     run("bench", lambda: bench(*shp))
+
+def bench_cold(name, M, N, K, nbuf=6, **kw):
+    """rotate over nbuf operand/output sets so every launch reads from HBM (as inside the step)"""
+    As = [torch.randn(M, K, device=dev).to(h) for _ in range(nbuf)]
+    Bm = torch.randn(N, K, device=dev).to(h)
+    odt = kw.pop("odt", h)
+    outs = [torch.empty(M, N, device=dev, dtype=odt) for _ in range(nbuf)]
+    extra = {}
+    if kw.get("gelu"):
+        auxs = [torch.empty(M, N, device=dev, dtype=h) for _ in range(nbuf)]
+    if kw.get("res"):
+        ress = [torch.randn(M, N, device=dev) for _ in range(nbuf)]
+    bias = torch.randn(N, device=dev)
+    def call(i):
+        j = i % nbuf
+        if kw.get("gelu"):
+            mv.gemm(As[j], Bm, outs[j], bias=bias, aux=auxs[j], epilogue=mv.EPI_GELU, q_res=(5, 10))
+        elif kw.get("res"):
+            mv.gemm(As[j], Bm, outs[j], bias=bias, residual=ress[j])
+        else:
+            mv.gemm(As[j], Bm, outs[j], bias=bias)
+    for i in range(nbuf): call(i)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3 * nbuf): call(i)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (3 * nbuf)
+    print("cold %-28s M%d N%d K%d: %.3f ms  %.1f TFLOP/s" % (name, M, N, K, ms, 2.0*M*N*K/ms/1e9), flush=True)
+run("c", lambda: bench_cold("qkv fwd (f16 out)", 65792, 1152, 384))
+run("c", lambda: bench_cold("proj fwd (+res, f32 out)", 65792, 384, 384, res=True, odt=f32))
+run("c", lambda: bench_cold("fc1 fwd (gelu)", 65792, 1536, 384, gelu=True))
+run("c", lambda: bench_cold("fc2 fwd (+res, f32 out)", 65792, 384, 1536, res=True, odt=f32))
+def wgrad_cold(T, No, Ki, nbuf=4):
+    dYs = [torch.randn(T, No, device=dev).to(h) for _ in range(nbuf)]; Xs = [torch.randn(T, Ki, device=dev).to(h) for _ in range(nbuf)]
+    out = torch.zeros(No, Ki, device=dev)
+    for i in range(nbuf): mv.gemm(dYs[i], Xs[i], out, a_major=1, b_major=1, accumulate=True)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3 * nbuf): mv.gemm(dYs[i % nbuf], Xs[i % nbuf], out, a_major=1, b_major=1, accumulate=True)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (3 * nbuf)
+    print("cold wgrad T%d %dx%d: %.3f ms %.1f TFLOP/s" % (T, No, Ki, ms, 2.0*T*No*Ki/ms/1e9), flush=True)
+run("w", lambda: wgrad_cold(65792, 1536, 384))
+run("w", lambda: wgrad_cold(65792, 384, 1536))
+run("w", lambda: wgrad_cold(65792, 1152, 384))
+run("w", lambda: wgrad_cold(65792, 384, 384))
