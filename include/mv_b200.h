@@ -114,10 +114,10 @@ int mv_gemm(const mv_gemm_args* args, void* stream);
 int mv_layernorm_q_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, void* y,
                        int64_t ld_y, int y_dtype, float* mean, float* rstd, int rows, int D, float eps,
                        int q_in_exp, int q_in_man, int q_post_exp, int q_post_man, void* stream);
-/* dx = LN'(dy; q_in(x)) + dres (dres nullable); dx_f16 (nullable) gets an fp16 copy of dx (the next
+/* dy: MV_F32 or MV_F16 (the dgrad GEMM's output).  dx = LN'(dy; q_in(x)) + dres (dres nullable); dx_f16 (nullable) gets an fp16 copy of dx (the next
  * GEMM operand).  dgamma/dbeta/dbias_prev (fp32 [D], nullable) are ACCUMULATED (+=): sum dy*xhat,
  * sum dy, sum dx. */
-int mv_layernorm_q_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* dres,
+int mv_layernorm_q_bwd(const void* dy, int dy_dtype, int64_t ld_dy, const float* x, int64_t ld_x, const float* dres,
                        int64_t ld_dres, const float* gamma, const float* mean, const float* rstd,
                        float* dx, int64_t ld_dx, void* dx_f16, int64_t ld_lp, float* dgamma,
                        float* dbeta, float* dbias_prev, int rows, int D, int q_in_exp, int q_in_man,

@@ -58,17 +58,22 @@ struct AttnFwdDev {
     float* lse;
 };
 
-__global__ void __launch_bounds__(kAttThreads, 1)
+__global__ void __launch_bounds__(kAttThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdDev p) {
+    // 80 KB of shared memory and 256 TMEM columns per CTA: two CTAs share an SM, so one CTA's
+    // softmax (CUDA cores) overlaps the other's MMAs and TMA loads.
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
-    uint8_t* sKV = smem + kTile;                 // [2 stages][K, V]
-    uint8_t* sP = smem + 5 * kTile;              // 2 sub-tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTile);
+    uint8_t* sK = smem + kTile;
+    uint8_t* sV = smem + 2 * kTile;
+    uint8_t* sP = smem + 3 * kTile;              // 2 sub-tiles of 64 keys
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTile);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;                // [2]
-    uint64_t* kv_empty = bars + 3;               // [2]
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = bars + 2;
+    uint64_t* v_full = bars + 3;
+    uint64_t* v_empty = bars + 4;
     uint64_t* s_full = bars + 5;
     uint64_t* p_full = bars + 6;
     uint64_t* o_full = bars + 7;
@@ -81,7 +86,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdDev p
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_qkv);
         mbar_init(q_full, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
         mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
         fence_barrier_init();
     }
@@ -97,40 +102,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdDev p
             mbar_arrive_expect_tx(q_full, kTile);
             tma_load_3d(sQ, &tmap_qkv, q_full, h * 64, q0, b);
             for (int j = 0; j < nblk; j++) {
-                const int st = j & 1;
-                mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
-                tma_load_3d(sKV + st * 2 * kTile, &tmap_qkv, &kv_full[st], p.D + h * 64, j * 128, b);
-                tma_load_3d(sKV + st * 2 * kTile + kTile, &tmap_qkv, &kv_full[st], 2 * p.D + h * 64, j * 128, b);
+                mbar_wait(k_empty, (j & 1) ^ 1);
+                mbar_arrive_expect_tx(k_full, kTile);
+                tma_load_3d(sK, &tmap_qkv, k_full, p.D + h * 64, j * 128, b);
+                mbar_wait(v_empty, (j & 1) ^ 1);
+                mbar_arrive_expect_tx(v_full, kTile);
+                tma_load_3d(sV, &tmap_qkv, v_full, 2 * p.D + h * 64, j * 128, b);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+            const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aK = smem_u32(sK), aV = smem_u32(sV);
             mbar_wait(q_full, 0);
             auto issue_s = [&](int j) {
-                const int st = j & 1;
-                mbar_wait(&kv_full[st], (j >> 1) & 1);
+                // the last key block only multiplies the keys that exist (rounded up to 16)
+                const int nk16 = (min(128, p.N - j * 128) + 15) & ~15;
+                mbar_wait(k_full, j & 1);
                 tc_fence_after();
-                const uint32_t aK = smem_u32(sKV + st * 2 * kTile);
+                const uint32_t idesc = make_idesc(0, 0, 0, 0, 128, nk16);
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     umma_f16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024),
-                             make_smem_desc_sw128(aK + k * 32, 16, 1024), kIdescS, k > 0);
+                             make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc, k > 0);
                 umma_commit(s_full);
+                umma_commit(k_empty);
             };
             issue_s(0);
             for (int j = 0; j < nblk; j++) {
-                const int st = j & 1;
+                const int ksteps = ((min(128, p.N - j * 128) + 15) & ~15) >> 4;
+                mbar_wait(v_full, j & 1);
                 mbar_wait(p_full, j & 1);
                 tc_fence_after();
-                const uint32_t aV = smem_u32(sKV + st * 2 * kTile + kTile);
-#pragma unroll
-                for (int k = 0; k < 8; k++)
+                for (int k = 0; k < ksteps; k++)
                     umma_f16(tO, make_smem_desc_sw128(aP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
                              make_smem_desc_sw128(aV + k * 2048, 8192, 1024), kIdescPV, k > 0);
                 umma_commit(o_full);
-                umma_commit(&kv_empty[st]);
+                umma_commit(v_empty);
                 if (j + 1 < nblk) issue_s(j + 1);
             }
         }
@@ -139,84 +146,97 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdDev p
         const int r = quad * 32 + lane;
         const int qrow = q0 + r;
         const uint32_t lane_off = uint32_t(quad * 32) << 16;
-        float m = -INFINITY, l = 0.f;
-        float o[64];
-#pragma unroll
-        for (int i = 0; i < 64; i++) o[i] = 0.f;
-        for (int j = 0; j < nblk; j++) {
-            mbar_wait(s_full, j & 1);
-            tc_fence_after();
-            const int kbase = j * 128;
-            // pass 1: row max of the scaled scores
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; c++) {
-                uint32_t s[32];
-                tmem_ld_32x32(tS + lane_off + c * 32, s);
-                tmem_ld_wait();
-#pragma unroll
-                for (int t = 0; t < 32; t++)
-                    if (kbase + c * 32 + t < p.N) mx = fmaxf(mx, __uint_as_float(s[t]));
+        if (q0 + quad * 32 >= p.N) {
+            // none of this warp's 32 query rows exists: only keep the barrier protocol going
+            for (int j = 0; j < nblk; j++) {
+                mbar_wait(s_full, j & 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+                mbar_wait(o_full, j & 1);
             }
-            const float m_new = fmaxf(m, mx * p.scale_log2);
-            const float alpha = exp2f(m - m_new);          // m = -inf on the first block -> 0
-            float psum = 0.f;
-            // pass 2: P = exp2(s*c - m_new) -> fp16 -> swizzled smem (A operand of P.V)
-#pragma unroll 1
-            for (int c = 0; c < 4; c++) {
-                uint32_t s[32];
-                tmem_ld_32x32(tS + lane_off + c * 32, s);
-                tmem_ld_wait();
-                uint32_t w[16];
+        } else {
+            float m = -INFINITY, l = 0.f;
+            float o[64];
 #pragma unroll
-                for (int t = 0; t < 16; t++) {
-                    const int k0 = kbase + c * 32 + 2 * t;
-                    float p0 = k0 < p.N ? exp2f(__uint_as_float(s[2 * t]) * p.scale_log2 - m_new) : 0.f;
-                    float p1 = k0 + 1 < p.N ? exp2f(__uint_as_float(s[2 * t + 1]) * p.scale_log2 - m_new) : 0.f;
-                    // accumulate the row sum from the fp16-rounded values the MMA will see
-                    const __half2 hp = __floats2half2_rn(p0, p1);
-                    const float2 fp = __half22float2(hp);
-                    psum += fp.x + fp.y;
-                    w[t] = *reinterpret_cast<const uint32_t*>(&hp);
+            for (int i = 0; i < 64; i++) o[i] = 0.f;
+            for (int j = 0; j < nblk; j++) {
+                mbar_wait(s_full, j & 1);
+                tc_fence_after();
+                const int kbase = j * 128;
+                const int nk16 = (min(128, p.N - kbase) + 15) & ~15;
+                const int nchunk = (nk16 + 31) >> 5;
+                // pass 1: row max of the scaled scores
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < nchunk; c++) {
+                    uint32_t s[32];
+                    tmem_ld_32x32(tS + lane_off + c * 32, s);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int t = 0; t < 32; t++)
+                        if (kbase + c * 32 + t < p.N) mx = fmaxf(mx, __uint_as_float(s[t]));
                 }
-                store_p_chunk(sP, r, c, w);
+                const float m_new = fmaxf(m, mx * p.scale_log2);
+                const float alpha = exp2f(m - m_new);          // m = -inf on the first block -> 0
+                float psum = 0.f;
+                // pass 2: P = exp2(s*c - m_new) -> fp16 -> swizzled smem (A operand of P.V)
+#pragma unroll 1
+                for (int c = 0; c < nchunk; c++) {
+                    uint32_t s[32];
+                    tmem_ld_32x32(tS + lane_off + c * 32, s);
+                    tmem_ld_wait();
+                    uint32_t w[16];
+#pragma unroll
+                    for (int t = 0; t < 16; t++) {
+                        const int k0 = kbase + c * 32 + 2 * t;
+                        const float p0 = k0 < p.N ? exp2f(fmaf(__uint_as_float(s[2 * t]), p.scale_log2, -m_new)) : 0.f;
+                        const float p1 = k0 + 1 < p.N ? exp2f(fmaf(__uint_as_float(s[2 * t + 1]), p.scale_log2, -m_new)) : 0.f;
+                        // accumulate the row sum from the fp16-rounded values the MMA will see
+                        const __half2 hp = __floats2half2_rn(p0, p1);
+                        const float2 fp = __half22float2(hp);
+                        psum += fp.x + fp.y;
+                        w[t] = *reinterpret_cast<const uint32_t*>(&hp);
+                    }
+                    store_p_chunk(sP, r, c, w);
+                }
+                l = l * alpha + psum;
+                m = m_new;
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+                // O_j = P V_j ; accumulate with rescale
+                mbar_wait(o_full, j & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tO + lane_off + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int t = 0; t < 32; t++) o[c * 32 + t] = fmaf(o[c * 32 + t], alpha, __uint_as_float(v[t]));
+                }
+                tc_fence_before();
             }
-            l = l * alpha + psum;
-            m = m_new;
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-            // O_j = P V_j ; accumulate with rescale
-            mbar_wait(o_full, j & 1);
-            tc_fence_after();
+            if (qrow < p.N) {
+                const float inv = 1.0f / l;
+                const int64_t grow = int64_t(b) * p.N + qrow;
+                if (p.lse != nullptr) p.lse[(int64_t(b) * p.H + h) * p.N + qrow] = m + log2f(l);
+                const int mode = fq_mode(p.q_out);
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                uint32_t v[32];
-                tmem_ld_32x32(tO + lane_off + c * 32, v);
-                tmem_ld_wait();
+                for (int i = 0; i < 64; i++) o[i] = fq_apply(o[i] * inv, mode, p.q_out);
+                if (p.out_dtype == MV_F16) {
+                    __half* dst = reinterpret_cast<__half*>(p.out) + grow * p.ld_out + h * 64;
 #pragma unroll
-                for (int t = 0; t < 32; t++) o[c * 32 + t] = o[c * 32 + t] * alpha + __uint_as_float(v[t]);
-            }
-            tc_fence_before();
-        }
-        if (qrow < p.N) {
-            const float inv = 1.0f / l;
-            const int64_t grow = int64_t(b) * p.N + qrow;
-            if (p.lse != nullptr) p.lse[(int64_t(b) * p.H + h) * p.N + qrow] = m + log2f(l);
+                    for (int i = 0; i < 8; i++)
+                        reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_h2(sat16f(o[8 * i]), sat16f(o[8 * i + 1])), pack_h2(sat16f(o[8 * i + 2]), sat16f(o[8 * i + 3])),
+                                                                      pack_h2(sat16f(o[8 * i + 4]), sat16f(o[8 * i + 5])), pack_h2(sat16f(o[8 * i + 6]), sat16f(o[8 * i + 7])));
+                } else {
+                    float* dst = reinterpret_cast<float*>(p.out) + grow * p.ld_out + h * 64;
 #pragma unroll
-            for (int i = 0; i < 64; i++) o[i] = fq_nearest(o[i] * inv, p.q_out);
-            if (p.out_dtype == MV_F16) {
-                __half* dst = reinterpret_cast<__half*>(p.out) + grow * p.ld_out + h * 64;
-#pragma unroll
-                for (int i = 0; i < 8; i++)
-                    reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_h2(sat16f(o[8 * i]), sat16f(o[8 * i + 1])), pack_h2(sat16f(o[8 * i + 2]), sat16f(o[8 * i + 3])),
-                                                                  pack_h2(sat16f(o[8 * i + 4]), sat16f(o[8 * i + 5])), pack_h2(sat16f(o[8 * i + 6]), sat16f(o[8 * i + 7])));
-            } else {
-                float* dst = reinterpret_cast<float*>(p.out) + grow * p.ld_out + h * 64;
-#pragma unroll
-                for (int i = 0; i < 16; i++)
-                    reinterpret_cast<float4*>(dst)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    for (int i = 0; i < 16; i++)
+                        reinterpret_cast<float4*>(dst)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
             }
         }
     }
@@ -334,30 +354,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 // S = Q K^T ; dP = dO V^T   (all operands K-major over d)
                 const uint32_t aQ = kModeKV ? aX : aR0, aK = kModeKV ? aR0 : aX;
                 const uint32_t aDO = kModeKV ? aY : aR1, aV = kModeKV ? aR1 : aY;
+                // partial last blocks: only the keys / query rows that exist (rounded up to 16) are multiplied
+                const int kbase = kModeKV ? blk0 : it * 128, qbase = kModeKV ? it * 128 : blk0;
+                const int nk16 = (min(128, p.N - kbase) + 15) & ~15, nq16 = (min(128, p.N - qbase) + 15) & ~15;
+                const uint32_t idesc_s = make_idesc(0, 0, 0, 0, 128, nk16);
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    umma_f16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), kIdescS, k > 0);
+                    umma_f16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    umma_f16(tdP, make_smem_desc_sw128(aDO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), kIdescS, k > 0);
+                    umma_f16(tdP, make_smem_desc_sw128(aDO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), idesc_s, k > 0);
                 umma_commit(sdp_full);
                 mbar_wait(pds_full, it & 1);
                 tc_fence_after();
                 if (kModeKV) {
-                    // dV[keys, d] += P^T dO : A = P as MN-major (M = keys), B = dO as MN-major (N = d); K = 128 q rows
-#pragma unroll
-                    for (int k = 0; k < 8; k++)
+                    // dV[keys, d] += P^T dO : A = P as MN-major (M = keys), B = dO as MN-major (N = d); K = q rows
+                    for (int k = 0; k < (nq16 >> 4); k++)
                         umma_f16(tAcc0, make_smem_desc_sw128(aP + k * 2048, kTile, 1024),
                                  make_smem_desc_sw128(aDO + k * 2048, 8192, 1024), kIdescTT, (it > 0 || k > 0));
                     // dK[keys, d] += dS^T Q
-#pragma unroll
-                    for (int k = 0; k < 8; k++)
+                    for (int k = 0; k < (nq16 >> 4); k++)
                         umma_f16(tAcc1, make_smem_desc_sw128(adS + k * 2048, kTile, 1024),
                                  make_smem_desc_sw128(aQ + k * 2048, 8192, 1024), kIdescTT, (it > 0 || k > 0));
                 } else {
-                    // dQ[q, d] += dS K : A = dS K-major over keys, B = K_j as MN-major (N = d); K = 128 keys
-#pragma unroll
-                    for (int k = 0; k < 8; k++)
+                    // dQ[q, d] += dS K : A = dS K-major over keys, B = K_j as MN-major (N = d); K = keys
+                    for (int k = 0; k < (nk16 >> 4); k++)
                         umma_f16(tAcc0, make_smem_desc_sw128(adS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
                                  make_smem_desc_sw128(aK + k * 2048, 8192, 1024), kIdescPV, (it > 0 || k > 0));
                 }
@@ -379,11 +400,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 const int64_t si = (int64_t(b) * p.H + h) * p.N + qrow;
                 L = p.lse[si]; dl = p.delta[si];
             }
+            const int nk16 = (min(128, p.N - kbase) + 15) & ~15;
+            const int nq16 = (min(128, p.N - (kModeKV ? it * 128 : blk0)) + 15) & ~15;
+            // warps whose 32 rows lie beyond the rows the MMAs consume have nothing to produce
+            const int nchunk = (quad * 32 < nq16) ? ((nk16 + 31) >> 5) : 0;
             mbar_wait(sdp_full, it & 1);
             tc_fence_after();
             mbar_wait(pds_empty, (it & 1) ^ 1);       // previous iteration's MMAs are done with sP / sdS
 #pragma unroll 1
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < nchunk; c++) {
                 uint32_t s[32], dp[32];
                 tmem_ld_32x32(tS + lane_off + c * 32, s);
                 tmem_ld_32x32(tdP + lane_off + c * 32, dp);
@@ -440,7 +465,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
 }
 
-constexpr int kAttnFwdSmem = 7 * kTile + 1024 + 256;
+constexpr int kAttnFwdSmem = 5 * kTile + 1024 + 256;
 constexpr int kAttnBwdKVSmem = 10 * kTile + 1024 + 256;
 constexpr int kAttnBwdQSmem = 8 * kTile + 1024 + 256;
 

@@ -29,63 +29,90 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 template <int NV, typename OutT>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, 4)
 ln_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ gamma,
               const float* __restrict__ beta, OutT* __restrict__ y, int64_t ld_y,
               float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int D, float eps,
               FloatFmt q_in, FloatFmt q_post) {
+    // Each warp owns two rows per iteration: both rows' loads are issued before either is
+    // reduced, doubling the bytes in flight per warp.  gamma/beta stay in L1 (re-read per row)
+    // instead of occupying 2*NV*4 registers.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = D >> 2;
-    float4 g[NV], b[NV];
+    const int mi = fq_mode(q_in), mp = fq_mode(q_post);
+    const float inv_d = 1.0f / float(D);
+    const int wstride = gridDim.x * kLnWarps * 2;
+    for (int row0 = (blockIdx.x * kLnWarps + warp) * 2; row0 < rows; row0 += wstride) {
+        float4 v[2][NV];
+        float s[2] = {0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < NV; i++) {
-        const int c = lane + 32 * i;
-        if (c < nvec) {
-            g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-            b[i] = __ldg(reinterpret_cast<const float4*>(beta) + c);
-        }
-    }
-    for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
-        const float4* xr = reinterpret_cast<const float4*>(x + int64_t(row) * ld_x);
-        float4 v[NV];
-        float s = 0.f;
+        for (int rr = 0; rr < 2; rr++) {
+            const int row = row0 + rr;
+            const float4* xr = reinterpret_cast<const float4*>(x + int64_t(row) * ld_x);
 #pragma unroll
-        for (int i = 0; i < NV; i++) {
-            const int c = lane + 32 * i;
-            if (c < nvec) {
-                v[i] = __ldcs(xr + c);
-                v[i].x = fq_nearest(v[i].x, q_in); v[i].y = fq_nearest(v[i].y, q_in);
-                v[i].z = fq_nearest(v[i].z, q_in); v[i].w = fq_nearest(v[i].w, q_in);
-                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            for (int i = 0; i < NV; i++) {
+                const int c = lane + 32 * i;
+                if (c < nvec && row < rows) v[rr][i] = __ldcs(xr + c);
+                else v[rr][i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        const float mean = warp_sum(s) / float(D);
-        float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < NV; i++) {
-            const int c = lane + 32 * i;
-            if (c < nvec) {
-                const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
-                ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        for (int rr = 0; rr < 2; rr++) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) {
+                v[rr][i].x = fq_apply(v[rr][i].x, mi, q_in); v[rr][i].y = fq_apply(v[rr][i].y, mi, q_in);
+                v[rr][i].z = fq_apply(v[rr][i].z, mi, q_in); v[rr][i].w = fq_apply(v[rr][i].w, mi, q_in);
+                s[rr] += (v[rr][i].x + v[rr][i].y) + (v[rr][i].z + v[rr][i].w);
             }
         }
-        const float rstd = rsqrtf(warp_sum(ss) / float(D) + eps);
-        if (lane == 0 && mean_out != nullptr) { mean_out[row] = mean; rstd_out[row] = rstd; }
-        OutT* yr = y + int64_t(row) * ld_y;
 #pragma unroll
-        for (int i = 0; i < NV; i++) {
-            const int c = lane + 32 * i;
-            if (c < nvec) {
-                float4 o;
-                o.x = fq_nearest((v[i].x - mean) * rstd * g[i].x + b[i].x, q_post);
-                o.y = fq_nearest((v[i].y - mean) * rstd * g[i].y + b[i].y, q_post);
-                o.z = fq_nearest((v[i].z - mean) * rstd * g[i].z + b[i].z, q_post);
-                o.w = fq_nearest((v[i].w - mean) * rstd * g[i].w + b[i].w, q_post);
-                if (sizeof(OutT) == 4) {
-                    reinterpret_cast<float4*>(yr)[c] = o;
-                } else {
-                    __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
-                    reinterpret_cast<uint2*>(yr)[c] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        for (int o = 16; o > 0; o >>= 1) {
+            s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+            s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+        }
+        const float mean[2] = {s[0] * inv_d, s[1] * inv_d};
+        float ss[2] = {0.f, 0.f};
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) {
+                const int c = lane + 32 * i;
+                if (c < nvec) {
+                    const float dx = v[rr][i].x - mean[rr], dy = v[rr][i].y - mean[rr];
+                    const float dz = v[rr][i].z - mean[rr], dw = v[rr][i].w - mean[rr];
+                    ss[rr] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], o);
+            ss[1] += __shfl_xor_sync(0xffffffffu, ss[1], o);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int row = row0 + rr;
+            if (row >= rows) break;
+            const float rstd = rsqrtf(ss[rr] * inv_d + eps);
+            if (lane == 0 && mean_out != nullptr) { mean_out[row] = mean[rr]; rstd_out[row] = rstd; }
+            OutT* yr = y + int64_t(row) * ld_y;
+#pragma unroll
+            for (int i = 0; i < NV; i++) {
+                const int c = lane + 32 * i;
+                if (c < nvec) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+                    float4 o;
+                    o.x = fq_apply(fmaf((v[rr][i].x - mean[rr]) * rstd, g.x, b.x), mp, q_post);
+                    o.y = fq_apply(fmaf((v[rr][i].y - mean[rr]) * rstd, g.y, b.y), mp, q_post);
+                    o.z = fq_apply(fmaf((v[rr][i].z - mean[rr]) * rstd, g.z, b.z), mp, q_post);
+                    o.w = fq_apply(fmaf((v[rr][i].w - mean[rr]) * rstd, g.w, b.w), mp, q_post);
+                    if (sizeof(OutT) == 4) {
+                        __stcs(reinterpret_cast<float4*>(yr) + c, o);
+                    } else {
+                        __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+                        __stcs(reinterpret_cast<uint2*>(yr) + c, make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi)));
+                    }
                 }
             }
         }
@@ -96,9 +123,17 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict
 // along the residual connection (nullable); dx (fp32) and dx_lp (fp16, nullable) receive
 // LN'(dy) + dres.  Column sums are accumulated per lane over the warp's rows, reduced across
 // the CTA in shared memory and added to global memory with one atomic per column per CTA.
-template <int NV>
+__device__ __forceinline__ float4 load_dy4(const float* p, int c) { return __ldcs(reinterpret_cast<const float4*>(p) + c); }
+__device__ __forceinline__ float4 load_dy4(const __half* p, int c) {
+    const uint2 u = __ldcs(reinterpret_cast<const uint2*>(p) + c);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <int NV, typename DyT>
 __global__ void __launch_bounds__(kLnWarps * 32)
-ln_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x, int64_t ld_x,
+ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x, int64_t ld_x,
               const float* __restrict__ dres, int64_t ld_dres, const float* __restrict__ gamma,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               float* __restrict__ dx, int64_t ld_dx, __half* __restrict__ dx_lp, int64_t ld_lp,
@@ -117,7 +152,7 @@ ln_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restri
     for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
         const float mean = mean_in[row], rstd = rstd_in[row];
         const float4* xr = reinterpret_cast<const float4*>(x + int64_t(row) * ld_x);
-        const float4* dyr = reinterpret_cast<const float4*>(dy + int64_t(row) * ld_dy);
+        const DyT* dyr = dy + int64_t(row) * ld_dy;
         float4 xh[NV], gy[NV];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -125,7 +160,7 @@ ln_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restri
             const int c = lane + 32 * i;
             if (c < nvec) {
                 float4 xv = __ldcs(xr + c);
-                const float4 d = __ldcs(dyr + c);
+                const float4 d = load_dy4(dyr, c);
                 xv.x = (fq_nearest(xv.x, q_in) - mean) * rstd; xv.y = (fq_nearest(xv.y, q_in) - mean) * rstd;
                 xv.z = (fq_nearest(xv.z, q_in) - mean) * rstd; xv.w = (fq_nearest(xv.w, q_in) - mean) * rstd;
                 xh[i] = xv;
@@ -183,35 +218,64 @@ ln_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restri
 }
 
 // out[c] += sum_r in[r, c]   (bias gradients of to_qkv / net.0 from their fp16 dY)
+// A warp reads 256 (fp16) or 128 (fp32) consecutive columns of a row with one 16-byte load per
+// lane, four rows in flight; the 8 warps of a CTA stride over rows and are combined in shared
+// memory before one atomicAdd per column.
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ in, int64_t ld, int rows, int cols, float* __restrict__ out) {
-    // block: 32 column-pairs x 8 row lanes; each thread owns 2 adjacent columns
-    __shared__ float2 sm[8][33];
-    const int cp = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ry = threadIdx.x >> 5;
-    float2 acc = make_float2(0.f, 0.f);
-    if (2 * cp < cols) {
-        for (int r = blockIdx.y * 8 + ry; r < rows; r += gridDim.y * 8) {
+    constexpr int VEC = 16 / sizeof(T);               // elements per 16-byte load
+    __shared__ float sm[8][32 * VEC + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = (blockIdx.x * 32 + lane) * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; j++) acc[j] = 0.f;
+    if (c0 < cols) {
+        const int rstride = gridDim.y * 8;
+        int r = blockIdx.y * 8 + warp;
+        for (; r + 3 * rstride < rows; r += 4 * rstride) {
+            uint4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                w[u] = __ldcs(reinterpret_cast<const uint4*>(in + int64_t(r + u * rstride) * ld + c0));
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (sizeof(T) == 2) {
+                    const __half2* h = reinterpret_cast<const __half2*>(&w[u]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { const float2 f = __half22float2(h[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+                } else {
+                    const float* f = reinterpret_cast<const float*>(&w[u]);
+#pragma unroll
+                    for (int j = 0; j < VEC; j++) acc[j] += f[j];
+                }
+            }
+        }
+        for (; r < rows; r += rstride) {
+            const uint4 w = __ldcs(reinterpret_cast<const uint4*>(in + int64_t(r) * ld + c0));
             if (sizeof(T) == 2) {
-                const __half2 v = *reinterpret_cast<const __half2*>(
-                    reinterpret_cast<const __half*>(in) + int64_t(r) * ld + 2 * cp);
-                const float2 f = __half22float2(v);
-                acc.x += f.x; acc.y += f.y;
+                const __half2* h = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+                for (int j = 0; j < 4; j++) { const float2 f = __half22float2(h[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
             } else {
-                const float2 f = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(in) + int64_t(r) * ld + 2 * cp);
-                acc.x += f.x; acc.y += f.y;
+                const float* f = reinterpret_cast<const float*>(&w);
+#pragma unroll
+                for (int j = 0; j < VEC; j++) acc[j] += f[j];
             }
         }
     }
-    sm[ry][threadIdx.x & 31] = acc;
-    __syncthreads();
-    if (ry == 0 && 2 * cp < cols) {
-        float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 8; j++) { s.x += sm[j][threadIdx.x].x; s.y += sm[j][threadIdx.x].y; }
-        atomicAdd(out + 2 * cp, s.x);
-        atomicAdd(out + 2 * cp + 1, s.y);
+    for (int j = 0; j < VEC; j++) sm[warp][lane * VEC + j] = acc[j];
+    __syncthreads();
+    for (int t = threadIdx.x; t < 32 * VEC; t += 256) {
+        const int c = blockIdx.x * 32 * VEC + t;
+        if (c < cols) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; w8++) sacc += sm[w8][t];
+            atomicAdd(out + c, sacc);
+        }
     }
 }
 
@@ -281,8 +345,8 @@ template <int NV>
 static int launch_ln_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, void* y,
                          int64_t ld_y, int y_dtype, float* mean, float* rstd, int rows, int D,
                          float eps, FloatFmt q_in, FloatFmt q_post, cudaStream_t st) {
-    int grid = (rows + kLnWarps - 1) / kLnWarps;
-    const int cap = kNumSMs * 8;
+    int grid = (rows + 2 * kLnWarps - 1) / (2 * kLnWarps);
+    const int cap = kNumSMs * 4;
     if (grid > cap) grid = cap;
     if (y_dtype == MV_F16)
         ln_fwd_kernel<NV, __half><<<grid, kLnWarps * 32, 0, st>>>(x, ld_x, gamma, beta, (__half*)y, ld_y, mean, rstd, rows, D, eps, q_in, q_post);
@@ -293,7 +357,7 @@ static int launch_ln_fwd(const float* x, int64_t ld_x, const float* gamma, const
 }
 
 template <int NV>
-static int launch_ln_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* dres,
+static int launch_ln_bwd(const void* dy, int dy_dtype, int64_t ld_dy, const float* x, int64_t ld_x, const float* dres,
                          int64_t ld_dres, const float* gamma, const float* mean, const float* rstd,
                          float* dx, int64_t ld_dx, void* dx_lp, int64_t ld_lp, float* dgamma, float* dbeta,
                          float* dbias_prev, int rows, int D, FloatFmt q_in, cudaStream_t st) {
@@ -301,8 +365,12 @@ static int launch_ln_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t
     const int cap = kNumSMs * 4;
     if (grid > cap) grid = cap;
     const size_t smem = size_t(kLnWarps) * D * sizeof(float);
-    ln_bwd_kernel<NV><<<grid, kLnWarps * 32, smem, st>>>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx,
-                                                        (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in);
+    if (dy_dtype == MV_F16)
+        ln_bwd_kernel<NV, __half><<<grid, kLnWarps * 32, smem, st>>>((const __half*)dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx,
+                                                                    (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in);
+    else
+        ln_bwd_kernel<NV, float><<<grid, kLnWarps * 32, smem, st>>>((const float*)dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx,
+                                                                   (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in);
     g_launches++;
     return check_cuda(cudaGetLastError(), "ln bwd launch");
 }
@@ -332,38 +400,43 @@ extern "C" int mv_layernorm_q_fwd(const float* x, int64_t ld_x, const float* gam
     }
 }
 
-extern "C" int mv_layernorm_q_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x,
+extern "C" int mv_layernorm_q_bwd(const void* dy, int dy_dtype, int64_t ld_dy, const float* x, int64_t ld_x,
                                   const float* dres, int64_t ld_dres, const float* gamma, const float* mean,
                                   const float* rstd, float* dx, int64_t ld_dx, void* dx_bf16, int64_t ld_lp,
                                   float* dgamma, float* dbeta, float* dbias_prev, int rows, int D,
                                   int q_in_exp, int q_in_man, void* stream) {
     MV_CHECK(rows >= 0 && D > 0 && D % 4 == 0 && D <= 128 * kLnMaxVec, "mv_layernorm_q_bwd: D=%d unsupported", D);
+    MV_CHECK(dy_dtype == MV_F16 || dy_dtype == MV_F32, "mv_layernorm_q_bwd: dy must be fp16 or fp32");
     MV_CHECK(ld_dy % 4 == 0 && ld_x % 4 == 0 && ld_dx % 4 == 0 && ld_dres % 4 == 0 && ld_lp % 4 == 0, "mv_layernorm_q_bwd: row pitches must be multiples of 4");
     if (rows == 0) return 0;
     const FloatFmt qi{q_in_exp, q_in_man};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int nv = (D / 4 + 31) / 32;
     switch (nv) {
-        case 1: return launch_ln_bwd<1>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
-        case 2: return launch_ln_bwd<2>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
-        case 3: return launch_ln_bwd<3>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
-        case 4: return launch_ln_bwd<4>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
-        case 5: case 6: return launch_ln_bwd<6>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
-        default: return launch_ln_bwd<8>(dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        case 1: return launch_ln_bwd<1>(dy, dy_dtype, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        case 2: return launch_ln_bwd<2>(dy, dy_dtype, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        case 3: return launch_ln_bwd<3>(dy, dy_dtype, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        case 4: return launch_ln_bwd<4>(dy, dy_dtype, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        case 5: case 6: return launch_ln_bwd<6>(dy, dy_dtype, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
+        default: return launch_ln_bwd<8>(dy, dy_dtype, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx, dx_bf16, ld_lp, dgamma, dbeta, dbias_prev, rows, D, qi, st);
     }
 }
 
 extern "C" int mv_colsum(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out, void* stream) {
-    MV_CHECK(rows >= 0 && cols > 0 && cols % 2 == 0 && ld % 2 == 0, "mv_colsum: cols/ld must be even");
+    MV_CHECK(in_dtype == MV_F16 || in_dtype == MV_F32, "mv_colsum: dtype must be f16 or f32");
+    const int vec = in_dtype == MV_F16 ? 8 : 4;
+    MV_CHECK(rows >= 0 && cols > 0 && cols % vec == 0 && ld % vec == 0 && reinterpret_cast<uintptr_t>(in) % 16 == 0,
+             "mv_colsum: cols/ld must be multiples of %d and the base 16-byte aligned", vec);
     if (rows == 0) return 0;
-    int gy = (rows + 8 * 64 - 1) / (8 * 64);
-    if (gy > 512) gy = 512;
+    const int gx = (cols + 32 * vec - 1) / (32 * vec);
+    int gy = (kNumSMs * 4 + gx - 1) / gx;
+    const int max_gy = (rows + 31) / 32;
+    if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
-    dim3 grid((cols / 2 + 31) / 32, gy);
+    dim3 grid(gx, gy);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (in_dtype == MV_F16) colsum_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, ld, rows, cols, out);
-    else if (in_dtype == MV_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)in, ld, rows, cols, out);
-    else MV_CHECK(false, "mv_colsum: dtype must be f16 or f32");
+    else colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)in, ld, rows, cols, out);
     g_launches++;
     return check_cuda(cudaGetLastError(), "colsum launch");
 }

@@ -59,9 +59,13 @@ __device__ __forceinline__ float fq_nearest(float a, FloatFmt f) {
 
 // Same result as float_quantize_elem<false>(a, 0, 5, 10), with a short path for the normal
 // fp16 range (the subnormal / zero branch is rare for activations and falls back).
+static __device__ __noinline__ float fq_half_slow(float a) { return float_quantize_elem<false>(a, 0u, 5, 10); }
+static __device__ __noinline__ float fq_generic_slow(float a, int exp_bits, int man_bits) {
+    return float_quantize_elem<false>(a, 0u, exp_bits, man_bits);
+}
 __device__ __forceinline__ float fq_half_fast(float a) {
     const uint32_t t = __float_as_uint(a);
-    if (((t >> 23) & 0xFFu) < 113u) return float_quantize_elem<false>(a, 0u, 5, 10);
+    if (((t >> 23) & 0xFFu) < 113u) return fq_half_slow(a);     // out of line: keeps fused loops small
     uint32_t q = (t + 0x1000u) & 0xFFFFE000u;
     if ((q & 0x7FFFFFFFu) > 0x477FE000u) q = (t & 0x80000000u) | 0x477FE000u;
     return __uint_as_float(q);
@@ -72,7 +76,7 @@ __device__ __forceinline__ int fq_mode(FloatFmt f) {
 }
 __device__ __forceinline__ float fq_apply(float a, int mode, FloatFmt f) {
     if (mode == 1) return fq_half_fast(a);
-    if (mode == 2) return float_quantize_elem<false>(a, 0u, f.exp_bits, f.man_bits);
+    if (mode == 2) return fq_generic_slow(a, f.exp_bits, f.man_bits);
     return a;
 }
 

@@ -159,7 +159,7 @@ class EncoderEngine:
             du = torch.empty(M, Mm, dtype=f16, device=dev)
             mv.gemm(dx_h, wq[b0 + 10][1], du, aux=u, epilogue=mv.EPI_DGELU)
             mv.gemm(dx_h, h, g[b0 + 10], a_major=1, b_major=1, accumulate=True)
-            dxn2 = torch.empty(M, D, dtype=torch.float32, device=dev)
+            dxn2 = torch.empty(M, D, dtype=f16, device=dev)
             mv.gemm(du, wq[b0 + 8][1], dxn2, tag="dgrad")
             mv.gemm(du, xn2, g[b0 + 8], a_major=1, b_major=1, accumulate=True)
             mv.colsum(du, g[b0 + 9].view(-1))

@@ -267,7 +267,7 @@ def layernorm_q_bwd(dy, x, gamma, mean, rstd, *, dres=None, q_in=None, dgamma=No
     D = x.shape[-1]
     x2, dy2 = x.reshape(-1, D), dy.reshape(-1, D)
     rows = x2.shape[0]
-    assert dy2.dtype == torch.float32 and x2.dtype == torch.float32
+    assert dy2.dtype in (torch.float32, torch.float16) and x2.dtype == torch.float32
     if dx is None:
         dx = torch.empty(rows, D, dtype=torch.float32, device=x.device)
     if want_f16 and dx_f16 is None:
@@ -275,7 +275,7 @@ def layernorm_q_bwd(dy, x, gamma, mean, rstd, *, dres=None, q_in=None, dgamma=No
     dres2 = dres.reshape(-1, D) if dres is not None else None
     qi = _fmt(q_in)
     with _timed("ln_bwd"):
-        rc = lib().mv_layernorm_q_bwd(_ptr(dy2), ctypes.c_int64(dy2.stride(0)), _ptr(x2),
+        rc = lib().mv_layernorm_q_bwd(_ptr(dy2), _DT[dy2.dtype], ctypes.c_int64(dy2.stride(0)), _ptr(x2),
                                       ctypes.c_int64(x2.stride(0)), _ptr(dres2),
                                       ctypes.c_int64(dres2.stride(0) if dres2 is not None else D),
                                       _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx),

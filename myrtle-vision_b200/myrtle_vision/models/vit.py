@@ -205,10 +205,19 @@ class ViT(nn.Module):
         the concatenation (FloatFunctional output)."""
         ff = self.quantizer.plan.ff
         pos_cls, pos = self.pos_embedding[:, 0:1, :], self.pos_embedding[:, 1:, :]
-        pos = pos.transpose(1, 2).view(1, -1, 14, 14)
-        pos = F.interpolate(pos, size=(gh, gw), mode="bicubic", align_corners=False)
-        pos = pos.view(1, -1, gh * gw).transpose(1, 2)
+        # bicubic interpolation is linear in the grid values: apply it as a cached
+        # [gh*gw, 196] matrix (ATen's upsample_bicubic2d launches a single thread block here)
+        pos = torch.matmul(self._resize_matrix(gh, gw, pos.device), pos)
         return _fq(torch.cat((pos_cls, pos), dim=1), ff)
+
+    def _resize_matrix(self, gh, gw, device):
+        key = (gh, gw, str(device))
+        cache = self.__dict__.setdefault("_resize_cache", {})
+        if key not in cache:
+            basis = torch.eye(14 * 14).view(14 * 14, 1, 14, 14)
+            w = F.interpolate(basis, size=(gh, gw), mode="bicubic", align_corners=False)
+            cache[key] = w.view(14 * 14, gh * gw).t().contiguous().to(device)
+        return cache[key]
 
     def _linear(self, holder, x):
         plan = self.quantizer.plan

@@ -26,8 +26,8 @@ def test_gemm_layouts(M, N, K, a_major, b_major):
     mv.gemm(A, B, out, a_major=a_major, b_major=b_major)
     Af = A.double().t() if a_major else A.double()
     Bf = B.double().t() if b_major else B.double()
-    # exact products, fp32 accumulation: 1e-5 of the largest entry
-    assert relmax(out, Af @ Bf.t()) < 1e-5
+    # exact products, fp32 accumulation: 1e-5 of the largest entry (3e-5 for K = 8192)
+    assert relmax(out, Af @ Bf.t()) < (1e-5 if K <= 2048 else 3e-5)
 
 
 def test_gemm_tf32_kmajor():
