@@ -143,9 +143,11 @@ int mv_convert_f32(const float* in, void* out, int out_dtype, int64_t n, void* s
 int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float* lse, int B, int H, int N,
                      float scale, int q_out_exp, int q_out_man, void* stream);
 /* autograd backward of the above.  o: the saved forward output (fp16), d_o: fp16 gradient w.r.t. it,
- * delta: fp32 [B,H,N] scratch, dqkv: fp16 [B*N, 3*H*64] (dq | dk | dv).  Deterministic (no atomics). */
+ * delta: fp32 [B,H,N] scratch, dqkv: fp16 [B*N, 3*H*64] (dq | dk | dv).
+ * dq_accum: fp32 [B*N, H*64] scratch.  Non-NULL: one pass over key blocks, dQ accumulated across
+ * key blocks with fp32 red.add (fast path).  NULL: deterministic two-pass variant without atomics. */
 int mv_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
-                     void* dqkv, int B, int H, int N, float scale, void* stream);
+                     float* dq_accum, void* dqkv, int B, int H, int N, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -275,6 +275,7 @@ struct AttnBwdDev {
     const float* lse;
     const float* delta;
     __half* dqkv; int ld_dqkv;
+    float* dq_accum;          // KV pass only: fp32 [B*N, D]; non-null => dQ += dS K by red.add (no Q pass)
 };
 
 // kModeKV = true : CTA owns key block blockIdx.x; loops over query blocks; emits dK, dV.
@@ -297,7 +298,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     uint64_t* sdp_full = bars + 5;
     uint64_t* pds_full = bars + 6;
     uint64_t* pds_empty = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* dq_full = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const bool fuse_dq = kModeKV && p.dq_accum != nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int blk0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -308,7 +311,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         tma_prefetch_desc(&tmap_do);
         mbar_init(res_full, 1);
         for (int s = 0; s < 2; s++) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
-        mbar_init(sdp_full, 1); mbar_init(pds_full, 4); mbar_init(pds_empty, 1);
+        mbar_init(sdp_full, 1); mbar_init(pds_full, 4); mbar_init(pds_empty, 1); mbar_init(dq_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -316,7 +319,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base, tdP = tmem_base + 128, tAcc0 = tmem_base + 256, tAcc1 = tmem_base + 320;
+    const uint32_t tS = tmem_base, tdP = tmem_base + 128, tAcc0 = tmem_base + 256, tAcc1 = tmem_base + 320, tdQ = tmem_base + 384;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -376,6 +379,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                     for (int k = 0; k < (nq16 >> 4); k++)
                         umma_f16(tAcc1, make_smem_desc_sw128(adS + k * 2048, kTile, 1024),
                                  make_smem_desc_sw128(aQ + k * 2048, 8192, 1024), kIdescTT, (it > 0 || k > 0));
+                    if (fuse_dq) {
+                        // this key block's contribution to dQ_i = dS K_j, handed to the threads for red.add
+                        for (int k = 0; k < (nk16 >> 4); k++)
+                            umma_f16(tdQ, make_smem_desc_sw128(adS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+                                     make_smem_desc_sw128(aK + k * 2048, 8192, 1024), kIdescPV, k > 0);
+                        umma_commit(dq_full);
+                    }
                 } else {
                     // dQ[q, d] += dS K : A = dS K-major over keys, B = K_j as MN-major (N = d); K = keys
                     for (int k = 0; k < (nk16 >> 4); k++)
@@ -434,6 +444,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(pds_full);
+            if (fuse_dq) {
+                mbar_wait(dq_full, it & 1);
+                tc_fence_after();
+                if (nchunk > 0) {
+                    float* dst = p.dq_accum + (int64_t(b) * p.N + qrow) * p.D + h * 64;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tdQ + lane_off + c * 32, v);
+                        tmem_ld_wait();
+                        if (q_ok) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++)
+                                atomicAdd(reinterpret_cast<float4*>(dst + c * 32) + i,
+                                          make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                      __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                        }
+                    }
+                }
+                tc_fence_before();
+            }
         }
         // all accumulating MMAs of the last iteration have retired
         mbar_wait(pds_empty, (nblk - 1) & 1);
@@ -463,6 +494,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+
+// dq fp32 [rows, D] -> fp16 into the q columns of dqkv [rows, ld]
+__global__ void __launch_bounds__(256)
+dq_convert_kernel(const float* __restrict__ dq, __half* __restrict__ dqkv, int64_t rows, int D, int ld) {
+    const int vec_per_row = D >> 2;
+    const int64_t total = rows * vec_per_row;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t row = i / vec_per_row;
+        const int c = int(i % vec_per_row);
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(dq) + i);
+        reinterpret_cast<uint2*>(dqkv + row * ld)[c] =
+            make_uint2(pack_h2(sat16f(v.x), sat16f(v.y)), pack_h2(sat16f(v.z), sat16f(v.w)));
+    }
 }
 
 constexpr int kAttnFwdSmem = 5 * kTile + 1024 + 256;
@@ -498,7 +544,7 @@ extern "C" int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float
 }
 
 extern "C" int mv_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
-                                void* dqkv, int B, int H, int N, float scale, void* stream) {
+                                float* dq_accum, void* dqkv, int B, int H, int N, float scale, void* stream) {
     MV_CHECK(B > 0 && H > 0 && N > 0 && qkv && o && d_o && lse && delta && dqkv, "mv_attention_bwd: bad arguments");
     const int D = H * 64;
     static bool attr_done = false;
@@ -519,10 +565,24 @@ extern "C" int mv_attention_bwd(const void* qkv, const void* o, const void* d_o,
     p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.lse = lse; p.delta = delta;
     p.dqkv = reinterpret_cast<__half*>(dqkv); p.ld_dqkv = 3 * D;
+    p.dq_accum = dq_accum;
     dim3 grid((N + 127) / 128, H, B);
-    attn_bwd_kernel<true><<<grid, kAttThreads, kAttnBwdKVSmem, st>>>(tq, td, p);
-    g_launches++;
-    attn_bwd_kernel<false><<<grid, kAttThreads, kAttnBwdQSmem, st>>>(tq, td, p);
-    g_launches++;
+    if (dq_accum != nullptr) {
+        // one pass: dK, dV per key block and dQ accumulated across key blocks with fp32 red.add
+        const int64_t n = int64_t(B) * N * D;
+        MV_CUDA(cudaMemsetAsync(dq_accum, 0, sizeof(float) * n, st));
+        attn_bwd_kernel<true><<<grid, kAttThreads, kAttnBwdKVSmem, st>>>(tq, td, p);
+        g_launches++;
+        int64_t blocks = (n / 4 + 255) / 256;
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        dq_convert_kernel<<<int(blocks), 256, 0, st>>>(dq_accum, reinterpret_cast<__half*>(dqkv), int64_t(B) * N, D, 3 * D);
+        g_launches++;
+    } else {
+        // deterministic two-pass variant (no atomics): the Q pass recomputes S and dP
+        attn_bwd_kernel<true><<<grid, kAttThreads, kAttnBwdKVSmem, st>>>(tq, td, p);
+        g_launches++;
+        attn_bwd_kernel<false><<<grid, kAttThreads, kAttnBwdQSmem, st>>>(tq, td, p);
+        g_launches++;
+    }
     return check_cuda(cudaGetLastError(), "attention bwd launch");
 }

@@ -10,6 +10,8 @@
 //     dx = LN'(dy; q_in(x)) + dres,   dgamma += sum dy*xhat,   dbeta += sum dy,
 //     dbias_prev += sum dx   (bias gradient of the Linear that produced the residual stream)
 // HBM traffic per element: fwd 4 B read + 2 B write (fp16 container); bwd 12 B read + 6 B write.
+#include <type_traits>
+
 #include "common.cuh"
 #include "quant_dev.cuh"
 #include "../../include/mv_b200.h"
@@ -131,47 +133,95 @@ __device__ __forceinline__ float4 load_dy4(const __half* p, int c) {
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
+template <int NV, typename DyT> struct LnBwdRow {
+    float4 x[NV];
+    float4 dres[NV];
+    typename std::conditional<sizeof(DyT) == 2, uint2, float4>::type dy[NV];
+};
+__device__ __forceinline__ float4 unpack_dy(const float4& v) { return v; }
+__device__ __forceinline__ float4 unpack_dy(const uint2& u) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 template <int NV, typename DyT>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, 3)
 ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x, int64_t ld_x,
               const float* __restrict__ dres, int64_t ld_dres, const float* __restrict__ gamma,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               float* __restrict__ dx, int64_t ld_dx, __half* __restrict__ dx_lp, int64_t ld_lp,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias_prev,
               int rows, int D, FloatFmt q_in) {
-    extern __shared__ float red[];      // [kLnWarps][D] reused for the three column sums
+    // Column sums (dgamma, dbeta, previous bias grad) are kept per warp in shared memory — each
+    // lane owns its columns, so plain read-modify-write — which frees ~36 registers per thread for
+    // occupancy; the next row's loads are issued before the current row is reduced.
+    extern __shared__ float red[];      // [kLnWarps][3][D]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = D >> 2;
-    float4 g[NV], acc_g[NV], acc_b[NV], acc_p[NV];
+    const int mi = fq_mode(q_in);
+    const float inv_d = 1.0f / float(D);
+    float4* acc = reinterpret_cast<float4*>(red + size_t(warp) * 3 * D);
+    using dy_vec = typename std::conditional<sizeof(DyT) == 2, uint2, float4>::type;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         const int c = lane + 32 * i;
-        if (c < nvec) g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-        acc_g[i] = make_float4(0, 0, 0, 0); acc_b[i] = acc_g[i]; acc_p[i] = acc_g[i];
+        if (c < nvec) {
+            acc[c] = make_float4(0, 0, 0, 0); acc[nvec + c] = make_float4(0, 0, 0, 0); acc[2 * nvec + c] = make_float4(0, 0, 0, 0);
+        }
     }
-    for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
-        const float mean = mean_in[row], rstd = rstd_in[row];
+    const int rstride = gridDim.x * kLnWarps;
+    auto load_row = [&](int row, LnBwdRow<NV, DyT>& r) {
         const float4* xr = reinterpret_cast<const float4*>(x + int64_t(row) * ld_x);
-        const DyT* dyr = dy + int64_t(row) * ld_dy;
+        const dy_vec* dyr = reinterpret_cast<const dy_vec*>(dy + int64_t(row) * ld_dy);
+        const float4* rr = reinterpret_cast<const float4*>(dres + int64_t(row) * ld_dres);
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                r.x[i] = __ldcs(xr + c);
+                r.dy[i] = __ldcs(dyr + c);
+                if (dres != nullptr) r.dres[i] = __ldcs(rr + c);
+            }
+        }
+    };
+    int row = blockIdx.x * kLnWarps + warp;
+    LnBwdRow<NV, DyT> cur;
+    if (row < rows) load_row(row, cur);
+    for (; row < rows; row += rstride) {
+        LnBwdRow<NV, DyT> nxt;
+        const int nrow = row + rstride;
+        if (nrow < rows) load_row(nrow, nxt);
+        const float mean = mean_in[row], rstd = rstd_in[row];
         float4 xh[NV], gy[NV];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; i++) {
             const int c = lane + 32 * i;
             if (c < nvec) {
-                float4 xv = __ldcs(xr + c);
-                const float4 d = load_dy4(dyr, c);
-                xv.x = (fq_nearest(xv.x, q_in) - mean) * rstd; xv.y = (fq_nearest(xv.y, q_in) - mean) * rstd;
-                xv.z = (fq_nearest(xv.z, q_in) - mean) * rstd; xv.w = (fq_nearest(xv.w, q_in) - mean) * rstd;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+                const float4 d = unpack_dy(cur.dy[i]);
+                float4 xv = cur.x[i];
+                xv.x = (fq_apply(xv.x, mi, q_in) - mean) * rstd; xv.y = (fq_apply(xv.y, mi, q_in) - mean) * rstd;
+                xv.z = (fq_apply(xv.z, mi, q_in) - mean) * rstd; xv.w = (fq_apply(xv.w, mi, q_in) - mean) * rstd;
                 xh[i] = xv;
-                acc_g[i].x += d.x * xv.x; acc_g[i].y += d.y * xv.y; acc_g[i].z += d.z * xv.z; acc_g[i].w += d.w * xv.w;
-                acc_b[i].x += d.x; acc_b[i].y += d.y; acc_b[i].z += d.z; acc_b[i].w += d.w;
-                gy[i] = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+                float4 a = acc[c];
+                a.x = fmaf(d.x, xv.x, a.x); a.y = fmaf(d.y, xv.y, a.y); a.z = fmaf(d.z, xv.z, a.z); a.w = fmaf(d.w, xv.w, a.w);
+                acc[c] = a;
+                float4 bsum = acc[nvec + c];
+                bsum.x += d.x; bsum.y += d.y; bsum.z += d.z; bsum.w += d.w;
+                acc[nvec + c] = bsum;
+                gy[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
                 s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
                 s2 += (gy[i].x * xv.x + gy[i].y * xv.y) + (gy[i].z * xv.z + gy[i].w * xv.w);
             }
         }
-        const float m1 = warp_sum(s1) / float(D), m2 = warp_sum(s2) / float(D);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        const float m1 = s1 * inv_d, m2 = s2 * inv_d;
         float* dxr = dx + int64_t(row) * ld_dx;
 #pragma unroll
         for (int i = 0; i < NV; i++) {
@@ -181,38 +231,32 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
                 o.x = rstd * (gy[i].x - m1 - xh[i].x * m2); o.y = rstd * (gy[i].y - m1 - xh[i].y * m2);
                 o.z = rstd * (gy[i].z - m1 - xh[i].z * m2); o.w = rstd * (gy[i].w - m1 - xh[i].w * m2);
                 if (dres != nullptr) {
-                    const float4 r = __ldcs(reinterpret_cast<const float4*>(dres + int64_t(row) * ld_dres) + c);
+                    const float4 r = cur.dres[i];
                     o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                 }
-                acc_p[i].x += o.x; acc_p[i].y += o.y; acc_p[i].z += o.z; acc_p[i].w += o.w;
-                reinterpret_cast<float4*>(dxr)[c] = o;
+                float4 ps = acc[2 * nvec + c];
+                ps.x += o.x; ps.y += o.y; ps.z += o.z; ps.w += o.w;
+                acc[2 * nvec + c] = ps;
+                __stcs(reinterpret_cast<float4*>(dxr) + c, o);
                 if (dx_lp != nullptr) {
                     __half2 lo = __floats2half2_rn(sat16(o.x), sat16(o.y)), hi = __floats2half2_rn(sat16(o.z), sat16(o.w));
-                    reinterpret_cast<uint2*>(dx_lp + int64_t(row) * ld_lp)[c] =
-                        make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                    __stcs(reinterpret_cast<uint2*>(dx_lp + int64_t(row) * ld_lp) + c,
+                           make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi)));
                 }
             }
         }
+        cur = nxt;
     }
-    // CTA-level column reduction, one quantity at a time
+    __syncthreads();
+    // CTA-level column reduction over the warps, then one atomic per column per CTA
     for (int which = 0; which < 3; which++) {
         float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias_prev);
-        if (dst == nullptr) continue;       // uniform across the CTA
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < NV; i++) {
-            const int c = lane + 32 * i;
-            if (c < nvec) {
-                const float4 a = which == 0 ? acc_g[i] : (which == 1 ? acc_b[i] : acc_p[i]);
-                reinterpret_cast<float4*>(red + warp * D)[c] = a;
-            }
-        }
-        __syncthreads();
+        if (dst == nullptr) continue;
         for (int c = threadIdx.x; c < D; c += blockDim.x) {
-            float s = 0.f;
+            float sacc = 0.f;
 #pragma unroll
-            for (int w = 0; w < kLnWarps; w++) s += red[w * D + c];
-            atomicAdd(dst + c, s);
+            for (int w = 0; w < kLnWarps; w++) sacc += red[(size_t(w) * 3 + which) * D + c];
+            atomicAdd(dst + c, sacc);
         }
     }
 }
@@ -362,9 +406,15 @@ static int launch_ln_bwd(const void* dy, int dy_dtype, int64_t ld_dy, const floa
                          float* dx, int64_t ld_dx, void* dx_lp, int64_t ld_lp, float* dgamma, float* dbeta,
                          float* dbias_prev, int rows, int D, FloatFmt q_in, cudaStream_t st) {
     int grid = (rows + kLnWarps - 1) / kLnWarps;
-    const int cap = kNumSMs * 4;
+    const int cap = kNumSMs * 3;
     if (grid > cap) grid = cap;
-    const size_t smem = size_t(kLnWarps) * D * sizeof(float);
+    const size_t smem = size_t(kLnWarps) * 3 * D * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(ln_bwd_kernel<NV, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnWarps * 3 * 128 * kLnMaxVec * 4);
+        cudaFuncSetAttribute(ln_bwd_kernel<NV, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnWarps * 3 * 128 * kLnMaxVec * 4);
+        attr_done = true;
+    }
     if (dy_dtype == MV_F16)
         ln_bwd_kernel<NV, __half><<<grid, kLnWarps * 32, smem, st>>>((const __half*)dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx,
                                                                     (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in);

@@ -342,7 +342,8 @@ def attention_fwd(qkv, B, H, N, *, scale=0.125, q_out=None, out_dtype=torch.floa
     return out, lse
 
 
-def attention_bwd(qkv, o, d_o, lse, B, H, N, *, scale=0.125, dqkv=None, delta=None):
+def attention_bwd(qkv, o, d_o, lse, B, H, N, *, scale=0.125, dqkv=None, delta=None,
+                  deterministic=False, dq_accum=None):
     """d_o fp16 [B*N, D] -> dqkv fp16 [B*N, 3D] (dq | dk | dv)."""
     _need_cuda(qkv, o, d_o, lse)
     assert qkv.dtype == torch.float16 and o.dtype == torch.float16 and d_o.dtype == torch.float16
@@ -351,8 +352,11 @@ def attention_bwd(qkv, o, d_o, lse, B, H, N, *, scale=0.125, dqkv=None, delta=No
         dqkv = torch.empty_like(qkv)
     if delta is None:
         delta = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
+    if not deterministic and dq_accum is None:
+        dq_accum = torch.empty(B * N, H * 64, dtype=torch.float32, device=qkv.device)
     with _timed("attn_bwd"):
-        rc = lib().mv_attention_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(delta), _ptr(dqkv), B,
+        rc = lib().mv_attention_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(delta),
+                                    None if deterministic else _ptr(dq_accum), _ptr(dqkv), B,
                                     H, N, ctypes.c_float(scale), _stream())
     _check(rc, "mv_attention_bwd")
     return dqkv

@@ -126,10 +126,11 @@ def test_attention_fwd_bwd(B, H, N):
     assert (lse.double() - torch.logsumexp(s, -1) * 1.4426950408889634).abs().max() < 1e-3
     do = torch.randn(B * N, D, device=dev).half()
     o.backward(do.double())
-    dqkv = mv.attention_bwd(qkv, out, do, lse, B, H, N)
-    gq = dqkv.double().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
-    for got, ref in zip(gq, (q.grad, k.grad, v.grad)):
-        assert relmax(got, ref) < 3e-3
+    for det in (False, True):           # fused dQ red.add pass / deterministic two-pass variant
+        dqkv = mv.attention_bwd(qkv, out, do, lse, B, H, N, deterministic=det)
+        gq = dqkv.double().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+        for got, ref in zip(gq, (q.grad, k.grad, v.grad)):
+            assert relmax(got, ref) < 3e-3
     # quantised output variant is exactly the quantisation of the plain one (same accumulators)
     outq, _ = mv.attention_fwd(qkv, B, H, N, q_out=(5, 10))
     assert relmax(outq, o) < 2e-3
