@@ -181,8 +181,10 @@ def run_b200(args):
     n0 = mv_native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         step(*resident[i % 2])
+    host_enqueue_ms = (time.perf_counter() - t_host0) / args.steps * 1e3
     e1.record()
     barrier()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
@@ -291,6 +293,7 @@ def run_b200(args):
         "e2e": {"value": world * B / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "last_loss": loss_host},
         "gpu_launches": launches,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "model_tflops": value * fl / 1e12,
         "roofline": roofline,
         "kernels": breakdown,
