@@ -172,10 +172,7 @@ def run_b200(args):
 
     for i in range(args.warmup):
         step(*resident[i % 2])
-    # ---- timed region 1: inputs resident in HBM
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # ---- eager region: per-kernel-class CUDA-event timing (roofline / breakdown) + host enqueue cost
     mv_native.enable_timing(rank == 0 and not args.no_kernel_timing)
     barrier()
     n0 = mv_native.launch_count()
@@ -187,10 +184,32 @@ def run_b200(args):
     host_enqueue_ms = (time.perf_counter() - t_host0) / args.steps * 1e3
     e1.record()
     barrier()
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    launches = mv_native.launch_count() - n0
+    ms_eager = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches_per_step = (mv_native.launch_count() - n0) // args.steps
     kern = mv_native.timing_summary()
     mv_native.enable_timing(False)
+
+    # ---- timed region 1 (`value`): the same step captured in a CUDA graph, inputs resident in HBM
+    use_graph = not args.no_graph
+    if use_graph:
+        from myrtle_vision.utils.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(net, F.cross_entropy, resident[0][0], resident[0][1])
+        run_step = lambda img, y: gstep(img, y)
+    else:
+        run_step = step
+    for i in range(args.warmup):
+        run_step(*resident[i % 2])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        run_step(*resident[i % 2])
+    e1.record()
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- timed region 2 (e2e): every step copies its batch from pinned host memory (prefetched one
@@ -220,7 +239,7 @@ def run_b200(args):
         if i + 1 < args.steps:
             prefetch(i + 1)
         torch.cuda.current_stream().wait_event(ready[s])
-        loss = step(*bufs[s])
+        loss = run_step(*bufs[s])
         consumed[s].record()
         loss_host = loss.item()                       # device -> host read of the step result
     t_e2e1.record()
@@ -288,12 +307,15 @@ def run_b200(args):
         "config": {"workload": "ViT-Small cls 256x256x3, 45 classes, q_format=%s, batch %d/GPU, fwd+CE+bwd%s"
                                % (args.q_format, B, " + NCCL grad all-reduce" if world > 1 else ""),
                    "global_batch": world * B, "parallelism": "dp%d" % world,
+                   "launch": "whole step captured in one CUDA graph (myrtle_vision.utils.graph.GraphedTrainStep)" if use_graph else "eager launches",
                    "l2": "per-step working set (~11 GB of activations) >> 126 MB L2; two alternating input batches"},
         "clocks": clocks,
         "e2e": {"value": world * B / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "last_loss": loss_host},
         "gpu_launches": launches,
-        "host_enqueue_ms_per_step": host_enqueue_ms,
+        "cuda_graph": use_graph,
+        "eager_ms_per_step": ms_eager,
+        "host_enqueue_ms_per_step_eager": host_enqueue_ms,
         "model_tflops": value * fl / 1e12,
         "roofline": roofline,
         "kernels": breakdown,
@@ -314,6 +336,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eagerly launched step instead of the CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -77,8 +77,11 @@ class EncoderEngine:
         idx = self._weight_indices()
         versions = tuple(self.params[i]._version for i in idx) + tuple(
             self.params[i].data_ptr() for i in idx)
-        if self._wq is not None and versions == self._wq_versions:
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self._wq is not None and versions == self._wq_versions and not capturing:
             return self._wq
+        if capturing and getattr(self, "_wq_capture_done", None) == id(torch.cuda.current_stream()):
+            return self._wq          # already re-quantised once inside this capture (forward)
         wq = {}
         for i in idx:
             w = self.params[i].detach()
@@ -87,6 +90,9 @@ class EncoderEngine:
                                        out_t=old[1] if old else None)
             wq[i] = (q, qt)
         self._wq, self._wq_versions = wq, versions
+        # inside a CUDA-graph capture the re-quantisation must be part of the graph (weights change
+        # between replays) but only once per step: backward reuses the forward's operands
+        self._wq_capture_done = id(torch.cuda.current_stream()) if capturing else None
         return wq
 
     # ------------------------------------------------------------------ forward
