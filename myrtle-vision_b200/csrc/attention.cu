@@ -496,6 +496,204 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward, 64-key blocks: 80 KB of shared memory and 256 TMEM columns per CTA so that two CTAs
+// share an SM (one CTA's exp/dS math overlaps the other's MMAs and TMA loads).  CTA = (64 keys, head,
+// image); loops over 128-row query blocks; dK, dV accumulate in TMEM (lanes 0-63), dQ_i = dS K_j is
+// produced per iteration into the (dead) S columns and red.add-ed into an fp32 buffer.
+constexpr uint32_t kIdescTT64 = make_idesc(0, 0, 1, 1, 128, 64);
+
+__global__ void __launch_bounds__(kAttThreads, 2)
+attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv64,
+                  const __grid_constant__ CUtensorMap tmap_do, const AttnBwdDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // order matters: the MN-major M=128 A descriptors of P / dS step one tile (LBO) past their own
+    // 64-key tile for the unused upper 64 rows; that neighbour must hold finite data (dS, then Q)
+    uint8_t* sP = smem;                        // [128 q][64 keys] fp16
+    uint8_t* sdS = smem + kTile;
+    uint8_t* sQ = smem + 2 * kTile;            // ring: Q_i
+    uint8_t* sdO = smem + 3 * kTile;           // ring: dO_i
+    uint8_t* sK = smem + 4 * kTile;            // resident K_j  [64 keys][64 d] (8 KB)
+    uint8_t* sV = smem + 4 * kTile + 8192;     // resident V_j
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTile);
+    uint64_t* res_full = bars;
+    uint64_t* ring_full = bars + 1;
+    uint64_t* ring_empty = bars + 2;
+    uint64_t* sdp_full = bars + 3;
+    uint64_t* pds_full = bars + 4;
+    uint64_t* pds_empty = bars + 5;
+    uint64_t* dq_full = bars + 6;
+    uint64_t* dq_done = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.N + 127) / 128;                      // query blocks
+    const int nk16 = (min(64, p.N - blk0) + 15) & ~15;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q128); tma_prefetch_desc(&tmap_kv64); tma_prefetch_desc(&tmap_do);
+        mbar_init(res_full, 1); mbar_init(ring_full, 1); mbar_init(ring_empty, 1);
+        mbar_init(sdp_full, 1); mbar_init(pds_full, 4); mbar_init(pds_empty, 1);
+        mbar_init(dq_full, 1); mbar_init(dq_done, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdV = tmem_base + 128, tdK = tmem_base + 192;
+    const uint32_t tdQ = tS;                                   // S is dead once P / dS are in smem
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(res_full, 16384);
+            tma_load_3d(sK, &tmap_kv64, res_full, p.D + h * 64, blk0, b);
+            tma_load_3d(sV, &tmap_kv64, res_full, 2 * p.D + h * 64, blk0, b);
+            for (int it = 0; it < nblk; it++) {
+                mbar_wait(ring_empty, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(ring_full, 2 * kTile);
+                tma_load_3d(sQ, &tmap_q128, ring_full, h * 64, it * 128, b);
+                tma_load_3d(sdO, &tmap_do, ring_full, h * 64, it * 128, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS), aQ = smem_u32(sQ), aDO = smem_u32(sdO),
+                           aK = smem_u32(sK), aV = smem_u32(sV);
+            const uint32_t idesc_s = make_idesc(0, 0, 0, 0, 128, nk16);
+            mbar_wait(res_full, 0);
+            for (int it = 0; it < nblk; it++) {
+                const int nq16 = (min(128, p.N - it * 128) + 15) & ~15;
+                mbar_wait(ring_full, it & 1);
+                if (it > 0) mbar_wait(dq_done, (it - 1) & 1);        // dQ tile (aliasing S) has been read
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    umma_f16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    umma_f16(tdP, make_smem_desc_sw128(aDO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), idesc_s, k > 0);
+                umma_commit(sdp_full);
+                mbar_wait(pds_full, it & 1);
+                tc_fence_after();
+                // dV[keys, d] += P^T dO ; dK[keys, d] += dS^T Q   (M = 128: rows 64..127 are don't-care)
+                for (int k = 0; k < (nq16 >> 4); k++)
+                    umma_f16(tdV, make_smem_desc_sw128(aP + k * 2048, kTile, 1024),
+                             make_smem_desc_sw128(aDO + k * 2048, 8192, 1024), kIdescTT64, (it > 0 || k > 0));
+                for (int k = 0; k < (nq16 >> 4); k++)
+                    umma_f16(tdK, make_smem_desc_sw128(adS + k * 2048, kTile, 1024),
+                             make_smem_desc_sw128(aQ + k * 2048, 8192, 1024), kIdescTT64, (it > 0 || k > 0));
+                // dQ_i contribution of this key block = dS K_j
+                for (int k = 0; k < (nk16 >> 4); k++)
+                    umma_f16(tdQ, make_smem_desc_sw128(adS + k * 32, 16, 1024),
+                             make_smem_desc_sw128(aK + k * 2048, 8192, 1024), kIdescPV, k > 0);
+                umma_commit(dq_full);
+                umma_commit(ring_empty);
+                umma_commit(pds_empty);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_off = uint32_t(quad * 32) << 16;
+        for (int it = 0; it < nblk; it++) {
+            const int qrow = it * 128 + r;
+            const bool q_ok = qrow < p.N;
+            const int nq16 = (min(128, p.N - it * 128) + 15) & ~15;
+            const int nchunk = (quad * 32 < nq16) ? ((nk16 + 31) >> 5) : 0;
+            float L = 0.f, dl = 0.f;
+            if (q_ok) {
+                const int64_t si = (int64_t(b) * p.H + h) * p.N + qrow;
+                L = p.lse[si]; dl = p.delta[si];
+            }
+            mbar_wait(sdp_full, it & 1);
+            tc_fence_after();
+            mbar_wait(pds_empty, (it & 1) ^ 1);
+#pragma unroll 1
+            for (int c = 0; c < nchunk; c++) {
+                uint32_t s[32], dp[32];
+                tmem_ld_32x32(tS + lane_off + c * 32, s);
+                tmem_ld_32x32(tdP + lane_off + c * 32, dp);
+                tmem_ld_wait();
+                uint32_t wp[16], wd[16];
+#pragma unroll
+                for (int t = 0; t < 16; t++) {
+                    float pv[2], dv[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const bool ok = q_ok && (blk0 + c * 32 + 2 * t + u < p.N);
+                        const float pe = ok ? exp2f(fmaf(__uint_as_float(s[2 * t + u]), p.scale_log2, -L)) : 0.f;
+                        pv[u] = pe;
+                        dv[u] = ok ? sat16f(pe * (__uint_as_float(dp[2 * t + u]) - dl) * p.scale) : 0.f;
+                    }
+                    wp[t] = pack_h2(pv[0], pv[1]);
+                    wd[t] = pack_h2(dv[0], dv[1]);
+                }
+                store_p_chunk(sdS, r, c, wd);
+                store_p_chunk(sP, r, c, wp);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pds_full);
+            // dQ contribution: TMEM -> fp32 red.add
+            mbar_wait(dq_full, it & 1);
+            tc_fence_after();
+            if (nchunk > 0) {
+                float* dst = p.dq_accum + (int64_t(b) * p.N + qrow) * p.D + h * 64;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tdQ + lane_off + c * 32, v);
+                    tmem_ld_wait();
+                    if (q_ok) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            atomicAdd(reinterpret_cast<float4*>(dst + c * 32) + i,
+                                      make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_done);
+        }
+        mbar_wait(pds_empty, (nblk - 1) & 1);
+        tc_fence_after();
+        const int key = blk0 + r;
+        if (quad < 2) {                        // TMEM lanes 0..63 hold this CTA's 64 keys
+            for (int a = 0; a < 2; a++) {
+                uint32_t v[32];
+                const int col = (a == 0 ? 2 : 1) * p.D + h * 64;       // dV | dK
+                __half* dst = p.dqkv + (int64_t(b) * p.N + key) * p.ld_dqkv + col;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    tmem_ld_32x32((a == 0 ? tdV : tdK) + lane_off + c * 32, v);
+                    tmem_ld_wait();
+                    if (key < p.N) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            reinterpret_cast<uint4*>(dst + c * 32)[i] =
+                                make_uint4(pack_h2(sat16f(__uint_as_float(v[8 * i])), sat16f(__uint_as_float(v[8 * i + 1]))),
+                                           pack_h2(sat16f(__uint_as_float(v[8 * i + 2])), sat16f(__uint_as_float(v[8 * i + 3]))),
+                                           pack_h2(sat16f(__uint_as_float(v[8 * i + 4])), sat16f(__uint_as_float(v[8 * i + 5]))),
+                                           pack_h2(sat16f(__uint_as_float(v[8 * i + 6])), sat16f(__uint_as_float(v[8 * i + 7]))));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem_base); }
+}
+
+constexpr int kAttnBwd64Smem = 5 * kTile + 1024 + 256;
+
 // dq fp32 [rows, D] -> fp16 into the q columns of dqkv [rows, ld]
 __global__ void __launch_bounds__(256)
 dq_convert_kernel(const float* __restrict__ dq, __half* __restrict__ dqkv, int64_t rows, int D, int ld) {
@@ -551,6 +749,7 @@ extern "C" int mv_attention_bwd(const void* qkv, const void* o, const void* d_o,
     if (!attr_done) {
         MV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdKVSmem));
         MV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdQSmem));
+        MV_CUDA(cudaFuncSetAttribute(attn_bwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwd64Smem));
         attr_done = true;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -571,7 +770,10 @@ extern "C" int mv_attention_bwd(const void* qkv, const void* o, const void* d_o,
         // one pass: dK, dV per key block and dQ accumulated across key blocks with fp32 red.add
         const int64_t n = int64_t(B) * N * D;
         MV_CUDA(cudaMemsetAsync(dq_accum, 0, sizeof(float) * n, st));
-        attn_bwd_kernel<true><<<grid, kAttThreads, kAttnBwdKVSmem, st>>>(tq, td, p);
+        CUtensorMap tk64;
+        if (make_tmap_3d(&tk64, qkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 64, 1)) return 1;
+        dim3 grid64((N + 63) / 64, H, B);
+        attn_bwd64_kernel<<<grid64, kAttThreads, kAttnBwd64Smem, st>>>(tq, tk64, td, p);
         g_launches++;
         int64_t blocks = (n / 4 + 255) / 256;
         if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
