@@ -102,6 +102,7 @@ typedef struct {
     int accumulate;               /* split-K atomic accumulation into fp32 `out` */
     int rows_per_img;             /* residual row = m % rows_per_img when > 0 */
     int tile_n;                   /* 0 = auto; 128 forces 128-wide tiles (testing) */
+    int cluster;                  /* 2 = CTA pairs share the B tile by TMA multicast (opt-in; not faster on B200) */
 } mv_gemm_args;
 
 int mv_gemm(const mv_gemm_args* args, void* stream);

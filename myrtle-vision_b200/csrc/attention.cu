@@ -35,6 +35,18 @@ constexpr uint32_t kIdescPV = make_idesc(0, 0, 0, 1, 128, 64);     // A K-major,
 constexpr uint32_t kIdescTT = make_idesc(0, 0, 1, 1, 128, 64);     // A MN-major, B MN-major, N=64
 
 __device__ __forceinline__ float sat16f(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+// single-instruction MUFU.EX2 (exp2f() adds denormal range handling the softmax does not need)
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// {lo, hi} -> packed fp16x2 with saturation to +-65504 in one F2FP
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -167,17 +179,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdDev p
                 const int nchunk = (nk16 + 31) >> 5;
                 // pass 1: row max of the scaled scores
                 float mx = -INFINITY;
+                const bool full_blk = kbase + 128 <= p.N;       // only the last block needs key masking
 #pragma unroll 1
                 for (int c = 0; c < nchunk; c++) {
                     uint32_t s[32];
                     tmem_ld_32x32(tS + lane_off + c * 32, s);
                     tmem_ld_wait();
+                    if (full_blk) {
 #pragma unroll
-                    for (int t = 0; t < 32; t++)
-                        if (kbase + c * 32 + t < p.N) mx = fmaxf(mx, __uint_as_float(s[t]));
+                        for (int t = 0; t < 32; t++) mx = fmaxf(mx, __uint_as_float(s[t]));
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 32; t++)
+                            if (kbase + c * 32 + t < p.N) mx = fmaxf(mx, __uint_as_float(s[t]));
+                    }
                 }
                 const float m_new = fmaxf(m, mx * p.scale_log2);
-                const float alpha = exp2f(m - m_new);          // m = -inf on the first block -> 0
+                const float alpha = ex2_fast(m - m_new);         // m = -inf on the first block -> 0
                 float psum = 0.f;
                 // pass 2: P = exp2(s*c - m_new) -> fp16 -> swizzled smem (A operand of P.V)
 #pragma unroll 1
@@ -186,16 +204,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdDev p
                     tmem_ld_32x32(tS + lane_off + c * 32, s);
                     tmem_ld_wait();
                     uint32_t w[16];
+                    if (full_blk) {
 #pragma unroll
-                    for (int t = 0; t < 16; t++) {
-                        const int k0 = kbase + c * 32 + 2 * t;
-                        const float p0 = k0 < p.N ? exp2f(fmaf(__uint_as_float(s[2 * t]), p.scale_log2, -m_new)) : 0.f;
-                        const float p1 = k0 + 1 < p.N ? exp2f(fmaf(__uint_as_float(s[2 * t + 1]), p.scale_log2, -m_new)) : 0.f;
-                        // accumulate the row sum from the fp16-rounded values the MMA will see
-                        const __half2 hp = __floats2half2_rn(p0, p1);
-                        const float2 fp = __half22float2(hp);
-                        psum += fp.x + fp.y;
-                        w[t] = *reinterpret_cast<const uint32_t*>(&hp);
+                        for (int t = 0; t < 16; t++) {
+                            const float p0 = ex2_fast(fmaf(__uint_as_float(s[2 * t]), p.scale_log2, -m_new));
+                            const float p1 = ex2_fast(fmaf(__uint_as_float(s[2 * t + 1]), p.scale_log2, -m_new));
+                            psum += p0 + p1;
+                            w[t] = pack_h2(p0, p1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 16; t++) {
+                            const int k0 = kbase + c * 32 + 2 * t;
+                            const float p0 = k0 < p.N ? ex2_fast(fmaf(__uint_as_float(s[2 * t]), p.scale_log2, -m_new)) : 0.f;
+                            const float p1 = k0 + 1 < p.N ? ex2_fast(fmaf(__uint_as_float(s[2 * t + 1]), p.scale_log2, -m_new)) : 0.f;
+                            psum += p0 + p1;
+                            w[t] = pack_h2(p0, p1);
+                        }
                     }
                     store_p_chunk(sP, r, c, w);
                 }
@@ -430,12 +455,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         const bool ok = q_ok && (kbase + c * 32 + 2 * t + u < p.N);
-                        const float pe = ok ? exp2f(__uint_as_float(s[2 * t + u]) * p.scale_log2 - L) : 0.f;
+                        const float pe = ok ? ex2_fast(fmaf(__uint_as_float(s[2 * t + u]), p.scale_log2, -L)) : 0.f;
                         pv[u] = pe;
-                        dv[u] = ok ? sat16f(pe * (__uint_as_float(dp[2 * t + u]) - dl) * p.scale) : 0.f;
+                        dv[u] = pe * (__uint_as_float(dp[2 * t + u]) - dl) * p.scale;
                     }
                     wp[t] = pack_h2(pv[0], pv[1]);
-                    wd[t] = pack_h2(dv[0], dv[1]);
+                    wd[t] = pack_h2_sat(dv[0], dv[1]);
                 }
                 store_p_chunk(sdS, r, c, wd);
                 if (kModeKV) store_p_chunk(sP, r, c, wp);
@@ -625,12 +650,12 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_co
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         const bool ok = q_ok && (blk0 + c * 32 + 2 * t + u < p.N);
-                        const float pe = ok ? exp2f(fmaf(__uint_as_float(s[2 * t + u]), p.scale_log2, -L)) : 0.f;
+                        const float pe = ok ? ex2_fast(fmaf(__uint_as_float(s[2 * t + u]), p.scale_log2, -L)) : 0.f;
                         pv[u] = pe;
-                        dv[u] = ok ? sat16f(pe * (__uint_as_float(dp[2 * t + u]) - dl) * p.scale) : 0.f;
+                        dv[u] = pe * (__uint_as_float(dp[2 * t + u]) - dl) * p.scale;
                     }
                     wp[t] = pack_h2(pv[0], pv[1]);
-                    wd[t] = pack_h2(dv[0], dv[1]);
+                    wd[t] = pack_h2_sat(dv[0], dv[1]);
                 }
                 store_p_chunk(sdS, r, c, wd);
                 store_p_chunk(sP, r, c, wp);

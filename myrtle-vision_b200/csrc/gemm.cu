@@ -160,7 +160,11 @@ __device__ __forceinline__ void store_out(void* base, int dtype, int64_t row, in
 }
 
 // kEsz: operand element size (2: f16/bf16, kind::f16; 4: tf32-in-fp32, kind::tf32)
-template <int BN, int kEsz>
+// kCluster: CTA pairs (cluster 2x1x1) work on vertically adjacent tiles that share the B tile; each CTA
+// fetches half of it and TMA-multicasts it into both CTAs' shared memory (halves the L2->SM traffic
+// of B, the bound of these small-K GEMMs).  MMAs stay per-CTA (cta_group::1); a stage is recycled
+// when both CTAs' MMAs have released it (multicast tcgen05.commit onto both empty barriers).
+template <int BN, int kEsz, bool kCluster>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmDev p) {
@@ -186,26 +190,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kCluster ? 2 : 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (kCluster) cluster_sync_all();          // the peer's barriers exist before anything lands on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_units = p.m_tiles * p.n_tiles * p.splits;
+    // work units: (tile pair, k split); both CTAs of a cluster walk the same unit sequence
+    const int ncta = kCluster ? 2 : 1;
+    const int cta_rank = kCluster ? int(cluster_ctarank()) : 0;
+    const int unit0 = blockIdx.x / ncta, unit_stride = gridDim.x / ncta;
+    const int total_units = ((p.m_tiles + ncta - 1) / ncta) * p.n_tiles * p.splits;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            for (int u = unit0; u < total_units; u += unit_stride) {
                 const int split = u % p.splits;
                 const int tile = u / p.splits;
-                const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+                const int m0 = ((tile / p.n_tiles) * ncta + cta_rank) * BM, n0 = (tile % p.n_tiles) * BN;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; kb++) {
@@ -221,13 +230,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                             tma_load_2d(sa + c * kMnBoxBytes, &tmap_a, &full_bar[stage], m0 + c * kMnChunk, kb * BK);
                     }
                     if (p.b_major == 0) {
+                        // two half-tiles of BN/2 rows; in cluster mode each CTA fetches one and multicasts it
 #pragma unroll
-                        for (int c = 0; c < BN / 128; c++)
-                            tma_load_2d(sb + c * kATileBytes, &tmap_b, &full_bar[stage], kb * BK, n0 + c * 128);
+                        for (int c = 0; c < 2; c++) {
+                            uint8_t* dst = sb + c * (BN / 2) * 128;
+                            if (!kCluster) tma_load_2d(dst, &tmap_b, &full_bar[stage], kb * BK, n0 + c * (BN / 2));
+                            else if (c == cta_rank) tma_load_2d_mc(dst, &tmap_b, &full_bar[stage], kb * BK, n0 + c * (BN / 2), 3);
+                        }
                     } else {
+                        constexpr int kChunks = BN / kMnChunk;
 #pragma unroll
-                        for (int c = 0; c < BN / kMnChunk; c++)
-                            tma_load_2d(sb + c * kMnBoxBytes, &tmap_b, &full_bar[stage], n0 + c * kMnChunk, kb * BK);
+                        for (int c = 0; c < kChunks; c++) {
+                            uint8_t* dst = sb + c * kMnBoxBytes;
+                            if (!kCluster) tma_load_2d(dst, &tmap_b, &full_bar[stage], n0 + c * kMnChunk, kb * BK);
+                            else if (c / (kChunks / 2) == cta_rank) tma_load_2d_mc(dst, &tmap_b, &full_bar[stage], n0 + c * kMnChunk, kb * BK, 3);
+                        }
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -243,7 +260,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             // MN elements one TMA box further (LBO); K advance = UMMA_K rows.
             const uint32_t a_lbo = p.a_major ? kMnBoxBytes : 16, b_lbo = p.b_major ? kMnBoxBytes : 16;
             const uint32_t a_kstep = p.a_major ? UMMA_K * 128 : 32, b_kstep = p.b_major ? UMMA_K * 128 : 32;
-            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            for (int u = unit0; u < total_units; u += unit_stride) {
                 const int split = u % p.splits;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -263,7 +280,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         if (kEsz == 2) umma_f16(tmem_d, adesc, bdesc, p.idesc, accum);
                         else umma_tf32(tmem_d, adesc, bdesc, p.idesc, accum);
                     }
-                    umma_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
+                    if (kCluster) umma_commit_mc(&empty_bar[stage], 3);    // both CTAs' producers wait for both MMAs
+                    else umma_commit(&empty_bar[stage]);       // frees the smem slot when the MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tmem_full[acc]);                  // accumulator ready for the epilogue
@@ -280,9 +298,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
         const int mode_out = fq_mode(p.q_out), mode_res = fq_mode(p.q_res);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        for (int u = unit0; u < total_units; u += unit_stride) {
             const int tile = u / p.splits;
-            const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+            const int m0 = ((tile / p.n_tiles) * ncta + cta_rank) * BM, n0 = (tile % p.n_tiles) * BN;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int m = m0 + quad * 32 + lane;
@@ -399,6 +417,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (kCluster) cluster_sync_all();          // no CTA exits while its peer may still write into it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<2 * BN>(tmem_base);
@@ -419,9 +438,11 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     const int BK = 128 / esz;
     static bool attr_done = false;
     if (!attr_done) {
-        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem));
-        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem));
-        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmem));
         attr_done = true;
     }
     // 128x256 tiles cut the L2->SM operand traffic per flop by a quarter; use them when N tiles evenly
@@ -434,7 +455,7 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     // MN-major operand stored [K, M|N]: box = BK k-rows x 128 B of M|N.
     if (a->a_major == 0) { if (make_tmap_2d(&ta, a->A, a->a_dtype, a->M, a->K, a->lda, BM, BK)) return 1; }
     else                 { if (make_tmap_2d(&ta, a->A, a->a_dtype, a->K, a->M, a->lda, BK, 128 / esz)) return 1; }
-    if (a->b_major == 0) { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->N, a->K, a->ldb, 128, BK)) return 1; }
+    if (a->b_major == 0) { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->N, a->K, a->ldb, BN / 2, BK)) return 1; }
     else                 { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->K, a->N, a->ldb, BK, 128 / esz)) return 1; }
 
     GemmDev p;
@@ -465,12 +486,37 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     p.accumulate = a->accumulate;
     p.rows_per_img = a->rows_per_img;
 
-    const int units = p.m_tiles * p.n_tiles * p.splits;
-    const int grid = units < kNumSMs ? units : kNumSMs;
+    // CTA pairs sharing B through TMA multicast: measured no faster on B200 (the bound is the per-SM
+    // L2->SM ingest, which multicast does not reduce), so it is opt-in (cluster == 2)
+    const bool cluster = !tf32 && p.m_tiles >= 2 && a->cluster == 2;
+    const int ncta = cluster ? 2 : 1;
+    int splits2 = p.splits;
+    if (cluster && a->accumulate) {
+        // re-derive the k split for pair units
+        const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+        int sp = (kNumSMs / 2) / pairs;
+        if (sp < 1) sp = 1;
+        if (sp > p.kb_total) sp = p.kb_total;
+        p.kb_per_split = (p.kb_total + sp - 1) / sp;
+        p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+        splits2 = p.splits;
+    }
+    const int units = ((p.m_tiles + ncta - 1) / ncta) * p.n_tiles * splits2;
+    int grid = units * ncta < kNumSMs ? units * ncta : kNumSMs;
+    grid -= grid % ncta;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (tf32) gemm_kernel<128, 4><<<grid, kGemmThreads, GemmCfg<128>::kSmem, st>>>(ta, tb, p);
-    else if (BN == 256) gemm_kernel<256, 2><<<grid, kGemmThreads, GemmCfg<256>::kSmem, st>>>(ta, tb, p);
-    else gemm_kernel<128, 2><<<grid, kGemmThreads, GemmCfg<128>::kSmem, st>>>(ta, tb, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kGemmThreads); cfg.stream = st;
+    cfg.dynamicSmemBytes = BN == 256 ? GemmCfg<256>::kSmem : GemmCfg<128>::kSmem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = cluster ? 1 : 0;
+    if (tf32) MV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<128, 4, false>, ta, tb, p));
+    else if (BN == 256 && cluster) MV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<256, 2, true>, ta, tb, p));
+    else if (BN == 256) MV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<256, 2, false>, ta, tb, p));
+    else if (cluster) MV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<128, 2, true>, ta, tb, p));
+    else MV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<128, 2, false>, ta, tb, p));
     g_launches++;
     return check_cuda(cudaGetLastError(), "gemm launch");
 }

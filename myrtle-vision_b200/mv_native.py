@@ -39,6 +39,7 @@ class GemmArgs(ctypes.Structure):
         ("accumulate", ctypes.c_int),
         ("rows_per_img", ctypes.c_int),
         ("tile_n", ctypes.c_int),
+        ("cluster", ctypes.c_int),
     ]
 
 
@@ -197,7 +198,7 @@ def quantize_weight(w, exp, man, out_dtype=torch.float16, transpose=True, out=No
 # ------------------------------------------------------------------------ GEMM
 def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out2=None,
          epilogue=EPI_NONE, q_out=None, q_res=None, accumulate=False, rows_per_img=0,
-         M=None, N=None, K=None, tag=None, tile_n=0):
+         M=None, N=None, K=None, tag=None, tile_n=0, cluster=0):
     """out[M,N] = A . B^T over K with the fused epilogue of mv_gemm (include/mv_b200.h).
     a_major/b_major = 0: operand is [M|N, K] (K contiguous); 1: operand is [K, M|N]."""
     _need_cuda(A, B, out)
@@ -230,6 +231,7 @@ def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None,
     a.accumulate = int(bool(accumulate))
     a.rows_per_img = rows_per_img
     a.tile_n = tile_n
+    a.cluster = cluster
     kind = "gemm_wgrad" if accumulate else ("gemm_dgrad" if epilogue == EPI_DGELU or tag == "dgrad"
                                             else "gemm_fwd")
     with _timed(kind):
