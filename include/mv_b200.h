@@ -101,8 +101,10 @@ typedef struct {
     int q_res_exp, q_res_man;
     int accumulate;               /* split-K atomic accumulation into fp32 `out` */
     int rows_per_img;             /* residual row = m % rows_per_img when > 0 */
-    int tile_n;                   /* 0 = auto; 128 forces 128-wide tiles (testing) */
-    int cluster;                  /* 2 = CTA pairs share the B tile by TMA multicast (opt-in; not faster on B200) */
+    int tile_n;                   /* 0 = auto; 128 / 192 / 256 forces the tile width (testing) */
+    int cluster;                  /* 0 = CTA-pair kernel (tcgen05 cta_group::2, 256 x tile_n cluster tiles; 16-bit operands);
+                                   * 1 = single-CTA kernel (always used for tf32); 2 = single-CTA MMAs with the B tile
+                                   * TMA-multicast across a CTA pair (kept for comparison) */
 } mv_gemm_args;
 
 int mv_gemm(const mv_gemm_args* args, void* stream);

@@ -35,12 +35,6 @@ constexpr uint32_t kIdescPV = make_idesc(0, 0, 0, 1, 128, 64);     // A K-major,
 constexpr uint32_t kIdescTT = make_idesc(0, 0, 1, 1, 128, 64);     // A MN-major, B MN-major, N=64
 
 __device__ __forceinline__ float sat16f(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
-// single-instruction MUFU.EX2 (exp2f() adds denormal range handling the softmax does not need)
-__device__ __forceinline__ float ex2_fast(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 // {lo, hi} -> packed fp16x2 with saturation to +-65504 in one F2FP
 __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
     uint32_t r;

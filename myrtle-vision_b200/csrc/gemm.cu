@@ -44,28 +44,51 @@ struct GemmDev {
     FloatFmt q_out, q_res;
     int accumulate;
     int rows_per_img;
+    int variant;                // CTA-pair kernel: compile-time epilogue variant (0 = generic), see gemm2_host
 };
 
 __device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
 
-// erf-GELU (nn.GELU default, models/vit.py:49) and its derivative, branch-free.
-// 0.5*erfc(z) = 0.5 / (1 + a1 z + ... + a6 z^6)^16 for z >= 0 (Abramowitz & Stegun 7.1.28,
-// |error| <= 3e-7 on erf); measured max abs error vs the exact fp64 GELU: 8.2e-7 (gelu), 9e-7 (gelu').
-// The epilogue is ALU-bound, so the ~40-instruction branching erff() is not affordable here.
+// erf-GELU (nn.GELU default, models/vit.py:49) and its derivative, branch-free:
+//   0.5*erfc(|x|/sqrt2) = t (b1 + t (b2 + t (b3 + t (b4 + t b5)))) exp(-x^2/2),  t = 1 / (1 + 0.2316419 |x|)
+// (Abramowitz & Stegun 26.2.17 / 7.1.26).  The exponential is shared with the derivative's pdf term,
+// so gelu and gelu' together cost 16 FP32 instructions + 2 MUFU.  Max abs error against the exact fp64
+// GELU over [-12, 12]: 4.2e-7 (gelu), 3.0e-7 (gelu') — below half an fp16 ulp of the stored values.
 __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
-    const float z = fabsf(x) * 0.70710678f;
-    float den = fmaf(z, 0.0000430638f, 0.0002765672f);
-    den = fmaf(den, z, 0.0001520143f);
-    den = fmaf(den, z, 0.0092705272f);
-    den = fmaf(den, z, 0.0422820123f);
-    den = fmaf(den, z, 0.0705230784f);
-    den = fmaf(den, z, 1.0f);
-    den *= den; den *= den; den *= den; den *= den;
-    const float half_erfc = __fdividef(0.5f, den);
+    const float t = rcp_fast(fmaf(fabsf(x), 0.2316418882f, 1.0f));
+    const float E = ex2_fast(x * x * -0.7213475204f);
+    float poly = fmaf(t, 0.5307027145f, -0.7265760135f);
+    poly = fmaf(poly, t, 0.7107068705f);
+    poly = fmaf(poly, t, -0.142248368f);
+    poly = fmaf(poly, t, 0.127414796f);
+    const float half_erfc = poly * t * E;
     const float cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
-    const float pdf = 0.3989422804f * exp2f(-0.7213475204f * x * x);
     g = x * cdf;
-    dg = fmaf(x, pdf, cdf);
+    dg = fmaf(x, 0.3989422804f * E, cdf);
+}
+
+// float_quantize(5,10) of four values at once: one range test for the group, then 2 integer
+// instructions per value.  kSatLater: the caller converts with cvt.rn.satfinite.f16, which performs
+// the clip to +-65504 (the rounded value is exactly representable in fp16 otherwise).
+static __device__ __noinline__ float4 fq_half4_rare(float a, float b, float c, float d) {
+    return make_float4(fq_half_fast(a), fq_half_fast(b), fq_half_fast(c), fq_half_fast(d));
+}
+template <bool kSatLater>
+__device__ __forceinline__ void fq_half4(float (&v)[4]) {
+    const float mn = fminf(fminf(fabsf(v[0]), fabsf(v[1])), fminf(fabsf(v[2]), fabsf(v[3])));
+    if (mn >= 6.103515625e-05f) {                       // all four at or above fp16's lowest normal binade
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t t = __float_as_uint(v[j]);
+            uint32_t q = (t + 0x1000u) & 0xFFFFE000u;
+            if (!kSatLater && (q & 0x7FFFFFFFu) > 0x477FE000u) q = (t & 0x80000000u) | 0x477FE000u;
+            v[j] = __uint_as_float(q);
+        }
+    } else {
+        // out of line on purpose: inline, ptxas if-converts this into ~50 predicated instructions per group
+        const float4 r = fq_half4_rare(v[0], v[1], v[2], v[3]);
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+    }
 }
 
 __device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
@@ -424,9 +447,453 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
 }
 
+// =====================================================================================
+// CTA-pair kernel (cta_group::2): the default for 16-bit operands.
+//
+// A cluster of two CTAs (one TPC) owns a 256 x BN output tile.  Each CTA stages its own 128 rows
+// of A and BN/2 rows of B (one third less L2->SM operand traffic per flop than two independent
+// 128 x BN tiles, the bound of the K=384 GEMMs of ViT-Small); the leader CTA's elected lane issues
+// tcgen05.mma.cta_group::2 (M=256) and each CTA ends up with its 128 x BN half of the accumulator
+// in its own TMEM.  Barriers:
+//   full[s]   (leader's)  1 arrive.expect_tx by the leader's producer + TMA bytes of both CTAs
+//   empty[s]  (per CTA)   multicast tcgen05.commit from the leader: the stage is free in both CTAs
+//   tmem_full[a] (per CTA) multicast commit: accumulator a is complete
+//   tmem_empty[a] (leader's) 2 x kEpi2Warps arrivals: both CTAs' epilogues have drained accumulator a
+//
+// Epilogue: the TMEM layout (thread = row) would make every global access touch 32 different
+// lines per warp instruction, which made the previous kernel LSU-bound.  Here each warp moves a
+// 32 x 32 fp32 chunk TMEM -> registers -> padded shared memory and then works in a row-contiguous
+// layout (8 lanes x 16 B per row, 4 rows per instruction): every bias / residual / aux load and
+// every store covers whole 32-byte sectors of consecutive addresses.
+constexpr int kEpi2Warps = 16;
+constexpr int kGemm2Threads = 64 + 32 * kEpi2Warps;
+constexpr int kStgPitch = 36;                                  // floats per staged row: 32 + 4 pad
+constexpr int kStgBytesPerWarp = 32 * kStgPitch * 4;           // 4608
+template <int BN> struct Gemm2Cfg {
+    static constexpr int kBHalfBytes = (BN / 2) * 128;
+    static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
+    static constexpr int kStagingBytes = kEpi2Warps * kStgBytesPerWarp;
+    static constexpr int kStages = (232448 - kStagingBytes - 1024 - 256) / kStageBytes;
+    static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + 256;
+    static constexpr int kTmemCols = 2 * BN <= 256 ? 256 : 512;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+__device__ __forceinline__ uint2 pack4_f16_sat(const float (&v)[4]) {
+    uint2 r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(v[3]), "f"(v[2]));
+    return r;
+}
+__device__ __forceinline__ uint2 pack4_bf16(const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+// 4 consecutive outputs of one row; vec: 16-byte (fp32) / 8-byte (16-bit) aligned and all 4 in range
+__device__ __forceinline__ void store_out4(void* base, int dtype, int64_t row, int ld, int col,
+                                           const float (&v)[4], bool vec, int nvalid) {
+    if (dtype == MV_F32) {
+        float* o = reinterpret_cast<float*>(base) + row * ld + col;
+        if (vec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else for (int j = 0; j < 4; j++) if (j < nvalid) o[j] = v[j];
+    } else if (dtype == MV_F16) {
+        __half* o = reinterpret_cast<__half*>(base) + row * ld + col;
+        if (vec) *reinterpret_cast<uint2*>(o) = pack4_f16_sat(v);
+        else for (int j = 0; j < 4; j++) if (j < nvalid) o[j] = __float2half_rn(sat16(v[j]));
+    } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(base) + row * ld + col;
+        if (vec) *reinterpret_cast<uint2*>(o) = pack4_bf16(v);
+        else for (int j = 0; j < 4; j++) if (j < nvalid) o[j] = __float2bfloat16_rn(v[j]);
+    }
+}
+
+
+// ---- epilogue of the CTA-pair kernel ----------------------------------------------------------
+struct EpiWarp {
+    float* stg;                 // this warp's 32 x kStgPitch fp32 staging tile
+    int lane, lr, lc;           // row-contiguous layout: row = 4*it + lr, columns lc .. lc+3 of the chunk
+    int mode_out, mode_res;
+};
+
+// accumulator chunk (32 TMEM lanes x 32 columns): thread = row -> padded shared memory; optionally
+// release the accumulator buffer (arrive on the leader's tmem_empty barrier) right after the read
+__device__ __forceinline__ void stage_chunk(const EpiWarp& w, uint32_t taddr, uint32_t release) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr, r);
+    tmem_ld_wait();
+    float4* srow = reinterpret_cast<float4*>(w.stg + w.lane * kStgPitch);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    if (release != 0u) {
+        tc_fence_before();
+        __syncwarp();
+        if (w.lane == 0) mbar_arrive_cluster(release);
+    }
+    __syncwarp();
+}
+
+// Fast path: the chunk lies inside [M, N], every pointer / pitch is vector-aligned (checked on the
+// host, GemmDev::variant) and the epilogue's shape is a compile-time choice, so the unrolled row
+// loop is a few instructions per 4 outputs.  kRes: 0 none, 1 residual[m, n], 2 residual[m % rows_per_img, n].
+template <int kOut, int kEpi, int kRes, int kQO, int kQR, bool kAcc>
+__device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, uint32_t taddr, uint32_t release,
+                                          int mrow0, int nc0) {
+    const int n = nc0 + w.lc;
+    const int m_first = mrow0 + w.lr;
+    float4 res4[8];
+    uint2 aux2[8];
+    if (kRes != 0) {
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int m = m_first + it * 4;
+            const int64_t rrow = kRes == 2 ? (m % p.rows_per_img) : m;
+            res4[it] = __ldcs(reinterpret_cast<const float4*>(p.residual + rrow * p.ld_res + n));
+        }
+    }
+    if (kEpi == MV_EPI_DGELU) {
+#pragma unroll
+        for (int it = 0; it < 8; it++)
+            aux2[it] = __ldcs(reinterpret_cast<const uint2*>(p.aux + int64_t(m_first + it * 4) * p.ld_aux + n));
+    }
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!kAcc && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    stage_chunk(w, taddr, release);
+    const float* sp = w.stg + w.lr * kStgPitch + w.lc;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int m = m_first + it * 4;
+        const float4 a4 = *reinterpret_cast<const float4*>(sp + it * 4 * kStgPitch);
+        float v[4] = {a4.x, a4.y, a4.z, a4.w};
+        if (kAcc) {
+            red_add_v4(reinterpret_cast<float*>(p.out) + int64_t(m) * p.ld_out + n, v[0], v[1], v[2], v[3]);
+            continue;
+        }
+        v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+        if (kQO == 1) fq_half4<false>(v);
+        if (kEpi == MV_EPI_GELU) {
+            float d[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) gelu_both(v[j], v[j], d[j]);
+            *reinterpret_cast<uint2*>(p.aux + int64_t(m) * p.ld_aux + n) = pack4_f16_sat(d);
+        } else if (kEpi == MV_EPI_DGELU) {
+            const __half2* hh = reinterpret_cast<const __half2*>(&aux2[it]);
+            const float2 f0 = __half22float2(hh[0]), f1 = __half22float2(hh[1]);
+            v[0] *= f0.x; v[1] *= f0.y; v[2] *= f1.x; v[3] *= f1.y;
+        }
+        if (kRes != 0) { v[0] += res4[it].x; v[1] += res4[it].y; v[2] += res4[it].z; v[3] += res4[it].w; }
+        if (kQR == 1) fq_half4<kOut == MV_F16>(v);
+        if (kOut == MV_F32)
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + int64_t(m) * p.ld_out + n) =
+                make_float4(v[0], v[1], v[2], v[3]);
+        else
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + int64_t(m) * p.ld_out + n) = pack4_f16_sat(v);
+    }
+    __syncwarp();                                      // staging is rewritten by the next chunk
+}
+
+// Generic path: tails in M / N, unaligned pitches, bf16 / second outputs.  Same arithmetic, rolled loops.
+__device__ __forceinline__ void epi_chunk_generic(const GemmDev& p, const EpiWarp& w, uint32_t taddr, uint32_t release,
+                                               int mrow0, int nc0) {
+    stage_chunk(w, taddr, release);
+    const int n = nc0 + w.lc;
+    const int nvalid = min(4, p.N - n);
+    if (nvalid > 0) {
+#pragma unroll 1
+        for (int it = 0; it < 8; it++) {
+            const int row = it * 4 + w.lr;
+            const int m = mrow0 + row;
+            if (m >= p.M) break;
+            const float4 a4 = *reinterpret_cast<const float4*>(w.stg + row * kStgPitch + w.lc);
+            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+            if (p.accumulate) {
+                float* o = reinterpret_cast<float*>(p.out) + int64_t(m) * p.ld_out + n;
+                for (int j = 0; j < 4; j++) if (j < nvalid) atomicAdd(o + j, v[j]);
+                continue;
+            }
+            if (p.bias != nullptr) for (int j = 0; j < 4; j++) if (j < nvalid) v[j] += __ldg(p.bias + n + j);
+            if (w.mode_out) for (int j = 0; j < 4; j++) v[j] = fq_apply(v[j], w.mode_out, p.q_out);
+            if (p.epilogue == MV_EPI_GELU) {
+                __half* up = p.aux + int64_t(m) * p.ld_aux + n;
+                for (int j = 0; j < 4; j++) {
+                    float d;
+                    gelu_both(v[j], v[j], d);
+                    if (j < nvalid) up[j] = __float2half_rn(d);
+                }
+            } else if (p.epilogue == MV_EPI_DGELU) {
+                const __half* up = p.aux + int64_t(m) * p.ld_aux + n;
+                for (int j = 0; j < 4; j++) if (j < nvalid) v[j] *= __half2float(up[j]);
+            }
+            if (p.residual != nullptr) {
+                const int64_t rrow = p.rows_per_img > 0 ? (m % p.rows_per_img) : m;
+                const float* rp = p.residual + rrow * p.ld_res + n;
+                for (int j = 0; j < 4; j++) if (j < nvalid) v[j] += rp[j];
+            }
+            if (w.mode_res) for (int j = 0; j < 4; j++) v[j] = fq_apply(v[j], w.mode_res, p.q_res);
+            store_out4(p.out, p.out_dtype, m, p.ld_out, n, v, false, nvalid);
+            if (p.out2 != nullptr) store_out4(p.out2, p.out2_dtype, m, p.ld_out2, n, v, false, nvalid);
+        }
+    }
+    __syncwarp();
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ GemmDev p) {
+    using Cfg = Gemm2Cfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kStageBytes = Cfg::kStageBytes;
+    constexpr int BK = 64, UMMA_K = 16;
+    constexpr int kMnBoxBytes = BK * 128;      // one MN-major TMA box: 64 k-rows x 128 B (64 elements)
+    constexpr int BNH = BN / 2;                // B rows staged by each CTA
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* staging = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + Cfg::kStagingBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = int(cluster_ctarank());
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * kEpi2Warps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_cg2<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                        // both CTAs' barriers and TMEM exist before any cross-CTA signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work units: (256 x BN tile, k split); both CTAs of a pair walk the same sequence
+    const int unit0 = blockIdx.x >> 1, unit_stride = gridDim.x >> 1;
+    const int total_units = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 0) {
+        // ================================ TMA producer (both CTAs) ================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = unit0; u < total_units; u += unit_stride) {
+                const int split = u % p.splits;
+                const int tile = u / p.splits;
+                const int m0 = (tile / p.n_tiles) * 256 + rank * 128;
+                const int n0 = (tile % p.n_tiles) * BN + rank * BNH;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kStageBytes;
+                    uint8_t* sb = sa + kATileBytes;
+                    const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                    if (p.a_major == 0) {
+                        tma_load_2d_cg2(sa, &tmap_a, lead_full, kb * BK, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 2; c++)
+                            tma_load_2d_cg2(sa + c * kMnBoxBytes, &tmap_a, lead_full, m0 + c * 64, kb * BK);
+                    }
+                    if (p.b_major == 0) {
+                        tma_load_2d_cg2(sb, &tmap_b, lead_full, kb * BK, n0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BNH / 64; c++)
+                            tma_load_2d_cg2(sb + c * kMnBoxBytes, &tmap_b, lead_full, n0 + c * 64, kb * BK);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) ============================
+        if (rank == 0 && lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t a_lbo = p.a_major ? kMnBoxBytes : 16, b_lbo = p.b_major ? kMnBoxBytes : 16;
+            const uint32_t a_kstep = p.a_major ? UMMA_K * 128 : 32, b_kstep = p.b_major ? UMMA_K * 128 : 32;
+            for (int u = unit0; u < total_units; u += unit_stride) {
+                const int split = u % p.splits;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+                        umma_f16_cg2(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_cg2(&empty_bar[stage], 3);     // stage free in both CTAs when the MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_cg2(&tmem_full[acc], 3);           // both CTAs' epilogues may read accumulator acc
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================ epilogue (both CTAs) ====================================
+        const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
+        const int cg = (warp - 2) >> 2;                        // chunks cg, cg+4, ... of the tile's 32-column chunks
+        EpiWarp w;
+        w.stg = staging + (warp - 2) * (32 * kStgPitch);
+        w.lane = lane; w.lr = lane >> 3; w.lc = (lane & 7) * 4;
+        w.mode_out = fq_mode(p.q_out); w.mode_res = fq_mode(p.q_res);
+        const uint32_t lead_empty0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int u = unit0; u < total_units; u += unit_stride) {
+            const int tile = u / p.splits;
+            const int mrow0 = (tile / p.n_tiles) * 256 + rank * 128 + quad * 32;
+            const int n0 = (tile % p.n_tiles) * BN;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = cg; c < BN / 32; c += kEpi2Warps / 4) {
+                const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32;
+                // last TMEM read of this tile by this warp: hand the accumulator back to the MMA issuer
+                const uint32_t release = (c + kEpi2Warps / 4 >= BN / 32) ? lead_empty0 + acc * 8 : 0u;
+                const int nc0 = n0 + c * 32;
+                const bool fast = p.variant != 0 && mrow0 + 32 <= p.M && nc0 + 32 <= p.N;
+                if (!fast) { epi_chunk_generic(p, w, taddr, release, mrow0, nc0); continue; }
+                switch (p.variant) {
+                    //                 out     epilogue      res qo qr acc
+                    case 1: epi_chunk<MV_F16, MV_EPI_NONE, 0, 0, 0, false>(p, w, taddr, release, mrow0, nc0); break;
+                    case 2: epi_chunk<MV_F16, MV_EPI_NONE, 0, 1, 0, false>(p, w, taddr, release, mrow0, nc0); break;
+                    case 3: epi_chunk<MV_F32, MV_EPI_NONE, 1, 0, 0, false>(p, w, taddr, release, mrow0, nc0); break;
+                    case 4: epi_chunk<MV_F32, MV_EPI_NONE, 1, 1, 1, false>(p, w, taddr, release, mrow0, nc0); break;
+                    case 5: epi_chunk<MV_F16, MV_EPI_GELU, 0, 0, 1, false>(p, w, taddr, release, mrow0, nc0); break;
+                    case 6: epi_chunk<MV_F16, MV_EPI_DGELU, 0, 0, 0, false>(p, w, taddr, release, mrow0, nc0); break;
+                    case 7: epi_chunk<MV_F32, MV_EPI_NONE, 2, 0, 0, false>(p, w, taddr, release, mrow0, nc0); break;
+                    case 8: epi_chunk<MV_F32, MV_EPI_NONE, 0, 0, 0, true>(p, w, taddr, release, mrow0, nc0); break;
+                    case 9: epi_chunk<MV_F16, MV_EPI_GELU, 0, 1, 1, false>(p, w, taddr, release, mrow0, nc0); break;
+                    default: epi_chunk<MV_F32, MV_EPI_NONE, 2, 1, 1, false>(p, w, taddr, release, mrow0, nc0); break;
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                        // the peer may still be signalling / reading this CTA
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_cg2<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+template <int BN>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        MV_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::kSmem));
+        attr_done = true;
+    }
+    gemm2_kernel<BN><<<grid, kGemm2Threads, Gemm2Cfg<BN>::kSmem, st>>>(ta, tb, p);
+    return 0;
+}
+
 }  // namespace mv
 
 using namespace mv;
+
+// CTA-pair path: 16-bit operands, 256 x BN cluster tiles
+static int gemm2_host(const mv_gemm_args* a, void* stream) {
+    constexpr int BK = 64;
+    // BN: least padding of N, ties to the wider tile; MN-major B is staged in 64-element chunks per CTA
+    int BN = 128, best = -1;
+    const int cands[3] = {256, 192, 128};
+    for (int i = 0; i < 3; i++) {
+        const int bn = cands[i];
+        if (a->b_major == 1 && bn == 192) continue;
+        if (a->tile_n != 0 && a->tile_n != bn) continue;
+        const int padded = ((a->N + bn - 1) / bn) * bn;
+        if (best < 0 || padded < best) { best = padded; BN = bn; }
+    }
+    MV_CHECK(best >= 0, "mv_gemm: tile_n %d not available for this operand layout", a->tile_n);
+    CUtensorMap ta, tb;
+    if (a->a_major == 0) { if (make_tmap_2d(&ta, a->A, a->a_dtype, a->M, a->K, a->lda, BM, BK)) return 1; }
+    else                 { if (make_tmap_2d(&ta, a->A, a->a_dtype, a->K, a->M, a->lda, BK, 64)) return 1; }
+    if (a->b_major == 0) { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->N, a->K, a->ldb, BN / 2, BK)) return 1; }
+    else                 { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->K, a->N, a->ldb, BK, 64)) return 1; }
+
+    GemmDev p;
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.m_tiles = (a->M + 255) / 256;
+    p.n_tiles = (a->N + BN - 1) / BN;
+    p.kb_total = (a->K + BK - 1) / BK;
+    int splits = 1;
+    if (a->accumulate) {
+        splits = (kNumSMs / 2) / (p.m_tiles * p.n_tiles);
+        if (splits < 1) splits = 1;
+        if (splits > p.kb_total) splits = p.kb_total;
+    }
+    p.kb_per_split = (p.kb_total + splits - 1) / splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.a_major = a->a_major; p.b_major = a->b_major;
+    const int fmt = a->a_dtype == MV_BF16 ? 1 : 0;
+    p.idesc = make_idesc(fmt, fmt, a->a_major, a->b_major, 256, BN);
+    p.bias = a->bias; p.residual = a->residual; p.ld_res = a->ld_res;
+    p.aux = reinterpret_cast<__half*>(a->aux); p.ld_aux = a->ld_aux;
+    p.out = a->out; p.ld_out = a->ld_out; p.out_dtype = a->out_dtype;
+    p.out2 = a->out2; p.ld_out2 = a->ld_out2; p.out2_dtype = a->out2_dtype;
+    p.epilogue = a->epilogue;
+    p.q_out = FloatFmt{a->q_out_exp, a->q_out_man};
+    p.q_res = FloatFmt{a->q_res_exp, a->q_res_man};
+    p.accumulate = a->accumulate;
+    p.rows_per_img = a->rows_per_img;
+    // epilogue variant (epi_chunk<> instantiations in gemm2_kernel); anything else runs the generic path
+    {
+        auto al = [](const void* q, int bytes) { return (reinterpret_cast<uintptr_t>(q) & (bytes - 1)) == 0; };
+        auto qkind = [](int e, int m) { return e == 0 ? 0 : ((e == 5 && m == 10) ? 1 : 2); };
+        const int qo = qkind(a->q_out_exp, a->q_out_man), qr = qkind(a->q_res_exp, a->q_res_man);
+        const int res = a->residual == nullptr ? 0 : (a->rows_per_img > 0 ? 2 : 1);
+        const bool ok = a->out2 == nullptr && (a->ld_out & 3) == 0 && (a->bias == nullptr || al(a->bias, 16)) &&
+                        (res == 0 || ((a->ld_res & 3) == 0 && al(a->residual, 16))) &&
+                        (a->aux == nullptr || ((a->ld_aux & 3) == 0 && al(a->aux, 8))) &&
+                        al(a->out, a->out_dtype == MV_F32 ? 16 : 8);
+        struct Row { int id, out, epi, res, qo, qr; };
+        static const Row table[] = {
+            {1, MV_F16, MV_EPI_NONE, 0, 0, 0}, {2, MV_F16, MV_EPI_NONE, 0, 1, 0}, {3, MV_F32, MV_EPI_NONE, 1, 0, 0},
+            {4, MV_F32, MV_EPI_NONE, 1, 1, 1}, {5, MV_F16, MV_EPI_GELU, 0, 0, 1}, {6, MV_F16, MV_EPI_DGELU, 0, 0, 0},
+            {7, MV_F32, MV_EPI_NONE, 2, 0, 0}, {9, MV_F16, MV_EPI_GELU, 0, 1, 1}, {10, MV_F32, MV_EPI_NONE, 2, 1, 1}};
+        int v = 0;
+        if (ok && a->accumulate) v = 8;
+        else if (ok)
+            for (const Row& r : table)
+                if (r.out == a->out_dtype && r.epi == a->epilogue && r.res == res && r.qo == qo && r.qr == qr) v = r.id;
+        p.variant = v;
+    }
+
+    const int units = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = 2 * (units < kNumSMs / 2 ? units : kNumSMs / 2);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if (BN == 256) rc = launch_gemm2<256>(ta, tb, p, grid, st);
+    else if (BN == 192) rc = launch_gemm2<192>(ta, tb, p, grid, st);
+    else rc = launch_gemm2<128>(ta, tb, p, grid, st);
+    if (rc) return rc;
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "gemm2 launch");
+}
 
 extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     MV_CHECK(a != nullptr, "mv_gemm: null args");
@@ -434,6 +901,9 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     MV_CHECK(a->A && a->B && a->out, "mv_gemm: null operand");
     const bool tf32 = a->a_dtype == MV_F32;
     MV_CHECK(a->a_dtype == a->b_dtype, "mv_gemm: A and B must share one element type (tcgen05 kind::f16 rejects f16 x bf16)");
+    if (a->accumulate) MV_CHECK(a->out_dtype == MV_F32, "mv_gemm: accumulate needs an fp32 output");
+    if (a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU) MV_CHECK(a->aux != nullptr, "mv_gemm: GELU epilogues need aux");
+    if (!tf32 && a->cluster == 0) return gemm2_host(a, stream);      // CTA-pair kernel (default)
     const int esz = tf32 ? 4 : 2;
     const int BK = 128 / esz;
     static bool attr_done = false;
@@ -447,8 +917,6 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     }
     // 128x256 tiles cut the L2->SM operand traffic per flop by a quarter; use them when N tiles evenly
     const int BN = (!tf32 && a->N % 256 == 0 && a->tile_n != 128) ? 256 : 128;
-    if (a->accumulate) MV_CHECK(a->out_dtype == MV_F32, "mv_gemm: accumulate needs an fp32 output");
-    if (a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU) MV_CHECK(a->aux != nullptr, "mv_gemm: GELU epilogues need aux");
 
     CUtensorMap ta, tb;
     // K-major operand [rows = M|N, cols = K]: box = 128 rows x 128 B of K.

@@ -59,13 +59,19 @@ __device__ __forceinline__ float fq_nearest(float a, FloatFmt f) {
 
 // Same result as float_quantize_elem<false>(a, 0, 5, 10), with a short path for the normal
 // fp16 range (the subnormal / zero branch is rare for activations and falls back).
-static __device__ __noinline__ float fq_half_slow(float a) { return float_quantize_elem<false>(a, 0u, 5, 10); }
 static __device__ __noinline__ float fq_generic_slow(float a, int exp_bits, int man_bits) {
     return float_quantize_elem<false>(a, 0u, exp_bits, man_bits);
 }
 __device__ __forceinline__ float fq_half_fast(float a) {
     const uint32_t t = __float_as_uint(a);
-    if (((t >> 23) & 0xFFu) < 113u) return fq_half_slow(a);     // out of line: keeps fused loops small
+    if (((t >> 23) & 0xFFu) < 113u) {
+        // below fp16's lowest normal binade (rare for activations): shift up to 2^-14, round there,
+        // shift back — float_quantize_elem's subnormal branch for (5,10), inline so that a warp
+        // with one such lane pays ~8 instructions instead of a call
+        const float shift = __uint_as_float(0x38800000u | (t & 0x80000000u));
+        const uint32_t vb = __float_as_uint(__fadd_rn(a, shift));
+        return __fsub_rn(__uint_as_float((vb + 0x1000u) & 0xFFFFE000u), shift);
+    }
     uint32_t q = (t + 0x1000u) & 0xFFFFE000u;
     if ((q & 0x7FFFFFFFu) > 0x477FE000u) q = (t & 0x80000000u) | 0x477FE000u;
     return __uint_as_float(q);
