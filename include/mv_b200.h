@@ -138,6 +138,10 @@ int mv_cls_rows(const float* cls, const float* pos_q, float* x, int B, int n_tok
 /* fp32 -> fp16 (saturating) / bf16 copy of n elements (n % 4 == 0) */
 int mv_convert_f32(const float* in, void* out, int out_dtype, int64_t n, void* stream);
 
+/* Library-wide switches (testing / A-B measurement).  "attn_sn": 1 (default) = sequences of at most
+ * 272 keys use the resident-K/V short-sequence attention kernels, 0 = always the blocked kernels. */
+int mv_set_option(const char* name, int value);
+
 /* ---------------------------------------------------------------- attention (tcgen05, flash-style)
  * Attention.forward's (q @ k^T) * scale -> softmax -> @ v -> transpose/reshape (models/vit.py:87-97).
  * qkv: fp16 [B*N, 3*H*64] as written by the to_qkv GEMM (q | k | v, 64 columns per head).

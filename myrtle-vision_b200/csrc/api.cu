@@ -9,6 +9,7 @@ namespace mv {
 
 static thread_local char g_err[512] = "";
 int64_t g_launches = 0;
+int g_opt_attn_sn = 1;          // short-sequence attention kernels (attention_sn.cu) when N fits
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -99,3 +100,9 @@ int make_tmap_3d(CUtensorMap* map, const void* ptr, int dtype, uint64_t d0, uint
 extern "C" const char* mv_last_error(void) { return mv::g_err; }
 extern "C" int mv_version(void) { return 100; }
 extern "C" int64_t mv_launch_count(void) { return mv::g_launches; }
+
+extern "C" int mv_set_option(const char* name, int value) {
+    if (name != nullptr && strcmp(name, "attn_sn") == 0) { mv::g_opt_attn_sn = value; return 0; }
+    mv::set_error("mv_set_option: unknown option '%s'", name ? name : "(null)");
+    return 1;
+}

@@ -736,10 +736,17 @@ constexpr int kAttnBwdQSmem = 8 * kTile + 1024 + 256;
 
 using namespace mv;
 
+namespace mv { extern int g_opt_attn_sn; }
+extern "C" int mv_attention_sn_supported(int N);
+int mv_attention_fwd_sn(const void* qkv, void* out, int out_dtype, float* lse, int B, int H, int N,
+                        float scale, int q_out_exp, int q_out_man, void* stream);
+
 extern "C" int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float* lse, int B, int H, int N,
                                 float scale, int q_out_exp, int q_out_man, void* stream) {
     MV_CHECK(B > 0 && H > 0 && N > 0 && qkv && out, "mv_attention_fwd: bad arguments");
     MV_CHECK(out_dtype == MV_F16 || out_dtype == MV_F32, "mv_attention_fwd: bad output container");
+    if (g_opt_attn_sn && mv_attention_sn_supported(N))
+        return mv_attention_fwd_sn(qkv, out, out_dtype, lse, B, H, N, scale, q_out_exp, q_out_man, stream);
     const int D = H * 64;
     static bool attr_done = false;
     if (!attr_done) {

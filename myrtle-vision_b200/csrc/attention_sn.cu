@@ -1,0 +1,529 @@
+// attention_sn.cu — softmax attention for SHORT sequences (N <= 272 keys, head dim 64): the ViT
+// classification / segmentation shapes (256x256 images, patch 16 -> N = 257).
+//
+// Same operator as attention.cu (Attention.forward's (q @ k^T) * scale -> softmax -> @ v,
+// src/myrtle_vision/models/vit.py:87-97, and its autograd backward), different schedule:
+//   * one persistent CTA per SM walks (image, head) pairs; the pair's whole K and V (<= 272 x 64 fp16
+//     each) are resident in shared memory and double-buffered across pairs, so the next pair's loads
+//     overlap this pair's math;
+//   * the full score row of a 128-query tile fits TMEM (<= 256 fp32 columns): plain two-pass softmax,
+//     no online rescaling; P is written back over the consumed S columns as the fp16 TMEM A operand
+//     of P.V (never touches shared memory) and O lands in the same 256-column region, so TWO query
+//     tiles are in flight per SM — one group of 4 math warps (one thread per query row) each — and one
+//     tile's MMAs run under the other's softmax;
+//   * N = 257 = 2 x 128 + 1 = 16 x 16 + 1: neither the odd query row nor the odd key is padded up to a
+//     tensor-core tile.  Tail query rows (N mod 128 <= kSnTailMax) are computed by SIMT warps from the
+//     K / V already in shared memory, concurrently with the tiles; keys past the last multiple of 16
+//     (<= kSnExtraMax) are folded in by the math threads (one 64-element dot product per row).
+#include "common.cuh"
+#include "quant_dev.cuh"
+#include "../../include/mv_b200.h"
+
+namespace mv {
+
+extern int64_t g_launches;
+
+constexpr int kSnMaxKeys = 272;                 // padded keys (multiple of 16) that fit the TMEM plan
+constexpr int kSnTailMax = 2;                   // tail query rows (N mod 128) handled by the SIMT warp
+constexpr int kSnKVBytes = kSnMaxKeys * 128;    // one K or V stage: 272 rows x 128 B
+constexpr int kSnTile = 16384;                  // 128 rows x 128 B
+constexpr int kSnExtraMax = 2;                  // keys beyond the last multiple of 16 folded in on the CUDA cores
+constexpr int kSnMathWarps = 8;                 // two groups of four: one thread per query row
+constexpr int kSnTailWarps = 2;
+constexpr int kSnFwdThreads = 32 * (2 + kSnMathWarps + kSnTailWarps);   // producer, MMA, math, tail
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2_rn(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_h2_satf(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+struct SnFwdDev {
+    int B, H, N, D;
+    int Nk;                     // keys multiplied on the tensor cores (multiple of 16, <= 256)
+    int n_extra;                // keys [Nk, N) (at most kSnExtraMax) folded in by the math threads (SIMT)
+    int Nld;                    // key rows to stage in shared memory: Nk + 16 if n_extra else Nk
+    int n_tiles;                // 128-row tensor-core query tiles per (image, head)
+    int n_tail;                 // query rows [128 * n_tiles, N) computed by the SIMT warps
+    float scale_log2;
+    const __half* qkv;          // for the tail warps' q row
+    void* out; int out_dtype; int ld_out;
+    FloatFmt q_out;
+    float* lse;
+};
+
+// K / V loads of one (image, head): 128-row boxes, then 16-row boxes for the remainder
+__device__ __forceinline__ void sn_load_kv(uint8_t* dst, const CUtensorMap* m128, const CUtensorMap* m16,
+                                           uint64_t* bar, int col, int b, int rows) {
+    int r = 0;
+    for (; r + 128 <= rows; r += 128) tma_load_3d(dst + r * 128, m128, bar, col, r, b);
+    for (; r < rows; r += 16) tma_load_3d(dst + r * 128, m16, bar, col, r, b);
+}
+
+// dot product of two 64-element fp16 rows held in 128-byte-swizzled tiles (row index selects the XOR)
+__device__ __forceinline__ float sn_dot64(const uint8_t* tile_a, int ra, const uint8_t* tile_b, int rb) {
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const uint4 wa = *reinterpret_cast<const uint4*>(tile_a + ra * 128 + ((c ^ (ra & 7)) << 4));
+        const uint4 wb = *reinterpret_cast<const uint4*>(tile_b + rb * 128 + ((c ^ (rb & 7)) << 4));
+        const __half2* ha = reinterpret_cast<const __half2*>(&wa);
+        const __half2* hb = reinterpret_cast<const __half2*>(&wb);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float2 fa = __half22float2(ha[u]), fb = __half22float2(hb[u]);
+            acc = fmaf(fa.x, fb.x, acc);
+            acc = fmaf(fa.y, fb.y, acc);
+        }
+    }
+    return acc;
+}
+
+// ---- SIMT attention row (tail rows): one warp, K / V from the resident swizzled shared-memory tiles.
+// lane l owns output dims 2l, 2l+1.  scratch: 64 floats (q) + kSnMaxKeys floats (p).
+__device__ __forceinline__ void sn_tail_row_fwd(const SnFwdDev& p, const uint8_t* sK, const uint8_t* sV,
+                                                float* scratch, int b, int h, int row, int lane) {
+    float* sq = scratch;
+    float* sp = scratch + 64;
+    const __half* qrow = p.qkv + (int64_t(b) * p.N + row) * (3 * p.D) + h * 64;
+    {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(qrow + 2 * lane));
+        sq[2 * lane] = f.x; sq[2 * lane + 1] = f.y;
+    }
+    __syncwarp();
+    constexpr int kMaxPerLane = (kSnMaxKeys + 31) / 32;
+    float sc[kMaxPerLane];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; i++) {
+        const int j = lane + 32 * i;
+        float acc = -INFINITY;
+        if (j < p.N) {
+            acc = 0.f;
+            const uint8_t* krow = sK + j * 128;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const uint4 w = *reinterpret_cast<const uint4*>(krow + ((c ^ (j & 7)) << 4));
+                const __half2* hh = reinterpret_cast<const __half2*>(&w);
+                const float4 qa = *reinterpret_cast<const float4*>(sq + 8 * c);
+                const float4 qb = *reinterpret_cast<const float4*>(sq + 8 * c + 4);
+                const float2 k0 = __half22float2(hh[0]), k1 = __half22float2(hh[1]);
+                const float2 k2 = __half22float2(hh[2]), k3 = __half22float2(hh[3]);
+                acc = fmaf(qa.x, k0.x, acc); acc = fmaf(qa.y, k0.y, acc);
+                acc = fmaf(qa.z, k1.x, acc); acc = fmaf(qa.w, k1.y, acc);
+                acc = fmaf(qb.x, k2.x, acc); acc = fmaf(qb.y, k2.y, acc);
+                acc = fmaf(qb.z, k3.x, acc); acc = fmaf(qb.w, k3.y, acc);
+            }
+        }
+        sc[i] = acc;
+        mx = fmaxf(mx, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float m = mx * p.scale_log2;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; i++) {
+        const int j = lane + 32 * i;
+        const float e = j < p.N ? ex2_fast(fmaf(sc[i], p.scale_log2, -m)) : 0.f;
+        sum += e;
+        if (j < p.Nld) sp[j] = e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    // o[2l], o[2l+1] = sum_j p_j V[j][2l..2l+1]; V row j: 16-byte chunk (l >> 2) sits at position (l >> 2) ^ (j & 7)
+    float o0 = 0.f, o1 = 0.f;
+    const int cl = lane >> 2, wi = (lane & 3) * 4;
+    for (int j0 = 0; j0 < p.Nld; j0 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int j = j0 + u;
+            const float pj = sp[j];
+            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(sV + j * 128 + ((cl ^ u) << 4) + wi));
+            o0 = fmaf(pj, v.x, o0); o1 = fmaf(pj, v.y, o1);
+        }
+    }
+    const float inv = 1.0f / sum;
+    const int mode = fq_mode(p.q_out);
+    o0 = fq_apply(o0 * inv, mode, p.q_out);
+    o1 = fq_apply(o1 * inv, mode, p.q_out);
+    const int64_t grow = int64_t(b) * p.N + row;
+    if (p.out_dtype == MV_F16)
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(p.out) + grow * p.ld_out + h * 64 + 2 * lane) = pack_h2_satf(o0, o1);
+    else
+        *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + grow * p.ld_out + h * 64 + 2 * lane) = make_float2(o0, o1);
+    if (lane == 0 && p.lse != nullptr) p.lse[(int64_t(b) * p.H + h) * p.N + row] = m + log2f(sum);
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kSnFwdThreads, 1)
+attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant__ CUtensorMap tmap16,
+                   const __grid_constant__ SnFwdDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;                                   // [2 stages][272 x 128 B]
+    uint8_t* sV = smem + 2 * kSnKVBytes;
+    uint8_t* sQ = smem + 4 * kSnKVBytes;                  // ring of 2 query tiles
+    float* s_tail = reinterpret_cast<float*>(smem + 4 * kSnKVBytes + 2 * kSnTile);   // [2 warps][64 + kSnMaxKeys]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail + kSnTailWarps * (64 + kSnMaxKeys));
+    uint64_t* k_full = bars;            // [2]
+    uint64_t* k_empty = bars + 2;       // [2]
+    uint64_t* v_full = bars + 4;        // [2]
+    uint64_t* v_empty = bars + 6;       // [2]
+    uint64_t* q_full = bars + 8;        // [2]
+    uint64_t* q_empty = bars + 10;      // [2]
+    uint64_t* s_full = bars + 12;       // [2]  per math group
+    uint64_t* p_full = bars + 14;       // [2]
+    uint64_t* o_full = bars + 16;       // [2]
+    uint64_t* o_empty = bars + 18;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_bh = p.B * p.H;
+    const int n_local = blockIdx.x < n_bh ? (n_bh - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // pairs of this CTA
+    const int total_tiles = n_local * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap128); tma_prefetch_desc(&tmap16);
+        for (int s = 0; s < 2; s++) {
+            // a K / V stage is released by the MMA commit, the tail warp and the 4 math warps of every query tile
+            mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 2 + 4 * p.n_tiles);
+            mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 2 + 4 * p.n_tiles);
+            mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1 + 4);       // MMA commit + the tile's 4 math warps
+            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM, per math group (256 columns): S fp32 [0, Nk) -> P fp16 in place [0, Nk/2) -> O fp32 [128, 192)
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int qi = 0;
+            for (int n = 0; n < n_local; n++) {
+                const int bh = blockIdx.x + n * gridDim.x;
+                const int b = bh / p.H, h = bh % p.H, s = n & 1;
+                const uint32_t ph = (n >> 1) & 1;
+                mbar_wait_relaxed(&k_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&k_full[s], p.Nld * 128);
+                sn_load_kv(sK + s * kSnKVBytes, &tmap128, &tmap16, &k_full[s], p.D + h * 64, b, p.Nld);
+                for (int t = 0; t < p.n_tiles; t++, qi++) {
+                    const int qs = qi & 1;
+                    mbar_wait_relaxed(&q_empty[qs], ((qi >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&q_full[qs], kSnTile);
+                    tma_load_3d(sQ + qs * kSnTile, &tmap128, &q_full[qs], h * 64, t * 128, b);
+                    if (t == 0) {                                           // V is first needed after the first softmax
+                        mbar_wait_relaxed(&v_empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&v_full[s], p.Nld * 128);
+                        sn_load_kv(sV + s * kSnKVBytes, &tmap128, &tmap16, &v_full[s], 2 * p.D + h * 64, b, p.Nld);
+                    }
+                }
+                if (p.n_tiles == 0) {
+                    mbar_wait_relaxed(&v_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&v_full[s], p.Nld * 128);
+                    sn_load_kv(sV + s * kSnKVBytes, &tmap128, &tmap16, &v_full[s], 2 * p.D + h * 64, b, p.Nld);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc(0, 0, 0, 0, 128, p.Nk);
+            const uint32_t idesc_pv = make_idesc(0, 0, 0, 1, 128, 64);     // A (TMEM) K-major, B = V MN-major
+            const int ksteps = p.Nk >> 4;
+            auto issue_s = [&](int g) {
+                const int n = g / p.n_tiles, t = g % p.n_tiles, s = n & 1, grp = g & 1;
+                const uint32_t tS = tmem_base + grp * 256;
+                if (g >= 2) mbar_wait(&o_empty[grp], ((g - 2) >> 1) & 1);   // O(g-2) (inside this region) has been read
+                if (t == 0) mbar_wait(&k_full[s], (n >> 1) & 1);
+                mbar_wait(&q_full[g & 1], (g >> 1) & 1);
+                tc_fence_after();
+                const uint32_t aQ = smem_u32(sQ + (g & 1) * kSnTile), aK = smem_u32(sK + s * kSnKVBytes);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    umma_f16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024),
+                             make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k > 0);
+                umma_commit(&s_full[grp]);
+                umma_commit(&q_empty[g & 1]);
+                if (t == p.n_tiles - 1) umma_commit(&k_empty[s]);
+            };
+            if (p.n_tiles == 0) {
+                for (int n = 0; n < n_local; n++) {
+                    mbar_wait(&k_full[n & 1], (n >> 1) & 1); mbar_arrive(&k_empty[n & 1]);
+                    mbar_wait(&v_full[n & 1], (n >> 1) & 1); mbar_arrive(&v_empty[n & 1]);
+                }
+            } else {
+                if (total_tiles > 0) issue_s(0);
+                if (total_tiles > 1) issue_s(1);
+                for (int g = 0; g < total_tiles; g++) {
+                    const int n = g / p.n_tiles, t = g % p.n_tiles, s = n & 1, grp = g & 1;
+                    const uint32_t tP = tmem_base + grp * 256, tO = tP + 128;
+                    if (t == 0) mbar_wait(&v_full[s], (n >> 1) & 1);
+                    mbar_wait(&p_full[grp], (g >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t aV = smem_u32(sV + s * kSnKVBytes);
+                    for (int k = 0; k < ksteps; k++)
+                        umma_f16_ts(tO, tP + k * 8, make_smem_desc_sw128(aV + k * 2048, 8192, 1024), idesc_pv, k > 0);
+                    umma_commit(&o_full[grp]);
+                    if (t == p.n_tiles - 1) umma_commit(&v_empty[s]);
+                    if (g + 2 < total_tiles) issue_s(g + 2);
+                }
+            }
+        }
+    } else if (warp < 2 + kSnMathWarps) {
+        // ================================ softmax / epilogue: two groups of 4 warps ================================
+        // group = tile parity; one thread per query row (TMEM lane), all keys of the row
+        const int quad = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const int rl = quad * 32 + lane;
+        const uint32_t tS = tmem_base + grp * 256 + (uint32_t(quad * 32) << 16);
+        const uint32_t tO = tS + 128;
+        const int mode = fq_mode(p.q_out);
+        for (int g = grp; g < total_tiles; g += 2) {
+            const int n = g / p.n_tiles, t = g % p.n_tiles, s = n & 1;
+            const int bh = blockIdx.x + n * gridDim.x;
+            const int b = bh / p.H, h = bh % p.H;
+            const int row = t * 128 + rl;
+            const uint8_t* cK = sK + s * kSnKVBytes;
+            const uint8_t* cV = sV + s * kSnKVBytes;
+            // the loads themselves must be observed by this thread before it reads the tiles
+            mbar_wait(&k_full[s], (n >> 1) & 1);
+            mbar_wait(&q_full[g & 1], (g >> 1) & 1);
+            // keys beyond the tensor-core part: s = q . k on the CUDA cores
+            float sx[kSnExtraMax];
+#pragma unroll
+            for (int e = 0; e < kSnExtraMax; e++)
+                sx[e] = e < p.n_extra ? sn_dot64(sQ + (g & 1) * kSnTile, rl, cK, p.Nk + e) : -INFINITY;
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&q_empty[g & 1]); mbar_arrive(&k_empty[s]); }
+            mbar_wait(&s_full[grp], (g >> 1) & 1);
+            tc_fence_after();
+            // pass 1: row max
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < kSnExtraMax; e++) mx0 = fmaxf(mx0, sx[e]);
+#pragma unroll 1
+            for (int k0 = 0; k0 < p.Nk; k0 += 32) {
+                if (k0 + 32 <= p.Nk) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tS + k0, v);
+                    tmem_ld_wait();
+                    if (k0 + 32 <= p.N) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            mx0 = fmaxf(mx0, __uint_as_float(v[2 * i]));
+                            mx1 = fmaxf(mx1, __uint_as_float(v[2 * i + 1]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) if (k0 + i < p.N) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+                    }
+                } else {
+                    uint32_t v[16];
+                    tmem_ld_32x16(tS + k0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) if (k0 + i < p.N) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+                }
+            }
+            const float m = fmaxf(mx0, mx1) * p.scale_log2;
+            // pass 2: P = exp2(s * c - m) -> fp16, written over the S columns already consumed
+            float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll 1
+            for (int k0 = 0; k0 < p.Nk; k0 += 32) {
+                if (k0 + 32 <= p.Nk) {
+                    uint32_t v[32], w[16];
+                    tmem_ld_32x32(tS + k0, v);
+                    tmem_ld_wait();
+                    if (k0 + 32 <= p.N) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float p0 = ex2_fast(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m));
+                            const float p1 = ex2_fast(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m));
+                            sum0 += p0; sum1 += p1;
+                            w[i] = pack_h2_rn(p0, p1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float p0 = k0 + 2 * i < p.N ? ex2_fast(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m)) : 0.f;
+                            const float p1 = k0 + 2 * i + 1 < p.N ? ex2_fast(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m)) : 0.f;
+                            sum0 += p0; sum1 += p1;
+                            w[i] = pack_h2_rn(p0, p1);
+                        }
+                    }
+                    tmem_st_32x16(tS + (k0 >> 1), w);
+                } else {
+                    uint32_t v[16], w[8];
+                    tmem_ld_32x16(tS + k0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float p0 = k0 + 2 * i < p.N ? ex2_fast(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m)) : 0.f;
+                        const float p1 = k0 + 2 * i + 1 < p.N ? ex2_fast(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m)) : 0.f;
+                        sum0 += p0; sum1 += p1;
+                        w[i] = pack_h2_rn(p0, p1);
+                    }
+                    tmem_st_32x8(tS + (k0 >> 1), w);
+                }
+            }
+            float px[kSnExtraMax];
+#pragma unroll
+            for (int e = 0; e < kSnExtraMax; e++) {
+                px[e] = e < p.n_extra ? ex2_fast(fmaf(sx[e], p.scale_log2, -m)) : 0.f;
+                sum0 += px[e];
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[grp]);
+            const float l = sum0 + sum1;
+            // O = P V (+ the extra keys' p * v)
+            mbar_wait(&v_full[s], (n >> 1) & 1);
+            mbar_wait(&o_full[grp], (g >> 1) & 1);
+            tc_fence_after();
+            float o[64];
+            {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(tO, v0);
+                tmem_ld_32x32(tO + 32, v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&o_empty[grp]);
+#pragma unroll
+                for (int i = 0; i < 32; i++) { o[i] = __uint_as_float(v0[i]); o[32 + i] = __uint_as_float(v1[i]); }
+            }
+            for (int e = 0; e < p.n_extra; e++) {
+                const int j = p.Nk + e;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const uint4 wv = *reinterpret_cast<const uint4*>(cV + j * 128 + ((c ^ (j & 7)) << 4));
+                    const __half2* hv = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const float2 f = __half22float2(hv[u]);
+                        o[8 * c + 2 * u] = fmaf(px[e], f.x, o[8 * c + 2 * u]);
+                        o[8 * c + 2 * u + 1] = fmaf(px[e], f.y, o[8 * c + 2 * u + 1]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&v_empty[s]);
+            if (row < p.N) {
+                const float inv = 1.0f / l;
+                const int64_t grow = int64_t(b) * p.N + row;
+                if (mode == 1) {
+#pragma unroll
+                    for (int i = 0; i < 64; i++) o[i] = fq_half_fast(o[i] * inv);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 64; i++) o[i] = fq_apply(o[i] * inv, mode, p.q_out);
+                }
+                if (p.out_dtype == MV_F16) {
+                    __half* dst = reinterpret_cast<__half*>(p.out) + grow * p.ld_out + h * 64;
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        reinterpret_cast<uint4*>(dst)[i] =
+                            make_uint4(pack_h2_satf(o[8 * i], o[8 * i + 1]), pack_h2_satf(o[8 * i + 2], o[8 * i + 3]),
+                                       pack_h2_satf(o[8 * i + 4], o[8 * i + 5]), pack_h2_satf(o[8 * i + 6], o[8 * i + 7]));
+                } else {
+                    float* dst = reinterpret_cast<float*>(p.out) + grow * p.ld_out + h * 64;
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        reinterpret_cast<float4*>(dst)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+                if (p.lse != nullptr) p.lse[(int64_t(b) * p.H + h) * p.N + row] = m + log2f(l);
+            }
+        }
+    } else {
+        // ================================ SIMT tail rows: the tail warps alternate (image, head) pairs ================================
+        const int tw = warp - (2 + kSnMathWarps);
+        for (int n = 0; n < n_local; n++) {
+            const int s = n & 1;
+            if ((n % kSnTailWarps) != tw) continue;
+            const int bh = blockIdx.x + n * gridDim.x;
+            const int b = bh / p.H, h = bh % p.H;
+            const uint32_t ph = (n >> 1) & 1;
+            mbar_wait_relaxed(&k_full[s], ph);
+            mbar_wait_relaxed(&v_full[s], ph);
+            for (int r = 0; r < p.n_tail; r++)
+                sn_tail_row_fwd(p, sK + s * kSnKVBytes, sV + s * kSnKVBytes, s_tail + tw * (64 + kSnMaxKeys), b, h,
+                                p.n_tiles * 128 + r, lane);
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&k_empty[s]); mbar_arrive(&v_empty[s]); }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+
+constexpr int kSnFwdSmem = 4 * kSnKVBytes + 2 * kSnTile + kSnTailWarps * (64 + kSnMaxKeys) * 4 + 256 + 1024;
+
+}  // namespace mv
+
+using namespace mv;
+
+// dispatch rule shared with attention.cu
+// keys on the tensor cores: a multiple of 16, at most 256 (two score tiles share the 512 TMEM columns);
+// up to kSnExtraMax keys beyond that are folded in by the math threads
+static void sn_key_split(int N, int* Nk, int* n_extra) {
+    const int rem = N % 16;
+    if (rem > 0 && rem <= kSnExtraMax && N > 16) { *Nk = N - rem; *n_extra = rem; }
+    else { *Nk = (N + 15) & ~15; *n_extra = 0; }
+}
+extern "C" int mv_attention_sn_supported(int N) {
+    int Nk, ne;
+    sn_key_split(N, &Nk, &ne);
+    return Nk <= 256 ? 1 : 0;
+}
+
+int mv_attention_fwd_sn(const void* qkv, void* out, int out_dtype, float* lse, int B, int H, int N,
+                        float scale, int q_out_exp, int q_out_man, void* stream) {
+    const int D = H * 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MV_CUDA(cudaFuncSetAttribute(attn_fwd_sn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSnFwdSmem));
+        attr_done = true;
+    }
+    CUtensorMap t128, t16;
+    if (make_tmap_3d(&t128, qkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 128, 1)) return 1;
+    if (make_tmap_3d(&t16, qkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 16, 1)) return 1;
+    SnFwdDev p;
+    p.B = B; p.H = H; p.N = N; p.D = D;
+    sn_key_split(N, &p.Nk, &p.n_extra);
+    p.Nld = p.Nk + (p.n_extra > 0 ? 16 : 0);
+    const int tail = N % 128;
+    if (tail > 0 && tail <= kSnTailMax) { p.n_tiles = N / 128; p.n_tail = tail; }
+    else { p.n_tiles = (N + 127) / 128; p.n_tail = 0; }
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.qkv = reinterpret_cast<const __half*>(qkv);
+    p.out = out; p.out_dtype = out_dtype; p.ld_out = D;
+    p.q_out = FloatFmt{q_out_exp, q_out_man};
+    p.lse = lse;
+    const int n_bh = B * H;
+    const int grid = n_bh < kNumSMs ? n_bh : kNumSMs;
+    attn_fwd_sn_kernel<<<grid, kSnFwdThreads, kSnFwdSmem, static_cast<cudaStream_t>(stream)>>>(t128, t16, p);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "attention fwd (short-sequence) launch");
+}

@@ -61,6 +61,11 @@ def lib():
     return _lib
 
 
+def set_option(name, value):
+    """Library-wide switch (mv_set_option in include/mv_b200.h), e.g. set_option("attn_sn", 0)."""
+    _check(lib().mv_set_option(name.encode(), int(value)), "mv_set_option")
+
+
 def _check(rc, what):
     if rc != 0:
         raise MvError("%s failed: %s" % (what, lib().mv_last_error().decode()))
