@@ -740,6 +740,8 @@ namespace mv { extern int g_opt_attn_sn; }
 extern "C" int mv_attention_sn_supported(int N);
 int mv_attention_fwd_sn(const void* qkv, void* out, int out_dtype, float* lse, int B, int H, int N,
                         float scale, int q_out_exp, int q_out_man, void* stream);
+int mv_attention_bwd_sn(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
+                        void* dqkv, int B, int H, int N, float scale, void* stream);
 
 extern "C" int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float* lse, int B, int H, int N,
                                 float scale, int q_out_exp, int q_out_man, void* stream) {
@@ -770,6 +772,8 @@ extern "C" int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float
 extern "C" int mv_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
                                 float* dq_accum, void* dqkv, int B, int H, int N, float scale, void* stream) {
     MV_CHECK(B > 0 && H > 0 && N > 0 && qkv && o && d_o && lse && delta && dqkv, "mv_attention_bwd: bad arguments");
+    if (g_opt_attn_sn && N <= 272)
+        return mv_attention_bwd_sn(qkv, o, d_o, lse, delta, dqkv, B, H, N, scale, stream);
     const int D = H * 64;
     static bool attr_done = false;
     if (!attr_done) {

@@ -480,6 +480,417 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
 
 constexpr int kSnFwdSmem = 4 * kSnKVBytes + 2 * kSnTile + kSnTailWarps * (64 + kSnMaxKeys) * 4 + 256 + 1024;
 
+
+// =====================================================================================
+// Backward.  One persistent CTA per SM walks (image, head) pairs; Q and dO of the pair (<= 272 rows)
+// are resident in shared memory, K_j / V_j stream through a 2-stage ring, one 128-key tile per pass.
+// Everything is computed TRANSPOSED — keys on the TMEM lanes, query rows on the columns:
+//   pre   S^T = K_j Q_c^T,  dP^T = V_j dO_c^T                     [128 keys x 64 rows] per block
+//   math  P^T = exp2(S^T c - L_row),  dS^T = P^T (dP^T - Delta_row) scale      (one thread per key)
+//   post  dV_j += P^T dO_c,  dK_j += dS^T Q_c      A = P^T / dS^T straight from TMEM (fp16, in place)
+//         dQ_i += dS_i K_j   per pair of blocks     A = the two blocks' dS^T tiles in shared memory
+//                                                   (MN-major: 64 query rows contiguous per key)
+// so P never leaves TMEM, dV_j / dK_j / dQ_i accumulate in TMEM (no atomics, no dQ pass, deterministic)
+// and the 512 TMEM columns hold two blocks in flight (one per math group of 4 warps) + 4 accumulators.
+// Rows >= 256 (the 257th token) form a 16-wide tail block; their dQ has no TMEM accumulator and is
+// reduced on the CUDA cores into shared memory.  Keys beyond N are zero rows (TMA fill) and fall out.
+constexpr int kSnBwdThreads = 32 * (2 + 8);
+constexpr int kSnQBytes = kSnMaxKeys * 128;            // Q or dO of one pair: 272 rows x 128 B
+constexpr int kSnOffQ = 4 * kSnTile;
+constexpr int kSnOffDO = kSnOffQ + kSnQBytes;
+constexpr int kSnOffDS = kSnOffDO + kSnQBytes;
+constexpr int kSnOffVec = kSnOffDS + 4 * kSnTile;      // L[272], Delta[272], dQ tail accumulators [16][64]
+constexpr int kSnOffBar = kSnOffVec + (2 * kSnMaxKeys + 16 * 64) * 4;
+constexpr int kSnBwdSmem = kSnOffBar + 256 + 1024;
+
+struct SnBwdDev {
+    int B, H, N, D;
+    int n_pass;                 // 128-key tiles
+    int n_reg;                  // regular 64-row blocks per pass (2 per 128 query rows below 256)
+    int tail_w;                 // width (multiple of 16) of the tail block of rows [256, 256 + tail_w); 0 if N <= 256
+    float scale_log2, scale;
+    const float* lse;
+    const __half* o;            // forward output and its gradient, [B*N, D]: Delta = rowsum(dO * O) per head
+    const __half* d_o;
+    __half* dqkv; int ld_dqkv;
+};
+
+__global__ void __launch_bounds__(kSnBwdThreads, 1)
+attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv16,
+                   const __grid_constant__ CUtensorMap tm_do128, const __grid_constant__ CUtensorMap tm_do16,
+                   const __grid_constant__ SnBwdDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;                                   // [2 stages][128 x 128 B]
+    uint8_t* sV = smem + 2 * kSnTile;
+    uint8_t* sQ = smem + kSnOffQ;                         // rows 0..271
+    uint8_t* sdO = smem + kSnOffDO;
+    uint8_t* sdS = smem + kSnOffDS;                       // ring of 4 dS^T tiles [128 keys][64 rows]
+    float* sL = reinterpret_cast<float*>(smem + kSnOffVec);
+    float* sDelta = sL + kSnMaxKeys;
+    float* sdQt = sDelta + kSnMaxKeys;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSnOffBar);
+    uint64_t* kv_full = bars;           // [2]
+    uint64_t* kv_empty = bars + 2;      // [2]
+    uint64_t* qdo_full = bars + 4;
+    uint64_t* qdo_empty = bars + 5;
+    uint64_t* sdp_full = bars + 6;      // [2] per math group
+    uint64_t* pds_full = bars + 8;      // [2]
+    uint64_t* acc_full = bars + 10;
+    uint64_t* acc_empty = bars + 11;
+    uint64_t* dq_full = bars + 12;
+    uint64_t* dq_empty = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_bh = p.B * p.H;
+    const int n_local = blockIdx.x < n_bh ? (n_bh - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int nblk = p.n_reg + (p.tail_w > 0 ? 1 : 0);           // blocks per pass
+    const int nb_bh = p.n_pass * nblk;                            // blocks per (image, head)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv128); tma_prefetch_desc(&tm_qkv16);
+        tma_prefetch_desc(&tm_do128); tma_prefetch_desc(&tm_do16);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+            mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], 4);
+        }
+        mbar_init(qdo_full, 1); mbar_init(qdo_empty, 1);
+        mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
+        mbar_init(dq_full, 1); mbar_init(dq_empty, 8);
+        fence_barrier_init();
+    }
+    // the dS^T tiles feed a K dimension: rows of keys that no thread writes must hold finite values
+    for (int i = threadIdx.x; i < 4 * kSnTile / 16; i += kSnBwdThreads)
+        reinterpret_cast<uint4*>(sdS)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: group g: S^T [g*128, +64) (P^T fp16 in place), dP^T [g*128+64, +64) (dS^T fp16 in place);
+    // dV_j 256, dK_j 320, dQ_0 384, dQ_1 448
+    const uint32_t tdV = tmem_base + 256, tdK = tmem_base + 320, tdQ = tmem_base + 384;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int pc = 0;
+            const int q_tiles = p.n_reg >> 1;
+            for (int n = 0; n < n_local; n++) {
+                const int bh = blockIdx.x + n * gridDim.x;
+                const int b = bh / p.H, h = bh % p.H;
+                for (int j = 0; j < p.n_pass; j++, pc++) {
+                    const int st = pc & 1;
+                    mbar_wait_relaxed(&kv_empty[st], ((pc >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&kv_full[st], 2 * kSnTile);
+                    tma_load_3d(sK + st * kSnTile, &tm_qkv128, &kv_full[st], p.D + h * 64, j * 128, b);
+                    tma_load_3d(sV + st * kSnTile, &tm_qkv128, &kv_full[st], 2 * p.D + h * 64, j * 128, b);
+                    if (j == 0) {
+                        mbar_wait_relaxed(qdo_empty, (n & 1) ^ 1);
+                        mbar_arrive_expect_tx(qdo_full, 2 * (q_tiles * kSnTile + p.tail_w * 128));
+                        for (int i = 0; i < q_tiles; i++) {
+                            tma_load_3d(sQ + i * kSnTile, &tm_qkv128, qdo_full, h * 64, i * 128, b);
+                            tma_load_3d(sdO + i * kSnTile, &tm_do128, qdo_full, h * 64, i * 128, b);
+                        }
+                        for (int r = 0; r < p.tail_w; r += 16) {
+                            tma_load_3d(sQ + (256 + r) * 128, &tm_qkv16, qdo_full, h * 64, 256 + r, b);
+                            tma_load_3d(sdO + (256 + r) * 128, &tm_do16, qdo_full, h * 64, 256 + r, b);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        // the whole warp walks the schedule (uniform values live in uniform registers); one elected lane issues
+        {
+            const bool leader = elect_one();
+            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO), adS = smem_u32(sdS);
+            const uint32_t idesc_mn = make_idesc(0, 0, 0, 1, 128, 64);     // A K-major (TMEM), B MN-major, N = 64
+            const uint32_t idesc_tt = make_idesc(0, 0, 1, 1, 128, 64);     // A MN-major, B MN-major, N = 64
+            const uint32_t idesc_s64 = make_idesc(0, 0, 0, 0, 128, 64);
+            const uint32_t idesc_stail = make_idesc(0, 0, 0, 0, 128, p.tail_w > 0 ? p.tail_w : 16);
+            int gb0 = 0, pc0 = 0;
+            for (int n = 0; n < n_local; n++, gb0 += nb_bh, pc0 += p.n_pass) {
+                mbar_wait(qdo_full, n & 1);
+                // Descriptors are built once per block and advanced with one 64-bit add per MMA: this lane
+                // issues ~25 MMAs of 32 tensor-pipe cycles each per block and must not be the bottleneck.
+                auto pre = [&](int lb) {
+                    const int gb = gb0 + lb, g = gb & 1, j = lb / nblk, c = lb % nblk;
+                    const int pc = pc0 + j, st = pc & 1;
+                    if (c == 0) mbar_wait(&kv_full[st], (pc >> 1) & 1);
+                    tc_fence_after();
+                    const bool regular = c < p.n_reg;
+                    const int row0 = regular ? 64 * c : 256;
+                    const uint32_t idesc = regular ? idesc_s64 : idesc_stail;
+                    const uint32_t tS = tmem_base + g * 128, tdP = tS + 64;
+                    const uint64_t dk = make_smem_desc_sw128(aK + st * kSnTile, 16, 1024);
+                    const uint64_t dv = make_smem_desc_sw128(aV + st * kSnTile, 16, 1024);
+                    const uint64_t dq = make_smem_desc_sw128(aQ + row0 * 128, 16, 1024);
+                    const uint64_t dd = make_smem_desc_sw128(adO + row0 * 128, 16, 1024);
+                    if (leader) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) umma_f16(tS, dk + 2 * k, dq + 2 * k, idesc, k > 0);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) umma_f16(tdP, dv + 2 * k, dd + 2 * k, idesc, k > 0);
+                        umma_commit(&sdp_full[g]);
+                    }
+                    __syncwarp();
+                };
+                auto post = [&](int lb) {
+                    const int gb = gb0 + lb, g = gb & 1, j = lb / nblk, c = lb % nblk;
+                    const int pc = pc0 + j, st = pc & 1;
+                    const bool regular = c < p.n_reg;
+                    const int row0 = regular ? 64 * c : 256;
+                    const uint32_t tS = tmem_base + g * 128, tdP = tS + 64;
+                    const uint64_t bdo = make_smem_desc_sw128(adO + row0 * 128, 8192, 1024);     // B = dO rows, MN-major
+                    const uint64_t bq = make_smem_desc_sw128(aQ + row0 * 128, 8192, 1024);
+                    mbar_wait(&pds_full[g], (gb >> 1) & 1);
+                    if (c == 0 && pc > 0) mbar_wait(acc_empty, (pc - 1) & 1);       // dV / dK of the previous pass were read
+                    tc_fence_after();
+                    const uint32_t acc0 = c > 0 ? 1u : 0u;
+                    if (regular && (c & 1) && j == 0 && (c >> 1) == 0 && n > 0) { mbar_wait(dq_empty, (n - 1) & 1); tc_fence_after(); }
+                    if (!leader) { __syncwarp(); return; }
+                    if (regular) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) umma_f16_ts(tdV, tS + k * 8, bdo + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+#pragma unroll
+                        for (int k = 0; k < 4; k++) umma_f16_ts(tdK, tdP + k * 8, bq + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                    } else {
+                        for (int k = 0; k < (p.tail_w >> 4); k++) umma_f16_ts(tdV, tS + k * 8, bdo + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                        for (int k = 0; k < (p.tail_w >> 4); k++) umma_f16_ts(tdK, tdP + k * 8, bq + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                    }
+                    if (regular && (c & 1)) {
+                        // dQ_i += dS_i K_j: A = the pair's dS^T tiles (M = 2 x 64 rows, K = 128 keys)
+                        const int i = c >> 1;
+                        const int buf = (j * p.n_reg + c - 1) & 3;
+                        const uint64_t ads = make_smem_desc_sw128(adS + buf * kSnTile, kSnTile, 1024);
+                        const uint64_t bk = make_smem_desc_sw128(aK + st * kSnTile, 8192, 1024);
+                        const uint32_t accq = j > 0 ? 1u : 0u;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) umma_f16(tdQ + i * 64, ads + 128 * k, bk + 128 * k, idesc_tt, accq | uint32_t(k > 0));
+                    }
+                    if (c == nblk - 1) {
+                        umma_commit(acc_full);
+                        umma_commit(&kv_empty[st]);
+                        if (j == p.n_pass - 1) { umma_commit(dq_full); umma_commit(qdo_empty); }
+                    }
+                    __syncwarp();
+                };
+                pre(0);
+                if (nb_bh > 1) pre(1);
+                for (int lb = 0; lb < nb_bh; lb++) {
+                    post(lb);
+                    if (lb + 2 < nb_bh) pre(lb + 2);
+                }
+            }
+        }
+    } else {
+        // ================================ math: two groups of four warps, one thread per key ================================
+        const int quad = warp & 3;
+        const int g = (warp - 2) >> 2;
+        const int lr = quad * 32 + lane;                     // key row within the 128-key tile = TMEM lane
+        const int mt = threadIdx.x - 64;                     // 0..255
+        const uint32_t lane_off = uint32_t(quad * 32) << 16;
+        const uint32_t tS = tmem_base + g * 128 + lane_off, tdP = tS + 64;
+        int gb0 = 0, pc0 = 0;
+        for (int n = 0; n < n_local; n++, gb0 += nb_bh, pc0 += p.n_pass) {
+            const int bh = blockIdx.x + n * gridDim.x;
+            const int b = bh / p.H, h = bh % p.H;
+            // per-row statistics of this pair; rows >= N get L = +inf so that their P is exactly 0
+            for (int r = mt; r < kSnMaxKeys; r += 256) {
+                float Lr = INFINITY, dl = 0.f;
+                if (r < p.N) {
+                    Lr = p.lse[(int64_t(b) * p.H + h) * p.N + r];
+                    const uint4* a = reinterpret_cast<const uint4*>(p.d_o + (int64_t(b) * p.N + r) * p.D + h * 64);
+                    const uint4* c4 = reinterpret_cast<const uint4*>(p.o + (int64_t(b) * p.N + r) * p.D + h * 64);
+#pragma unroll
+                    for (int t = 0; t < 8; t++) {
+                        const uint4 x = a[t], y = c4[t];
+                        const __half2* xh = reinterpret_cast<const __half2*>(&x);
+                        const __half2* yh = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const float2 fx = __half22float2(xh[u]), fy = __half22float2(yh[u]);
+                            dl = fmaf(fx.x, fy.x, dl); dl = fmaf(fx.y, fy.y, dl);
+                        }
+                    }
+                }
+                sL[r] = Lr;
+                sDelta[r] = dl;
+            }
+            for (int i = mt; i < 16 * 64; i += 256) sdQt[i] = 0.f;
+            named_bar_sync(1, 256);
+            for (int j = 0; j < p.n_pass; j++) {
+                const int pc = pc0 + j, st = pc & 1;
+                const int key = j * 128 + lr;
+                const bool warp_live = j * 128 + quad * 32 < p.N;      // some key of this warp exists
+                for (int c = 0; c < nblk; c++) {
+                    const int gb = gb0 + j * nblk + c;
+                    if ((gb & 1) != g) continue;
+                    const bool regular = c < p.n_reg;
+                    const int width = regular ? 64 : p.tail_w;
+                    const int row0 = regular ? 64 * c : 256;
+                    mbar_wait(&sdp_full[g], (gb >> 1) & 1);
+                    tc_fence_after();
+                    if (warp_live) {
+                        uint8_t* ds_row = sdS + ((j * p.n_reg + c) & 3) * kSnTile + lr * 128;
+                        for (int c0 = 0; c0 < width; c0 += 32) {
+                            if (c0 + 32 <= width) {
+                                uint32_t sv[32], dv[32], wp[16], wd[16];
+                                tmem_ld_32x32(tS + c0, sv);
+                                tmem_ld_32x32(tdP + c0, dv);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int q4 = 0; q4 < 8; q4++) {
+                                    const float4 L4 = *reinterpret_cast<const float4*>(sL + row0 + c0 + 4 * q4);
+                                    const float4 D4 = *reinterpret_cast<const float4*>(sDelta + row0 + c0 + 4 * q4);
+                                    const float Ls[4] = {L4.x, L4.y, L4.z, L4.w}, Ds[4] = {D4.x, D4.y, D4.z, D4.w};
+                                    float pe[4], de[4];
+#pragma unroll
+                                    for (int u = 0; u < 4; u++) {
+                                        pe[u] = ex2_fast(fmaf(__uint_as_float(sv[4 * q4 + u]), p.scale_log2, -Ls[u]));
+                                        de[u] = pe[u] * (__uint_as_float(dv[4 * q4 + u]) - Ds[u]) * p.scale;
+                                    }
+                                    wp[2 * q4] = pack_h2_rn(pe[0], pe[1]); wp[2 * q4 + 1] = pack_h2_rn(pe[2], pe[3]);
+                                    wd[2 * q4] = pack_h2_satf(de[0], de[1]); wd[2 * q4 + 1] = pack_h2_satf(de[2], de[3]);
+                                }
+                                tmem_st_32x16(tS + (c0 >> 1), wp);
+                                tmem_st_32x16(tdP + (c0 >> 1), wd);
+                                if (regular) {
+#pragma unroll
+                                    for (int t = 0; t < 4; t++)
+                                        *reinterpret_cast<uint4*>(ds_row + ((((c0 >> 3) + t) ^ (lr & 7)) << 4)) =
+                                            make_uint4(wd[4 * t], wd[4 * t + 1], wd[4 * t + 2], wd[4 * t + 3]);
+                                }
+                            } else {
+                                // 16-wide tail block: rows 256 .. 271
+                                uint32_t sv[16], dv[16], wp[8], wd[8];
+                                tmem_ld_32x16(tS + c0, sv);
+                                tmem_ld_32x16(tdP + c0, dv);
+                                tmem_ld_wait();
+                                float de[16];
+#pragma unroll
+                                for (int u = 0; u < 16; u++) {
+                                    const float pe = ex2_fast(fmaf(__uint_as_float(sv[u]), p.scale_log2, -sL[row0 + c0 + u]));
+                                    de[u] = pe * (__uint_as_float(dv[u]) - sDelta[row0 + c0 + u]) * p.scale;
+                                    sv[u] = __float_as_uint(pe);
+                                }
+#pragma unroll
+                                for (int u = 0; u < 8; u++) {
+                                    wp[u] = pack_h2_rn(__uint_as_float(sv[2 * u]), __uint_as_float(sv[2 * u + 1]));
+                                    wd[u] = pack_h2_satf(de[2 * u], de[2 * u + 1]);
+                                }
+                                tmem_st_32x8(tS + (c0 >> 1), wp);
+                                tmem_st_32x8(tdP + (c0 >> 1), wd);
+                                // dQ of these rows: sum over this warp's 32 keys of dS[row, key] K[key, :] on the
+                                // CUDA cores (lane l owns dims 2l, 2l+1), accumulated in shared memory
+                                const int nrows = min(16, p.N - (row0 + c0));
+                                const int cl = lane >> 2, wi = (lane & 3) * 4;
+#pragma unroll
+                                for (int u = 0; u < 16; u++) {
+                                    if (u < nrows) {
+                                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+                                        for (int kk = 0; kk < 32; kk++) {
+                                            const float v = __shfl_sync(0xffffffffu, de[u], kk);
+                                            const int kr = quad * 32 + kk;
+                                            const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(
+                                                sK + st * kSnTile + kr * 128 + ((cl ^ (kr & 7)) << 4) + wi));
+                                            a0 = fmaf(v, kf.x, a0); a1 = fmaf(v, kf.y, a1);
+                                        }
+                                        atomicAdd(&sdQt[(c0 + u) * 64 + 2 * lane], a0);
+                                        atomicAdd(&sdQt[(c0 + u) * 64 + 2 * lane + 1], a1);
+                                    }
+                                }
+                            }
+                        }
+                        tmem_st_wait();
+                        fence_proxy_async();
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&pds_full[g]);
+                }
+                // ---- pass epilogue: group 0 stores dV_j, group 1 stores dK_j
+                mbar_wait(acc_full, pc & 1);
+                tc_fence_after();
+                {
+                    uint32_t v0[32], v1[32];
+                    const uint32_t src = (g == 0 ? tdV : tdK) + lane_off;
+                    tmem_ld_32x32(src, v0);
+                    tmem_ld_32x32(src + 32, v1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                    if (key < p.N) {
+                        __half* dst = p.dqkv + (int64_t(b) * p.N + key) * p.ld_dqkv + (g == 0 ? 2 : 1) * p.D + h * 64;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            reinterpret_cast<uint4*>(dst)[i] = make_uint4(
+                                pack_h2_satf(__uint_as_float(v0[8 * i]), __uint_as_float(v0[8 * i + 1])),
+                                pack_h2_satf(__uint_as_float(v0[8 * i + 2]), __uint_as_float(v0[8 * i + 3])),
+                                pack_h2_satf(__uint_as_float(v0[8 * i + 4]), __uint_as_float(v0[8 * i + 5])),
+                                pack_h2_satf(__uint_as_float(v0[8 * i + 6]), __uint_as_float(v0[8 * i + 7])));
+                            reinterpret_cast<uint4*>(dst)[4 + i] = make_uint4(
+                                pack_h2_satf(__uint_as_float(v1[8 * i]), __uint_as_float(v1[8 * i + 1])),
+                                pack_h2_satf(__uint_as_float(v1[8 * i + 2]), __uint_as_float(v1[8 * i + 3])),
+                                pack_h2_satf(__uint_as_float(v1[8 * i + 4]), __uint_as_float(v1[8 * i + 5])),
+                                pack_h2_satf(__uint_as_float(v1[8 * i + 6]), __uint_as_float(v1[8 * i + 7])));
+                        }
+                    }
+                }
+            }
+            // ---- pair epilogue: group g stores dQ of query rows [128 g, 128 g + 128)
+            mbar_wait(dq_full, n & 1);
+            tc_fence_after();
+            {
+                uint32_t v0[32], v1[32];
+                const bool have = g < (p.n_reg >> 1);
+                if (have) {
+                    tmem_ld_32x32(tdQ + g * 64 + lane_off, v0);
+                    tmem_ld_32x32(tdQ + g * 64 + 32 + lane_off, v1);
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dq_empty);
+                const int row = g * 128 + lr;
+                if (have && row < p.N) {
+                    __half* dst = p.dqkv + (int64_t(b) * p.N + row) * p.ld_dqkv + h * 64;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        reinterpret_cast<uint4*>(dst)[i] = make_uint4(
+                            pack_h2_satf(__uint_as_float(v0[8 * i]), __uint_as_float(v0[8 * i + 1])),
+                            pack_h2_satf(__uint_as_float(v0[8 * i + 2]), __uint_as_float(v0[8 * i + 3])),
+                            pack_h2_satf(__uint_as_float(v0[8 * i + 4]), __uint_as_float(v0[8 * i + 5])),
+                            pack_h2_satf(__uint_as_float(v0[8 * i + 6]), __uint_as_float(v0[8 * i + 7])));
+                        reinterpret_cast<uint4*>(dst)[4 + i] = make_uint4(
+                            pack_h2_satf(__uint_as_float(v1[8 * i]), __uint_as_float(v1[8 * i + 1])),
+                            pack_h2_satf(__uint_as_float(v1[8 * i + 2]), __uint_as_float(v1[8 * i + 3])),
+                            pack_h2_satf(__uint_as_float(v1[8 * i + 4]), __uint_as_float(v1[8 * i + 5])),
+                            pack_h2_satf(__uint_as_float(v1[8 * i + 6]), __uint_as_float(v1[8 * i + 7])));
+                    }
+                }
+            }
+            // rows >= 256: dQ from the shared-memory accumulators
+            named_bar_sync(1, 256);
+            for (int i = mt; i < (p.N - 256) * 32; i += 256) {
+                const int r = i >> 5, l2 = i & 31;
+                *reinterpret_cast<uint32_t*>(p.dqkv + (int64_t(b) * p.N + 256 + r) * p.ld_dqkv + h * 64 + 2 * l2) =
+                    pack_h2_satf(sdQt[r * 64 + 2 * l2], sdQt[r * 64 + 2 * l2 + 1]);
+            }
+            named_bar_sync(1, 256);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+
 }  // namespace mv
 
 using namespace mv;
@@ -526,4 +937,35 @@ int mv_attention_fwd_sn(const void* qkv, void* out, int out_dtype, float* lse, i
     attn_fwd_sn_kernel<<<grid, kSnFwdThreads, kSnFwdSmem, static_cast<cudaStream_t>(stream)>>>(t128, t16, p);
     g_launches++;
     return check_cuda(cudaGetLastError(), "attention fwd (short-sequence) launch");
+}
+
+int mv_attention_bwd_sn(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
+                        void* dqkv, int B, int H, int N, float scale, void* stream) {
+    const int D = H * 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MV_CUDA(cudaFuncSetAttribute(attn_bwd_sn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSnBwdSmem));
+        attr_done = true;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUtensorMap q128, q16, d128, d16;
+    if (make_tmap_3d(&q128, qkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 128, 1)) return 1;
+    if (make_tmap_3d(&q16, qkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 16, 1)) return 1;
+    if (make_tmap_3d(&d128, d_o, MV_F16, D, N, B, D, uint64_t(N) * D, 64, 128, 1)) return 1;
+    if (make_tmap_3d(&d16, d_o, MV_F16, D, N, B, D, uint64_t(N) * D, 64, 16, 1)) return 1;
+    (void)delta;                                   // Delta is computed inside the kernel
+    SnBwdDev p;
+    p.B = B; p.H = H; p.N = N; p.D = D;
+    p.n_pass = (N + 127) / 128;
+    p.n_reg = 2 * (((N < 256 ? N : 256) + 127) / 128);
+    p.tail_w = N > 256 ? ((N - 256 + 15) & ~15) : 0;
+    p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+    p.lse = lse;
+    p.o = reinterpret_cast<const __half*>(o); p.d_o = reinterpret_cast<const __half*>(d_o);
+    p.dqkv = reinterpret_cast<__half*>(dqkv); p.ld_dqkv = 3 * D;
+    const int n_bh = B * H;
+    const int grid = n_bh < kNumSMs ? n_bh : kNumSMs;
+    attn_bwd_sn_kernel<<<grid, kSnBwdThreads, kSnBwdSmem, st>>>(q128, q16, d128, d16, p);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "attention bwd (short-sequence) launch");
 }

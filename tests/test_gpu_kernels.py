@@ -110,9 +110,14 @@ def test_layernorm_q(D):
     assert relmax(dg, gr.grad) < 1e-5 and relmax(db, br.grad) < 1e-5 and relmax(dp, want.sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize("B,H,N", [(1, 1, 64), (1, 1, 128), (2, 2, 257), (2, 3, 197), (1, 2, 1000)])
-def test_attention_fwd_bwd(B, H, N):
+@pytest.mark.parametrize("sn", [1, 0])
+@pytest.mark.parametrize("B,H,N", [(1, 1, 64), (1, 1, 128), (2, 2, 257), (2, 3, 197), (1, 2, 1000), (1, 1, 17),
+                                   (2, 1, 130), (2, 1, 131), (2, 1, 256), (1, 2, 272), (1, 1, 273), (40, 6, 257)])
+def test_attention_fwd_bwd(B, H, N, sn, request):
+    """sn=1: short-sequence kernels (attention_sn.cu, N <= 272); sn=0: the general streaming kernels."""
     import mv_native as mv
+    mv.set_option("attn_sn", sn)
+    request.addfinalizer(lambda: mv.set_option("attn_sn", 1))
     torch.manual_seed(N)
     D = H * 64
     qkv = torch.randn(B * N, 3 * D, device=dev).half()
