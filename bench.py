@@ -248,10 +248,14 @@ def run_b200(args):
     h2d = B * 3 * IMAGE * IMAGE * 4 + B * 8
     d2h = 4
 
+    if world > 1:
+        # Tear-down: the captured graph holds NCCL work, and destroy_process_group() has been seen to
+        # hang behind it.  All ranks meet here; non-zero ranks then leave without running destructors.
+        dist.barrier()
+        torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
     # ---- roofline of the dominant kernel class
     with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -323,7 +327,8 @@ def run_b200(args):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

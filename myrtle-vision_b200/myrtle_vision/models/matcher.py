@@ -1,0 +1,79 @@
+"""Bipartite matching between predicted and ground-truth boxes (config 5 loss, host side).
+
+Drop-in for src/myrtle_vision/models/matcher.py:13-87 of the reference (`HungarianMatcher`, same
+constructor, same `forward(outputs, targets)` result: one `(prediction_idx, target_idx)` int64
+pair per image, CPU tensors).  The matching cost is the reference's
+`cost_bbox * L1 + cost_class * (-prob[target class]) + cost_giou * (-GIoU)`, but it is built as
+ONE padded `[B, Q, Tmax]` block on the device (every image only against its own targets) and
+leaves the GPU in a single copy; the reference builds the `[B*Q, sum(T)]` cross product of
+every prediction with every image's targets and throws the off-diagonal blocks away.
+The assignment itself stays SciPy's `linear_sum_assignment`, as in the reference (:83-86).
+"""
+import torch
+from scipy.optimize import linear_sum_assignment
+from torch import nn
+
+
+def cxcywh_to_xyxy(b):
+    cx, cy, w, h = b.unbind(-1)
+    return torch.stack((cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h), dim=-1)
+
+
+def generalized_iou(a, b):
+    """GIoU of xyxy boxes, broadcasting over leading dimensions (a[..., 4] vs b[..., 4])."""
+    area_a = (a[..., 2] - a[..., 0]) * (a[..., 3] - a[..., 1])
+    area_b = (b[..., 2] - b[..., 0]) * (b[..., 3] - b[..., 1])
+    iw = (torch.minimum(a[..., 2], b[..., 2]) - torch.maximum(a[..., 0], b[..., 0])).clamp(min=0)
+    ih = (torch.minimum(a[..., 3], b[..., 3]) - torch.maximum(a[..., 1], b[..., 1])).clamp(min=0)
+    inter = iw * ih
+    union = area_a + area_b - inter
+    iou = inter / union
+    cw = (torch.maximum(a[..., 2], b[..., 2]) - torch.minimum(a[..., 0], b[..., 0])).clamp(min=0)
+    ch = (torch.maximum(a[..., 3], b[..., 3]) - torch.minimum(a[..., 1], b[..., 1])).clamp(min=0)
+    hull = cw * ch
+    return iou - (hull - union) / hull
+
+
+class HungarianMatcher(nn.Module):
+    def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1):
+        super().__init__()
+        self.cost_class = cost_class
+        self.cost_bbox = cost_bbox
+        self.cost_giou = cost_giou
+        assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0, "all costs cant be 0"
+
+    @torch.no_grad()
+    def cost_blocks(self, outputs, targets):
+        """[B, Q, Tmax] cost of matching prediction q of image b to its own target t (padding
+        columns hold copies of valid-shaped dummy boxes and are cut off by the caller)."""
+        logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
+        B, Q = logits.shape[:2]
+        sizes = [int(t["boxes"].shape[0]) for t in targets]
+        tmax = max(sizes) if sizes else 0
+        if tmax == 0:
+            return torch.zeros(B, Q, 0), sizes
+        dev = logits.device
+        ids = torch.zeros(B, tmax, dtype=torch.int64, device=dev)
+        tb = torch.empty(B, tmax, 4, dtype=boxes.dtype, device=dev)
+        tb[..., :2] = 0.5
+        tb[..., 2:] = 1.0
+        for b, t in enumerate(targets):
+            if sizes[b]:
+                ids[b, :sizes[b]] = t["labels"].to(dev)
+                tb[b, :sizes[b]] = t["boxes"].to(dev)
+        prob = logits.softmax(-1)                                         # [B, Q, C+1]
+        c_class = -prob.gather(2, ids[:, None, :].expand(B, Q, tmax))
+        c_bbox = (boxes[:, :, None, :] - tb[:, None, :, :]).abs().sum(-1)
+        c_giou = -generalized_iou(cxcywh_to_xyxy(boxes)[:, :, None, :],
+                                  cxcywh_to_xyxy(tb)[:, None, :, :])
+        C = self.cost_bbox * c_bbox + self.cost_class * c_class + self.cost_giou * c_giou
+        return C.cpu(), sizes
+
+    @torch.no_grad()
+    def forward(self, outputs, targets):
+        C, sizes = self.cost_blocks(outputs, targets)
+        result = []
+        for b, n in enumerate(sizes):
+            i, j = linear_sum_assignment(C[b, :, :n].numpy())
+            result.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
+        return result

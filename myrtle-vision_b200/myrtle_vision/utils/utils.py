@@ -63,3 +63,49 @@ def init_distributed(rank, num_gpus, dist_backend, dist_url, group_name=None):
 
 def cleanup_distributed():
     dist.destroy_process_group()
+
+
+# ---- rank helpers used by the detection criterion / evaluation (reference utils.py:153-260)
+def is_dist_avail_and_initialized():
+    return dist.is_available() and dist.is_initialized()
+
+
+def get_world_size():
+    return dist.get_world_size() if is_dist_avail_and_initialized() else 1
+
+
+def get_rank():
+    return dist.get_rank() if is_dist_avail_and_initialized() else 0
+
+
+def all_gather(data):
+    """Gather any picklable object from every rank -> list (one entry per rank)."""
+    if get_world_size() == 1:
+        return [data]
+    out = [None] * get_world_size()
+    dist.all_gather_object(out, data)
+    return out
+
+
+def reduce_dict(input_dict, average=True):
+    """Sum (or mean) a dict of scalar tensors over ranks; keys are sorted so ranks agree on order."""
+    world = get_world_size()
+    if world < 2:
+        return input_dict
+    with torch.no_grad():
+        names = sorted(input_dict.keys())
+        values = torch.stack([input_dict[k] for k in names], dim=0)
+        dist.all_reduce(values)
+        if average:
+            values /= world
+        return dict(zip(names, values))
+
+
+@torch.no_grad()
+def accuracy(output, target, topk=(1,)):
+    """precision@k in percent, one 0-dim tensor per k; zeros for an empty target."""
+    if target.numel() == 0:
+        return [torch.zeros([], device=output.device)]
+    top = output.topk(max(topk), dim=1).indices                       # [n, maxk]
+    hit = top.eq(target.view(-1, 1))
+    return [hit[:, :k].any(dim=1).float().sum() * (100.0 / target.size(0)) for k in topk]
