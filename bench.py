@@ -33,6 +33,10 @@ for _p in (ROOT, os.path.join(ROOT, "myrtle-vision_b200")):
 ARCH = dict(dim=384, depth=12, heads=6, mlp_dim=1536)
 IMAGE, PATCH, CLASSES = 256, 16, 45
 METRIC = "train images/sec, quantised ViT fwd+bwd"
+DTYPES = {"FP16_32": "f16 operands (exact fake-quant containers), f32 accumulate",
+          "FP16_16": "f16 operands (exact fake-quant containers), f32 accumulate",
+          "TF32": "tf32 operands (exact (8,10) fake-quant values in f32 containers), f32 accumulate",
+          "FP32": "tf32 tensor-core products of f32 operands, f32 accumulate"}
 
 
 def flops_per_image(n_tokens, dim, depth, mlp, classes, patch_dim=768):
@@ -262,37 +266,43 @@ def run_b200(args):
         peaks = json.load(f) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     n_tok = (IMAGE // PATCH) ** 2 + 1
     M, D, Mm, H, L = B * n_tok, ARCH["dim"], ARCH["mlp_dim"], ARCH["heads"], ARCH["depth"]
-    gemm_fwd_flops = 2.0 * M * (768 * D + L * (3 * D * D + D * D + 2 * D * Mm))
-    alg = {   # algorithmic work per STEP of each kernel class
-        "gemm_fwd": ("tensor", gemm_fwd_flops),
-        "gemm_dgrad": ("tensor", 2.0 * M * L * (3 * D * D + D * D + 2 * D * Mm)),
-        "gemm_wgrad": ("tensor", gemm_fwd_flops),
-        "attn_fwd": ("tensor", L * 4.0 * B * H * n_tok * n_tok * 64),
-        "attn_bwd": ("tensor", L * 10.0 * B * H * n_tok * n_tok * 64),
-        "ln_fwd": ("hbm", 2 * L * M * D * 6.0),
-        "ln_bwd": ("hbm", 2 * L * M * D * 18.0),
-        "colsum": ("hbm", L * M * (Mm + 3 * D) * 2.0),
-    }
+    def per_launch_work(name):
+        """(bound, ALGORITHMIC flop or bytes of ONE launch) — DESIGN.md §4 per-unit figures x units per launch."""
+        if name.startswith("gemm_"):
+            m, n, k = (int(v) for v in name.rsplit("_", 1)[1].split("x"))
+            return "tensor", 2.0 * m * n * k
+        table = {
+            "attn_fwd": ("tensor", 4.0 * B * H * n_tok * n_tok * 64),
+            "attn_bwd": ("tensor", 10.0 * B * H * n_tok * n_tok * 64),
+            "ln_fwd": ("hbm", M * D * 6.0),
+            "ln_bwd": ("hbm", M * D * 18.0),
+        }
+        return table.get(name, (None, None))
+
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch", {})
     breakdown, roofline = {}, None
     if kern:
-        top = max(kern.items(), key=lambda kv: kv[1][1])[0]
         for name, (cnt, tot) in sorted(kern.items(), key=lambda kv: -kv[1][1]):
-            breakdown[name] = {"launches_per_step": cnt / args.steps, "ms_per_step": tot / args.steps}
-        bound, work = alg[top]
-        per_launch = work / (kern[top][0] / args.steps)
-        avg_ms = kern[top][1] / kern[top][0]
-        if bound == "tensor":
-            peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            ach = per_launch / avg_ms / 1e9
-            unit = "TFLOP/s"
-        else:
-            peak = peaks.get("hbm_gbs", 6650.0)
-            ach = per_launch / avg_ms / 1e6
-            unit = "GB/s"
-        roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
-                    "frac": ach / peak, "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json (sustained)" if peaks else "fallback",
-                    "avg_launch_ms": avg_ms}
+            entry = {"launches_per_step": cnt / args.steps, "ms_per_step": tot / args.steps}
+            bound, work = per_launch_work(name)
+            if bound is not None:
+                avg_ms = tot / cnt
+                if bound == "tensor":
+                    peak, ach, unit = peaks.get("bf16_tflops_sustained", 1400.0), work / avg_ms / 1e9, "TFLOP/s"
+                else:
+                    peak, ach, unit = peaks.get("hbm_gbs", 6650.0), work / avg_ms / 1e6, "GB/s"
+                entry.update({"bound": bound, "achieved": ach, "unit": unit, "frac": ach / peak,
+                              "avg_launch_ms": avg_ms})
+                if roofline is None:              # the dominant kernel (most time per step)
+                    roofline = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+                                "frac": ach / peak, "traffic": traffic.get(name),
+                                "peak_source": "MEASURED_PEAKS.json (sustained)" if peaks else "fallback",
+                                "avg_launch_ms": avg_ms, "algorithmic_per_launch": work}
+            breakdown[name] = entry
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -306,7 +316,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f16 operands (exact fake-quant containers), f32 accumulate",
+        "vs_baseline": None, "dtype": DTYPES[args.q_format],
         "data": "synthetic",
         "config": {"workload": "ViT-Small cls 256x256x3, 45 classes, q_format=%s, batch %d/GPU, fwd+CE+bwd%s"
                                % (args.q_format, B, " + NCCL grad all-reduce" if world > 1 else ""),
@@ -337,7 +347,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--q-format", default="FP16_32", choices=["FP16_32", "FP16_16"])
+    ap.add_argument("--q-format", default="FP16_32", choices=["FP16_32", "FP16_16", "TF32", "FP32"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")

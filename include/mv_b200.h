@@ -137,6 +137,12 @@ int mv_cls_rows(const float* cls, const float* pos_q, float* x, int B, int n_tok
                 int q_man, void* stream);
 /* fp32 -> fp16 (saturating) / bf16 copy of n elements (n % 4 == 0) */
 int mv_convert_f32(const float* in, void* out, int out_dtype, int64_t n, void* stream);
+/* fp16 / fp32 in[rows, cols] (row pitch ld elements) times `mul` -> fp32 copy out[rows, cols] and / or
+ * fp32 transpose out_t[cols, rows] with row pitch ld_t >= rows (either may be NULL).  The 32-bit formats (q_format TF32 / FP32) run
+ * their contractions as kind::tf32 on K-major fp32 operands; this prepares dY^T / X^T for wgrad and
+ * widens the fp16 attention tensors. */
+int mv_widen_transpose(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out,
+                       float* out_t, int64_t ld_t, float mul, void* stream);
 
 /* Library-wide switches (testing / A-B measurement).  "attn_sn": 1 (default) = sequences of at most
  * 272 keys use the resident-K/V short-sequence attention kernels, 0 = always the blocked kernels. */
@@ -155,6 +161,32 @@ int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float* lse, int 
  * key blocks with fp32 red.add (fast path).  NULL: deterministic two-pass variant without atomics. */
 int mv_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
                      float* dq_accum, void* dqkv, int B, int H, int N, float scale, void* stream);
+
+/* ---------------------------------------------------------------- optimizer step
+ * Multi-tensor AdamW (torch.optim.AdamW / timm AdamW update rule, reference classification/train.py:
+ * 161-166, 274-277) in ONE launch, fused with the weight fake-quantisation of the next step: for a
+ * Linear weight (wq != NULL) the kernel also writes q(W) [rows, cols] and q(W)^T [cols, rows] in
+ * the tensor-core operand container, replacing torch.nn.qat.Linear's per-forward weight_fake_quant.
+ * `chunk0`: index of the tensor's first 1024-element chunk (a 32x32 tile for weights with wq); chunks
+ * are numbered consecutively over the table and total_chunks is their sum.
+ * hyper_dev (device, 6 floats): beta1, beta2, eps, step (>= 1), inv_scale (gradient un-scale),
+ * found_inf (non-zero: parameters and moments untouched, operands still emitted). */
+typedef struct {
+    float* param;                 /* fp32 [n], updated in place */
+    const float* grad;            /* fp32 [n] */
+    float* exp_avg;               /* fp32 [n] */
+    float* exp_avg_sq;            /* fp32 [n] */
+    void* wq;                     /* NULL or q(W)   [rows, cols] */
+    void* wq_t;                   /* NULL or q(W)^T [cols, rows] */
+    int64_t n;
+    int rows, cols;               /* rows * cols == n when wq != NULL */
+    int wq_dtype;                 /* MV_F16 or MV_F32 */
+    int q_exp, q_man;             /* weight format; q_exp == 0: identity */
+    float lr, weight_decay;
+    int chunk0;
+} mv_adamw_tensor;
+int mv_adamw_step(const mv_adamw_tensor* tensors_dev, int n_tensors, int total_chunks,
+                  const float* hyper_dev, void* stream);
 
 #ifdef __cplusplus
 }

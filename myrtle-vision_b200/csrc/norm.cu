@@ -425,6 +425,32 @@ static int launch_ln_bwd(const void* dy, int dy_dtype, int64_t ld_dy, const floa
     return check_cuda(cudaGetLastError(), "ln bwd launch");
 }
 
+// fp16 / fp32 [rows, cols] (row pitch ld) -> fp32 copy and / or fp32 transpose [cols, rows], 32x32 tiles
+// through shared memory so both directions are coalesced.  Feeds the kind::tf32 GEMMs of the 32-bit
+// formats (TF32 / FP32): wgrad there takes K-major operands, i.e. dY^T and X^T.
+template <typename InT>
+__global__ void widen_transpose_kernel(const InT* __restrict__ in, int64_t ld, int rows, int cols,
+                                       float* __restrict__ out, float* __restrict__ out_t, int64_t ld_t,
+                                       float mul) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (r < rows && c < cols) {
+            v = float(in[int64_t(r) * ld + c]) * mul;
+            if (out != nullptr) out[int64_t(r) * cols + c] = v;
+        }
+        tile[j][threadIdx.x] = v;
+    }
+    if (out_t == nullptr) return;
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out_t[int64_t(c) * ld_t + r] = tile[threadIdx.x][j];
+    }
+}
+
 }  // namespace mv
 
 using namespace mv;
@@ -525,4 +551,17 @@ extern "C" int mv_convert_f32(const float* in, void* out, int out_dtype, int64_t
     else MV_CHECK(false, "mv_convert_f32: bad dtype");
     g_launches++;
     return check_cuda(cudaGetLastError(), "convert launch");
+}
+
+extern "C" int mv_widen_transpose(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out,
+                                  float* out_t, int64_t ld_t, float mul, void* stream) {
+    MV_CHECK(in && rows > 0 && cols > 0 && (out || out_t) && (!out_t || ld_t >= rows), "mv_widen_transpose: bad arguments");
+    MV_CHECK((rows + 31) / 32 <= 65535, "mv_widen_transpose: too many rows");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (in_dtype == MV_F16) widen_transpose_kernel<__half><<<grid, block, 0, st>>>((const __half*)in, ld, rows, cols, out, out_t, ld_t, mul);
+    else if (in_dtype == MV_F32) widen_transpose_kernel<float><<<grid, block, 0, st>>>((const float*)in, ld, rows, cols, out, out_t, ld_t, mul);
+    else MV_CHECK(false, "mv_widen_transpose: bad dtype");
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "widen transpose launch");
 }

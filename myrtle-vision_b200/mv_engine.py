@@ -44,10 +44,12 @@ class EncoderEngine:
         self.params = list(params)
         assert len(self.params) == 2 + PER_LAYER * cfg.depth
         plan = cfg.plan
-        if plan.inp != (5, 10):
-            raise NotImplementedError(
-                "the fused tcgen05 path currently covers the fp16-operand formats (FP16_32, "
-                "FP16_16); q_format with input format %r is not wired yet" % (plan.inp,))
+        if plan.inp not in ((5, 10), (8, 10), None):
+            raise NotImplementedError("no tensor-core operand container for input format %r" % (plan.inp,))
+        # 32-bit formats (TF32: inputs/weights on the (8,10) grid; FP32: no quantisers) run their
+        # contractions as kind::tf32 on fp32 containers — what the reference's torch 1.11 does with its
+        # default allow_tf32 matmuls; (8,10) values are exact tf32 operands.
+        self.wide = plan.inp != (5, 10)
         if cfg.dim != cfg.heads * 64:
             raise ValueError("dim must equal heads * 64 (dim_head is fixed at 64, models/vit.py:178)")
         self.fmt = plan.inp
@@ -62,6 +64,9 @@ class EncoderEngine:
         self.gviews = [self.gflat[self.offsets[i]:self.offsets[i] + sizes[i]].view_as(p)
                        for i, p in enumerate(self.params)]
         self.reducer = None      # set by parallel.DataParallel: called with flat gradient slices
+        # True once an optimizer (utils/fused_adamw.FusedAdamW) emits q(W) / q(W)^T itself after every
+        # update: a CUDA-graph capture then leaves the re-quantisation out of the graph
+        self.external_requant = False
 
     # ------------------------------------------------------------------ weights
     def _weight_indices(self):
@@ -78,7 +83,8 @@ class EncoderEngine:
         versions = tuple(self.params[i]._version for i in idx) + tuple(
             self.params[i].data_ptr() for i in idx)
         capturing = torch.cuda.is_current_stream_capturing()
-        if self._wq is not None and versions == self._wq_versions and not capturing:
+        if self._wq is not None and versions == self._wq_versions and (
+                not capturing or self.external_requant):
             return self._wq
         if capturing and getattr(self, "_wq_capture_done", None) == id(torch.cuda.current_stream()):
             return self._wq          # already re-quantised once inside this capture (forward)
@@ -86,8 +92,10 @@ class EncoderEngine:
         for i in idx:
             w = self.params[i].detach()
             old = self._wq.get(i) if self._wq else None
-            q, qt = mv.quantize_weight(w, self.fmt[0], self.fmt[1], out=old[0] if old else None,
-                                       out_t=old[1] if old else None)
+            e, m = self.fmt if self.fmt else (0, 0)
+            q, qt = mv.quantize_weight(w, e, m, out=old[0] if old else None,
+                                       out_t=old[1] if old else None,
+                                       out_dtype=torch.float32 if self.wide else torch.float16)
             wq[i] = (q, qt)
         self._wq, self._wq_versions = wq, versions
         # inside a CUDA-graph capture the re-quantisation must be part of the graph (weights change
@@ -95,8 +103,16 @@ class EncoderEngine:
         self._wq_capture_done = id(torch.cuda.current_stream()) if capturing else None
         return wq
 
+    def mark_weights_fresh(self):
+        """The operand buffers were just rewritten from the current parameter values (fused optimizer)."""
+        idx = self._weight_indices()
+        self._wq_versions = tuple(self.params[i]._version for i in idx) + tuple(
+            self.params[i].data_ptr() for i in idx)
+
     # ------------------------------------------------------------------ forward
     def forward(self, img, pos_full, cls_token, save):
+        if self.wide:
+            return self._forward_wide(img, pos_full, cls_token, save)
         cfg, plan, fmt = self.cfg, self.cfg.plan, self.fmt
         B, C, Hh, Ww = img.shape
         P = cfg.patch
@@ -139,6 +155,8 @@ class EncoderEngine:
 
     # ----------------------------------------------------------------- backward
     def backward(self, saved, gx):
+        if self.wide:
+            return self._backward_wide(saved, gx)
         cfg, fmt = self.cfg, self.fmt
         B, N = saved["B"], saved["N"]
         M, D, Mm, H = B * N, cfg.dim, cfg.mlp_dim, cfg.heads
@@ -190,6 +208,10 @@ class EncoderEngine:
                 self.reducer.reduce_slice(self.gflat[lo:hi], 1.0 / S)
         # ---- patch embedding: dW = dx^T patches (cls rows of `patches` are zero)
         mv.gemm(dx_h, saved["patches"], g[0], a_major=1, b_major=1, accumulate=True)
+        return self._finish_backward(dx, S, B, N, D)
+
+    def _finish_backward(self, dx, S, B, N, D):
+        g, dev = self.gviews, dx.device
         dpos = torch.zeros(N * D, dtype=torch.float32, device=dev)
         mv.colsum(dx.view(B, N * D), dpos)
         dpos = dpos.view(1, N, D)
@@ -207,6 +229,115 @@ class EncoderEngine:
         grads = [out[self.offsets[i]:self.offsets[i] + p.numel()].view_as(p)
                  for i, p in enumerate(self.params)]
         return dpos, dcls, grads
+
+
+    # ------------------------------------------------- 32-bit formats (TF32 / FP32)
+    # Same step as above on fp32 containers.  Every Linear is a kind::tf32 GEMM on K-major operands;
+    # wgrad therefore takes explicit transposes (mv_widen_transpose) instead of the in-place MN-major
+    # reads of the 16-bit path.  Attention keeps the fp16 tcgen05 kernels: qkv / attention output /
+    # their gradients carry 11 significant bits, the same as a tf32 operand.
+    def _forward_wide(self, img, pos_full, cls_token, save):
+        cfg, plan, fmt = self.cfg, self.cfg.plan, self.fmt
+        B, C, Hh, Ww = img.shape
+        P = cfg.patch
+        N = (Hh // P) * (Ww // P) + 1
+        M, D, Mm, H = B * N, cfg.dim, cfg.mlp_dim, cfg.heads
+        prm = [p.detach() for p in self.params]
+        wq = self.quantised_weights()
+        f16, f32 = torch.float16, torch.float32
+        dev = img.device
+
+        patches = mv.patchify_q(img, P, q_in=fmt, out_dtype=f32, cls_slot=True)
+        x = torch.empty(M, D, dtype=f32, device=dev)
+        pos32 = pos_full.detach().reshape(N, D).contiguous()
+        mv.gemm(patches, wq[0][0], x, bias=prm[1], q_out=plan.out, residual=pos32, q_res=plan.ff,
+                rows_per_img=N)
+        mv.cls_rows(cls_token.detach().reshape(D).contiguous(), pos32, x, B, N, D, q_ff=plan.ff)
+
+        saved = {"B": B, "N": N, "patches": patches, "layers": []} if save else None
+        for l in range(cfg.depth):
+            b0 = 2 + PER_LAYER * l
+            xn1, mean1, rstd1 = mv.layernorm_q_fwd(x, prm[b0], prm[b0 + 1], q_in=fmt, q_post=fmt,
+                                                   out_dtype=f32)
+            qkv = torch.empty(M, 3 * D, dtype=f16, device=dev)
+            mv.gemm(xn1, wq[b0 + 2][0], qkv, bias=prm[b0 + 3], q_out=plan.out)
+            att16, lse = mv.attention_fwd(qkv, B, H, N, scale=0.125, q_out=fmt)
+            att, _ = mv.widen_transpose(att16, want_copy=True, want_t=False)
+            x1 = torch.empty(M, D, dtype=f32, device=dev)
+            mv.gemm(att, wq[b0 + 4][0], x1, bias=prm[b0 + 5], q_out=plan.out, residual=x, q_res=plan.ff)
+            xn2, mean2, rstd2 = mv.layernorm_q_fwd(x1, prm[b0 + 6], prm[b0 + 7], q_in=fmt, q_post=fmt,
+                                                   out_dtype=f32)
+            gd = torch.empty(M, Mm, dtype=f16, device=dev)                  # gelu'(u)
+            h = torch.empty(M, Mm, dtype=f32, device=dev)
+            mv.gemm(xn2, wq[b0 + 8][0], h, bias=prm[b0 + 9], q_out=plan.out, aux=gd,
+                    epilogue=mv.EPI_GELU, q_res=fmt)
+            x2 = torch.empty(M, D, dtype=f32, device=dev)
+            mv.gemm(h, wq[b0 + 10][0], x2, bias=prm[b0 + 11], q_out=plan.out, residual=x1, q_res=plan.ff)
+            if save:
+                saved["layers"].append((x, xn1, mean1, rstd1, qkv, att16, lse, x1, xn2, mean2, rstd2, gd, h))
+            x = x2
+        return x.view(B, N, D), saved
+
+    def _backward_wide(self, saved, gx):
+        cfg, fmt = self.cfg, self.fmt
+        B, N = saved["B"], saved["N"]
+        M, D, Mm, H = B * N, cfg.dim, cfg.mlp_dim, cfg.heads
+        prm = [p.detach() for p in self.params]
+        wq = self.quantised_weights()
+        g = self.gviews
+        dev = gx.device
+        f16, f32 = torch.float16, torch.float32
+
+        def wgrad(dy, act, out):                       # out[o, i] += sum_m dy[m, o] act[m, i]
+            _, dy_t = mv.widen_transpose(dy)
+            _, act_t = mv.widen_transpose(act)
+            mv.gemm(dy_t, act_t, out, accumulate=True)
+
+        # the fp16 attention backward wants its gradient operand inside fp16's range: same
+        # power-of-two scale as the 16-bit path, removed from the parameter gradients at the end
+        gx = gx.reshape(M, D)
+        amax = gx.abs().amax().clamp_min(1e-30)
+        S = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).clamp(2.0 ** -60, 2.0 ** 60)
+        dx = gx * S
+        self.gflat.zero_()
+        last = cfg.depth - 1
+        mv.colsum(dx, g[2 + PER_LAYER * last + 11].view(-1))
+
+        for l in range(last, -1, -1):
+            b0 = 2 + PER_LAYER * l
+            x, xn1, mean1, rstd1, qkv, att16, lse, x1, xn2, mean2, rstd2, gd, h = saved["layers"][l]
+            # ---- FeedForward
+            du = torch.empty(M, Mm, dtype=f32, device=dev)
+            mv.gemm(dx, wq[b0 + 10][1], du, aux=gd, epilogue=mv.EPI_DGELU)
+            wgrad(dx, h, g[b0 + 10])
+            dxn2 = torch.empty(M, D, dtype=f32, device=dev)
+            mv.gemm(du, wq[b0 + 8][1], dxn2, tag="dgrad")
+            wgrad(du, xn2, g[b0 + 8])
+            mv.colsum(du, g[b0 + 9].view(-1))
+            del du
+            dx1, _ = mv.layernorm_q_bwd(dxn2, x1, prm[b0 + 6], mean2, rstd2, dres=dx, q_in=fmt,
+                                        dgamma=g[b0 + 6], dbeta=g[b0 + 7], dbias_prev=g[b0 + 5],
+                                        want_f16=False)
+            # ---- Attention
+            datt = torch.empty(M, D, dtype=f16, device=dev)
+            mv.gemm(dx1, wq[b0 + 4][1], datt, tag="dgrad")
+            wgrad(dx1, att16, g[b0 + 4])
+            dqkv16 = mv.attention_bwd(qkv, att16, datt, lse, B, H, N, scale=0.125)
+            dqkv, dqkv_t = mv.widen_transpose(dqkv16, want_copy=True)
+            dxn1 = dxn2
+            mv.gemm(dqkv, wq[b0 + 2][1], dxn1, tag="dgrad")
+            _, xn1_t = mv.widen_transpose(xn1)
+            mv.gemm(dqkv_t, xn1_t, g[b0 + 2], accumulate=True)
+            mv.colsum(dqkv16, g[b0 + 3].view(-1))
+            prev_bias = g[b0 - 1] if l > 0 else None
+            dx, _ = mv.layernorm_q_bwd(dxn1, x, prm[b0], mean1, rstd1, dres=dx1, q_in=fmt,
+                                       dgamma=g[b0], dbeta=g[b0 + 1], dbias_prev=prev_bias,
+                                       want_f16=False, dx=dx)
+            if self.reducer is not None:
+                lo, hi = self.offsets[b0], self.offsets[b0 + PER_LAYER]
+                self.reducer.reduce_slice(self.gflat[lo:hi], 1.0 / S)
+        wgrad(dx, saved["patches"], g[0])
+        return self._finish_backward(dx, S, B, N, D)
 
 
 class EncoderFunction(torch.autograd.Function):

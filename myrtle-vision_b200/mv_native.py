@@ -239,6 +239,8 @@ def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None,
     a.cluster = cluster
     kind = "gemm_wgrad" if accumulate else ("gemm_dgrad" if epilogue == EPI_DGELU or tag == "dgrad"
                                             else "gemm_fwd")
+    if _TIMERS is not None:
+        kind = "%s_%dx%dx%d" % (kind, M, N, K)    # one roofline line per GEMM shape (M x N x K)
     with _timed(kind):
         _check(lib().mv_gemm(ctypes.byref(a), _stream()), "mv_gemm")
     return out
@@ -329,6 +331,23 @@ def convert_f32(x, out_dtype=torch.float16, out=None):
     _check(lib().mv_convert_f32(_ptr(x), _ptr(out), _DT[out.dtype], ctypes.c_int64(x.numel()),
                                 _stream()), "mv_convert_f32")
     return out
+
+
+def widen_transpose(x2d, *, want_copy=False, want_t=True, mul=1.0):
+    """fp16/fp32 [rows, cols] -> (fp32 copy or None, fp32 transpose [cols, rows] or None).  The
+    transpose is a view of a buffer whose row pitch is padded to 16 bytes (TMA global stride rule)."""
+    _need_cuda(x2d)
+    assert x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.dtype in (torch.float16, torch.float32)
+    rows, cols = x2d.shape
+    out = torch.empty(rows, cols, dtype=torch.float32, device=x2d.device) if want_copy else None
+    pitch = (rows + 3) // 4 * 4
+    out_t = (torch.empty(cols, pitch, dtype=torch.float32, device=x2d.device)[:, :rows]
+             if want_t else None)
+    _check(lib().mv_widen_transpose(_ptr(x2d), _DT[x2d.dtype], ctypes.c_int64(x2d.stride(0)), rows, cols,
+                                    _ptr(out), _ptr(out_t), ctypes.c_int64(pitch), ctypes.c_float(mul),
+                                    _stream()),
+           "mv_widen_transpose")
+    return out, out_t
 
 
 # ------------------------------------------------------------------- attention

@@ -58,3 +58,16 @@ def prepare_model_and_load_ckpt(train_config, model, optimizer=None, lr_schedule
         return load_checkpoint(model=model, optimizer=optimizer, lr_scheduler=lr_scheduler,
                                filepath=train_config["checkpoint_path"])
     return 0
+
+
+def get_optimizer_args(train_config):
+    """train_config -> the Namespace the optimizer / scheduler factories read (reference :84-110)."""
+    import argparse
+    cfg = train_config
+    return argparse.Namespace(
+        opt=cfg["optimizer"], opt_eps=cfg["opt_eps"], opt_betas=cfg["opt_betas"], clip_grad=cfg["clip_grad"],
+        momentum=cfg["momentum"], weight_decay=cfg["weight_decay"], sched=cfg["scheduler"], lr=cfg["lr"],
+        lr_noise=cfg.get("lr_noise"), lr_noise_pct=cfg.get("lr_noise_pct"), lr_noise_std=cfg.get("lr_noise_std"),
+        warmup_lr=cfg["warmup_lr"], min_lr=cfg["min_lr"], epochs=cfg["epochs"], decay_epochs=cfg["decay_epochs"],
+        warmup_epochs=cfg["warmup_epochs"], cooldown_epochs=cfg["cooldown_epochs"],
+        patience_epochs=cfg["patience_epochs"], decay_rate=cfg["decay_rate"])

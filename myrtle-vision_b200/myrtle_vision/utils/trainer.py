@@ -1,0 +1,176 @@
+"""The training loop behind the three train.py entry points (reference classification/train.py:55-318,
+segmentation/train.py, detection/train.py — one `train_deit(rank, num_gpus, config)` each, identical
+in shape).  Same config schema, batch-size solving, seeding, checkpoint cadence and printed lines;
+what differs is underneath:
+
+* the model is the fused sm_100a ViT, wrapped in `utils.parallel.DataParallel` (NCCL bucket
+  all-reduce overlapped with backward) instead of DistributedDataParallel;
+* forward + loss + backward run as ONE captured CUDA graph when shapes are static
+  (`train_config["cuda_graph"]`, default on for classification / segmentation);
+* the optimizer is `FusedAdamW` (one launch, emits next step's quantised weight operands);
+* the loss scale is applied inside the encoder backward (power-of-two, chosen on the device), so no
+  GradScaler and no per-iteration host sync: losses are printed every `log_every` iterations;
+* data: `data_config["synthetic"] = {"train_length": n, "val_length": m}` selects the synthetic datasets;
+  a real dataset is plugged in with `data_config["dataset_factory"] = "module:function"` returning
+  `(trainset, valset, collate_fn or None)`.
+"""
+import importlib
+import os
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch.utils.data import DataLoader
+from torch.utils.data.distributed import DistributedSampler
+
+from myrtle_vision.datasets.synthetic import SyntheticVision, detection_collate
+from myrtle_vision.utils.graph import GraphedTrainStep
+from myrtle_vision.utils.models import (get_models, get_optimizer_args, prepare_model_and_load_ckpt,
+                                        save_checkpoint)
+from myrtle_vision.utils.optim import create_optimizer, create_scheduler
+from myrtle_vision.utils.parallel import DataParallel
+from myrtle_vision.utils.utils import (cleanup_distributed, get_batch_sizes, init_distributed,
+                                       parse_config, seed_everything)
+
+
+def build_datasets(task, data_config, vit_config):
+    if "dataset_factory" in data_config:
+        mod, fn = data_config["dataset_factory"].split(":")
+        return getattr(importlib.import_module(mod), fn)(data_config)
+    syn = data_config.get("synthetic")
+    if syn is None:
+        raise NotImplementedError(
+            "dataset loaders are outside the B200 hot path: set data_config['synthetic'] or "
+            "data_config['dataset_factory'] = 'module:function'")
+    size, classes = vit_config["image_size"], data_config["number_of_classes"]
+    seed = syn.get("seed", 1234)
+    train = SyntheticVision(task, syn["train_length"], size, classes, seed)
+    val = SyntheticVision(task, syn.get("val_length", 0), size, classes, seed + 1)
+    return train, val, detection_collate if task == "detection" else None
+
+
+def build_criterion(task, train_config, num_classes, device):
+    """-> loss(outputs, targets) returning a scalar."""
+    if task != "detection":
+        return F.cross_entropy
+    from myrtle_vision.models.detector import SetCriterion
+    from myrtle_vision.models.matcher import HungarianMatcher
+    weights = {k: train_config[k] for k in ("loss_ce", "class_error", "loss_bbox", "loss_giou",
+                                            "cardinality_error") if k in train_config}
+    matcher = HungarianMatcher(cost_class=weights.get("loss_ce", 1), cost_bbox=weights.get("loss_bbox", 5),
+                               cost_giou=weights.get("loss_giou", 2))
+    crit = SetCriterion(num_classes, matcher, weights, train_config.get("eos_coef", 0.1),
+                        ["labels", "boxes", "cardinality"]).to(device)
+
+    def loss(outputs, targets):
+        terms = crit(outputs, targets)
+        return sum(terms[k] * weights[k] for k in terms if k in weights)
+    return loss
+
+
+def to_device(targets, device):
+    if isinstance(targets, list):
+        return [{k: v.to(device, non_blocking=True) for k, v in t.items()} for t in targets]
+    return targets.to(device, non_blocking=True)
+
+
+@torch.no_grad()
+def validation(task, loader, device, criterion, vit):
+    vit.eval()
+    total, metric, n = 0.0, 0.0, max(1, len(loader))
+    for imgs, targets in loader:
+        imgs, targets = imgs.to(device), to_device(targets, device)
+        out = vit(imgs)
+        total += float(criterion(out, targets)) / n
+        if task != "detection":
+            metric += float((out.argmax(dim=1) == targets).float().mean()) / n
+    vit.train()
+    return total, metric
+
+
+def train_deit(rank, num_gpus, config, task=None, max_iterations=None):
+    train_config, dist_config, vit_config = config["train_config"], config["dist_config"], config["vit_config"]
+    task = task or vit_config["decoder"]
+    data_config = config.get("data_config") or parse_config(config["data_config_path"])
+    config["data_config"] = data_config
+    seed_everything(train_config["seed"])
+    batch_size, n_batch_accum = get_batch_sizes(train_config["local_batch_size"], num_gpus,
+                                                train_config["global_batch_size"], verbose=(rank == 0))
+    train_config["local_batch_size"] = batch_size
+    train_config["global_batch_size"] = batch_size * n_batch_accum * max(1, num_gpus)
+    train_config["n_batch_accum"] = n_batch_accum
+    if num_gpus > 1:
+        init_distributed(rank, num_gpus, **dist_config)
+    torch.cuda.set_device(rank)
+    device = torch.device("cuda", rank)
+    out_dir = train_config["output_directory"]
+    if rank == 0:
+        os.makedirs(out_dir, exist_ok=True)
+        print("output directory:", out_dir)
+
+    trainset, valset, collate = build_datasets(task, data_config, vit_config)
+    sampler = DistributedSampler(trainset) if num_gpus > 1 else None
+    train_loader = DataLoader(trainset, num_workers=train_config.get("num_workers", 1), shuffle=sampler is None,
+                              sampler=sampler, batch_size=batch_size, pin_memory=True,
+                              drop_last=train_config["drop_last_batch"], collate_fn=collate)
+    val_loader = DataLoader(valset, num_workers=0, batch_size=batch_size, collate_fn=collate,
+                            drop_last=train_config["drop_last_batch"]) if len(valset) else []
+
+    vit, _ = get_models(config)
+    vit = vit.to(device)
+    net = DataParallel(vit) if num_gpus > 1 else vit
+    optimizer_args = get_optimizer_args(train_config)
+    optimizer = create_optimizer(optimizer_args, vit)
+    lr_scheduler, _ = create_scheduler(optimizer_args, optimizer)
+    criterion = build_criterion(task, train_config, data_config["number_of_classes"], device)
+    iteration = prepare_model_and_load_ckpt(train_config=train_config, model=vit, optimizer=optimizer,
+                                            lr_scheduler=lr_scheduler)
+    use_graph = train_config.get("cuda_graph", task != "detection") and n_batch_accum == 1 \
+        and train_config["drop_last_batch"]
+    iters_per_checkpoint = train_config.get("iters_per_checkpoint", 0)
+    iters_per_val = train_config.get("iters_per_val", 0)
+    log_every = train_config.get("log_every", 1)
+    epoch_offset = max(0, int(batch_size * max(1, num_gpus) * iteration / max(1, len(trainset))))
+    vit.train()
+    if num_gpus > 1:
+        dist.barrier()
+    graphed, n_accum, last_val, history = None, 0, (0.0, 0.0), []
+    for epoch in range(epoch_offset, train_config["epochs"]):
+        if sampler is not None:
+            sampler.set_epoch(epoch)
+        lr_scheduler.step(epoch)
+        for imgs, targets in train_loader:
+            if rank == 0 and n_accum == 0 and iters_per_checkpoint and iteration % iters_per_checkpoint == 0:
+                save_checkpoint(model=vit, optimizer=optimizer, lr_scheduler=lr_scheduler,
+                                iteration=iteration, filepath=f"{out_dir}/vit_{iteration:06}")
+            if rank == 0 and n_accum == 0 and iters_per_val and iteration % iters_per_val == 0 and len(valset):
+                last_val = validation(task, val_loader, device, criterion, vit)
+            imgs, targets = imgs.to(device, non_blocking=True), to_device(targets, device)
+            if use_graph:
+                if graphed is None:
+                    graphed = GraphedTrainStep(net, criterion, imgs, targets)
+                loss = graphed(imgs, targets)
+            else:
+                if n_accum == 0:
+                    vit.zero_grad(set_to_none=True)
+                loss = criterion(net(imgs), targets)
+                loss.backward()
+            if optimizer_args.clip_grad is not None:
+                torch.nn.utils.clip_grad_norm_(vit.parameters(), optimizer_args.clip_grad)
+            n_accum += 1
+            if n_accum == n_batch_accum:
+                n_accum = 0
+                optimizer.step()
+                iteration += 1
+                if rank == 0 and iteration % log_every == 0:
+                    history.append(float(loss.detach()))
+                    print(f"Iteration {iteration}:\tloss={history[-1]:.4f}")
+                if max_iterations is not None and iteration >= max_iterations:
+                    break
+        if rank == 0:
+            print(f"Epoch : {epoch + 1} - val_loss : {last_val[0]:.4f} - val_metric: {last_val[1]:.4f}\n")
+        if max_iterations is not None and iteration >= max_iterations:
+            break
+    if num_gpus > 1:
+        cleanup_distributed()
+    return history

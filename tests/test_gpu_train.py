@@ -1,0 +1,53 @@
+"""The train.py entry points (north star: drop-in classification / segmentation / detection training)
+run end to end on the fused path: synthetic data -> DataLoader -> (graphed) fwd+loss+bwd -> FusedAdamW."""
+import copy
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TRAIN = {"output_directory": "", "checkpoint_path": "", "epochs": 12, "local_batch_size": 4,
+         "global_batch_size": 4, "iters_per_checkpoint": 5, "iters_per_val": 5, "seed": 1234,
+         "drop_last_batch": True, "optimizer": "adamw", "opt_eps": 1e-8, "opt_betas": None, "clip_grad": None,
+         "momentum": 0.9, "weight_decay": 0.05, "scheduler": "cosine", "lr": 2e-3, "warmup_lr": 2e-3,
+         "min_lr": 1e-4, "decay_epochs": 15, "warmup_epochs": 0, "cooldown_epochs": 0, "patience_epochs": 5,
+         "decay_rate": 0.1, "distributed": False, "num_workers": 0,
+         "loss_ce": 1.0, "class_error": 0.0, "loss_bbox": 5.0, "loss_giou": 2.0, "cardinality_error": 0.0,
+         "eos_coef": 0.1}
+VIT = {"patch_size": 16, "embed_dim": 128, "depth": 2, "heads": 2, "mlp_dim": 256, "dropout": 0.0,
+       "emb_dropout": 0.0}
+
+
+def config(task, tmp_path, fmt, size, classes):
+    return {"train_config": dict(TRAIN, output_directory=str(tmp_path / "ckpt")),
+            "dist_config": {"dist_backend": "nccl", "dist_url": "tcp://127.0.0.1:54399"},
+            "vit_config": dict(VIT, decoder=task, image_size=size, q_format=fmt),
+            "data_config": {"number_of_classes": classes,
+                            "synthetic": {"train_length": 4, "val_length": 4, "seed": 7}}}
+
+
+@pytest.mark.parametrize("task,fmt,size,classes", [("classification", "FP16_32", 80, 5),
+                                                   ("classification", "FP16_16", 80, 5),
+                                                   ("segmentation", "FP16_32", 96, 4),
+                                                   ("detection", "FP16_32", 176, 3)])
+def test_entry_point_trains(task, fmt, size, classes, tmp_path):
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("train_%s" % task,
+                                                  os.path.join(root, "myrtle-vision_b200", task, "train.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg = config(task, tmp_path, fmt, size, classes)
+    history = mod.train_deit(0, 1, copy.deepcopy(cfg))
+    assert len(history) == 12 and all(torch.isfinite(torch.tensor(history)))
+    assert history[-1] < 0.8 * history[0], history          # memorises its 4 samples
+    ckpts = sorted(os.listdir(cfg["train_config"]["output_directory"]))
+    assert ckpts[:2] == ["vit_000000", "vit_000005"]
+    # resume from a checkpoint: iteration counter and optimizer state come back
+    cfg2 = copy.deepcopy(cfg)
+    cfg2["train_config"]["checkpoint_path"] = os.path.join(cfg["train_config"]["output_directory"], "vit_000010")
+    from myrtle_vision.utils.trainer import train_deit
+    more = train_deit(0, 1, cfg2, max_iterations=12)
+    assert len(more) == 2 and more[-1] < history[0]

@@ -124,3 +124,37 @@ def test_qtorch_facade_surface():
     import mv_native
     with pytest.raises(mv_native.MvError, match="CUDA tensors"):
         qq.float_quantize(torch.zeros(4), 5, 10, "nearest")
+
+
+def test_optimizer_groups_and_cosine_schedule():
+    """timm-0.5.4-shaped optimizer factory / cosine schedule used by the train.py entry points."""
+    import argparse
+    from myrtle_vision.utils.optim import add_weight_decay, create_optimizer, create_scheduler
+    m = make()
+    groups = add_weight_decay(m, 0.05)
+    assert groups[0]["weight_decay"] == 0.0 and groups[1]["weight_decay"] == 0.05
+    assert all(p.ndim >= 2 for p in groups[1]["params"])              # only matrices / tokens decay
+    names = {id(p): n for n, p in m.named_parameters()}
+    assert all(names[id(p)].endswith(".bias") or p.ndim <= 1 for p in groups[0]["params"])
+    assert sum(len(g["params"]) for g in groups) == len(list(m.parameters()))
+    args = argparse.Namespace(opt="adamw", opt_eps=1e-8, opt_betas=None, clip_grad=None, momentum=0.9,
+                              weight_decay=0.05, sched="cosine", lr=6.25e-5, warmup_lr=1e-6, min_lr=1e-5,
+                              epochs=300, decay_epochs=15, warmup_epochs=5, cooldown_epochs=5,
+                              patience_epochs=5, decay_rate=0.1)
+    opt = create_optimizer(args, m, fused=False)
+    assert isinstance(opt, torch.optim.AdamW) and len(opt.param_groups) == 2
+    sched, epochs = create_scheduler(args, opt)
+    assert epochs == 305
+    assert abs(opt.param_groups[0]["lr"] - 1e-6) < 1e-12              # warm-up start
+    sched.step(3)
+    assert abs(opt.param_groups[1]["lr"] - (1e-6 + 3 * (6.25e-5 - 1e-6) / 5)) < 1e-12
+    sched.step(150)
+    assert abs(opt.param_groups[0]["lr"] - (1e-5 + 0.5 * (6.25e-5 - 1e-5))) < 1e-10
+    sched.step(300)
+    assert opt.param_groups[0]["lr"] == 1e-5
+    state = sched.state_dict()
+    sched.step(10)
+    sched.load_state_dict(state)
+    assert opt.param_groups[0]["lr"] == 1e-5
+    with pytest.raises(NotImplementedError):
+        create_optimizer(argparse.Namespace(opt="lamb", weight_decay=0.0, lr=1e-3, opt_eps=None), m)
