@@ -70,9 +70,6 @@ __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
 // float_quantize(5,10) of four values at once: one range test for the group, then 2 integer
 // instructions per value.  kSatLater: the caller converts with cvt.rn.satfinite.f16, which performs
 // the clip to +-65504 (the rounded value is exactly representable in fp16 otherwise).
-static __device__ __noinline__ float4 fq_half4_rare(float a, float b, float c, float d) {
-    return make_float4(fq_half_fast(a), fq_half_fast(b), fq_half_fast(c), fq_half_fast(d));
-}
 template <bool kSatLater>
 __device__ __forceinline__ void fq_half4(float (&v)[4]) {
     const float mn = fminf(fminf(fabsf(v[0]), fabsf(v[1])), fminf(fabsf(v[2]), fabsf(v[3])));

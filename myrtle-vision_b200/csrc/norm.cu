@@ -62,8 +62,12 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict
         for (int rr = 0; rr < 2; rr++) {
 #pragma unroll
             for (int i = 0; i < NV; i++) {
-                v[rr][i].x = fq_apply(v[rr][i].x, mi, q_in); v[rr][i].y = fq_apply(v[rr][i].y, mi, q_in);
-                v[rr][i].z = fq_apply(v[rr][i].z, mi, q_in); v[rr][i].w = fq_apply(v[rr][i].w, mi, q_in);
+                if (mi == 1) {
+                    v[rr][i] = fq_half4_f32(v[rr][i]);          // one range test per four values
+                } else {
+                    v[rr][i].x = fq_apply(v[rr][i].x, mi, q_in); v[rr][i].y = fq_apply(v[rr][i].y, mi, q_in);
+                    v[rr][i].z = fq_apply(v[rr][i].z, mi, q_in); v[rr][i].w = fq_apply(v[rr][i].w, mi, q_in);
+                }
                 s[rr] += (v[rr][i].x + v[rr][i].y) + (v[rr][i].z + v[rr][i].w);
             }
         }
@@ -105,10 +109,17 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict
                     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
                     const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
                     float4 o;
-                    o.x = fq_apply(fmaf((v[rr][i].x - mean[rr]) * rstd, g.x, b.x), mp, q_post);
-                    o.y = fq_apply(fmaf((v[rr][i].y - mean[rr]) * rstd, g.y, b.y), mp, q_post);
-                    o.z = fq_apply(fmaf((v[rr][i].z - mean[rr]) * rstd, g.z, b.z), mp, q_post);
-                    o.w = fq_apply(fmaf((v[rr][i].w - mean[rr]) * rstd, g.w, b.w), mp, q_post);
+                    o.x = fmaf((v[rr][i].x - mean[rr]) * rstd, g.x, b.x);
+                    o.y = fmaf((v[rr][i].y - mean[rr]) * rstd, g.y, b.y);
+                    o.z = fmaf((v[rr][i].z - mean[rr]) * rstd, g.z, b.z);
+                    o.w = fmaf((v[rr][i].w - mean[rr]) * rstd, g.w, b.w);
+                    if (mp == 1 && sizeof(OutT) == 2) {
+                        // quantise + convert + pack in one step (cvt.rz on the half-ulp-biased word)
+                        __stcs(reinterpret_cast<uint2*>(yr) + c, fq_half4_pack(o.x, o.y, o.z, o.w));
+                        continue;
+                    }
+                    o.x = fq_apply(o.x, mp, q_post); o.y = fq_apply(o.y, mp, q_post);
+                    o.z = fq_apply(o.z, mp, q_post); o.w = fq_apply(o.w, mp, q_post);
                     if (sizeof(OutT) == 4) {
                         __stcs(reinterpret_cast<float4*>(yr) + c, o);
                     } else {
@@ -202,8 +213,14 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
                 const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
                 const float4 d = unpack_dy(cur.dy[i]);
                 float4 xv = cur.x[i];
-                xv.x = (fq_apply(xv.x, mi, q_in) - mean) * rstd; xv.y = (fq_apply(xv.y, mi, q_in) - mean) * rstd;
-                xv.z = (fq_apply(xv.z, mi, q_in) - mean) * rstd; xv.w = (fq_apply(xv.w, mi, q_in) - mean) * rstd;
+                if (mi == 1) {
+                    xv = fq_half4_f32(xv);
+                } else {
+                    xv.x = fq_apply(xv.x, mi, q_in); xv.y = fq_apply(xv.y, mi, q_in);
+                    xv.z = fq_apply(xv.z, mi, q_in); xv.w = fq_apply(xv.w, mi, q_in);
+                }
+                xv.x = (xv.x - mean) * rstd; xv.y = (xv.y - mean) * rstd;
+                xv.z = (xv.z - mean) * rstd; xv.w = (xv.w - mean) * rstd;
                 xh[i] = xv;
                 float4 a = acc[c];
                 a.x = fmaf(d.x, xv.x, a.x); a.y = fmaf(d.y, xv.y, a.y); a.z = fmaf(d.z, xv.z, a.z); a.w = fmaf(d.w, xv.w, a.w);
@@ -329,27 +346,52 @@ template <typename OutT>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, OutT* __restrict__ out, int B, int C, int H, int W,
                 int P, FloatFmt q_in, int cls_slot) {
-    // one CTA per (b, patch row gy): reads C x P rows of W contiguous floats, coalesced
+    // One CTA per (b, patch row gy).  Phase 1 reads the C x P image rows (W contiguous floats each,
+    // 16-byte loads), quantises and parks them in shared memory as [c][ph][w]; phase 2 walks the
+    // gw * pdim output elements of this patch row — one contiguous span of `out` — so the (ph, pw, c)
+    // interleave happens in shared memory and every global store is a full, consecutive sector.
+    extern __shared__ uint8_t patch_smem[];
+    OutT* sm = reinterpret_cast<OutT*>(patch_smem);
     const int gw = W / P, gh = H / P;
     const int b = blockIdx.x / gh, gy = blockIdx.x % gh;
     const int pdim = P * P * C;
-    const int total = C * P * W;
     const int64_t rows_per_img = int64_t(gh) * gw + cls_slot;
+    OutT* obase = out + (int64_t(b) * rows_per_img + cls_slot + int64_t(gy) * gw) * pdim;
     if (cls_slot && gy == 0) {          // row b*N + 0 is the (zero) slot of the class token
-        for (int i = threadIdx.x; i < pdim; i += blockDim.x) {
-            if (sizeof(OutT) == 4) reinterpret_cast<float*>(out)[int64_t(b) * rows_per_img * pdim + i] = 0.f;
-            else reinterpret_cast<__half*>(out)[int64_t(b) * rows_per_img * pdim + i] = __float2half_rn(0.f);
-        }
+        OutT* z = out + int64_t(b) * rows_per_img * pdim;
+        for (int i = threadIdx.x; i < pdim; i += blockDim.x) z[i] = OutT(0.f);
     }
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int w = i % W;
-        const int ph = (i / W) % P;
-        const int c = i / (W * P);
-        const float v = fq_nearest(__ldcs(img + ((int64_t(b) * C + c) * H + gy * P + ph) * W + w), q_in);
-        const int gx = w / P, pw = w % P;
-        const int64_t o = (int64_t(b) * rows_per_img + cls_slot + gy * gw + gx) * pdim + (ph * P + pw) * C + c;
-        if (sizeof(OutT) == 4) reinterpret_cast<float*>(out)[o] = v;
-        else reinterpret_cast<__half*>(out)[o] = __float2half_rn(v);
+    const int mode = fq_mode(q_in);
+    const int w4 = W >> 2;              // W % 4 == 0 checked on the host
+    for (int i = threadIdx.x; i < C * P * w4; i += blockDim.x) {
+        const int wv = i % w4, r = i / w4;                 // r = c * P + ph
+        const int c = r / P, ph = r % P;
+        float4 v = __ldcs(reinterpret_cast<const float4*>(img + ((int64_t(b) * C + c) * H + gy * P + ph) * W) + wv);
+        if (mode == 1) v = fq_half4_f32(v);
+        else { v.x = fq_apply(v.x, mode, q_in); v.y = fq_apply(v.y, mode, q_in); v.z = fq_apply(v.z, mode, q_in); v.w = fq_apply(v.w, mode, q_in); }
+        OutT* d = sm + r * W + wv * 4;
+        d[0] = OutT(v.x); d[1] = OutT(v.y); d[2] = OutT(v.z); d[3] = OutT(v.w);
+    }
+    __syncthreads();
+    const int total = gw * pdim;
+    const int PC = P * C;
+    if (sizeof(OutT) == 2 && (pdim & 1) == 0) {
+        for (int o = threadIdx.x * 2; o < total; o += blockDim.x * 2) {
+            OutT pair[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int gx = (o + e) / pdim, r = (o + e) % pdim;
+                const int ph = r / PC, pw = (r % PC) / C, c = r % C;
+                pair[e] = sm[(c * P + ph) * W + gx * P + pw];
+            }
+            *reinterpret_cast<uint32_t*>(obase + o) = *reinterpret_cast<const uint32_t*>(pair);
+        }
+    } else {
+        for (int o = threadIdx.x; o < total; o += blockDim.x) {
+            const int gx = o / pdim, r = o % pdim;
+            const int ph = r / PC, pw = (r % PC) / C, c = r % C;
+            obase[o] = sm[(c * P + ph) * W + gx * P + pw];
+        }
     }
 }
 
@@ -522,10 +564,17 @@ extern "C" int mv_patchify_q(const float* img, void* out, int out_dtype, int B, 
     MV_CHECK(B > 0 && C > 0 && P > 0 && H % P == 0 && W % P == 0, "mv_patchify_q: image dims must be divisible by the patch size");
     const FloatFmt q{q_exp, q_man};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MV_CHECK(W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0, "mv_patchify_q: image rows must be 16-byte aligned (W % 4 == 0)");
     const int grid = B * (H / P);
-    if (out_dtype == MV_F16) patchify_kernel<__half><<<grid, 256, 0, st>>>(img, (__half*)out, B, C, H, W, P, q, cls_slot ? 1 : 0);
-    else if (out_dtype == MV_F32) patchify_kernel<float><<<grid, 256, 0, st>>>(img, (float*)out, B, C, H, W, P, q, cls_slot ? 1 : 0);
-    else MV_CHECK(false, "mv_patchify_q: bad container");
+    const size_t smem = size_t(C) * P * W * (out_dtype == MV_F16 ? 2 : 4);
+    MV_CHECK(smem <= 200 * 1024, "mv_patchify_q: C * P * W too large for the shared-memory staging buffer");
+    if (out_dtype == MV_F16) {
+        MV_CUDA(cudaFuncSetAttribute(patchify_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        patchify_kernel<__half><<<grid, 256, smem, st>>>(img, (__half*)out, B, C, H, W, P, q, cls_slot ? 1 : 0);
+    } else if (out_dtype == MV_F32) {
+        MV_CUDA(cudaFuncSetAttribute(patchify_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        patchify_kernel<float><<<grid, 256, smem, st>>>(img, (float*)out, B, C, H, W, P, q, cls_slot ? 1 : 0);
+    } else MV_CHECK(false, "mv_patchify_q: bad container");
     g_launches++;
     return check_cuda(cudaGetLastError(), "patchify launch");
 }

@@ -86,6 +86,48 @@ __device__ __forceinline__ float fq_apply(float a, int mode, FloatFmt f) {
     return a;
 }
 
+// ---- (5,10) on four values at once: one range test for the group instead of one per value ----
+// Out of line on purpose: inline, ptxas if-converts the rare branch into ~50 predicated instructions.
+static __device__ __noinline__ float4 fq_half4_rare(float a, float b, float c, float d) {
+    return make_float4(fq_half_fast(a), fq_half_fast(b), fq_half_fast(c), fq_half_fast(d));
+}
+__device__ __forceinline__ bool fq_half4_all_normal(float a, float b, float c, float d) {
+    // all four at or above fp16's lowest normal binade (2^-14); zeros take the rare path
+    return fminf(fminf(fabsf(a), fabsf(b)), fminf(fabsf(c), fabsf(d))) >= 6.103515625e-05f;
+}
+// fp32 results (the value feeds more fp32 math)
+__device__ __forceinline__ float4 fq_half4_f32(float4 v) {
+    if (fq_half4_all_normal(v.x, v.y, v.z, v.w)) {
+        uint32_t q[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t t = q[j];
+            q[j] = (t + 0x1000u) & 0xFFFFE000u;
+            if ((q[j] & 0x7FFFFFFFu) > 0x477FE000u) q[j] = (t & 0x80000000u) | 0x477FE000u;
+        }
+        return make_float4(__uint_as_float(q[0]), __uint_as_float(q[1]), __uint_as_float(q[2]), __uint_as_float(q[3]));
+    }
+    return fq_half4_rare(v.x, v.y, v.z, v.w);
+}
+// packed fp16 results (the value is stored as a tensor-core operand).  In the normal range
+// float_quantize(5,10) nearest is "add half an fp16 ulp to the fp32 word, drop the low 13 bits, clip to
+// +-65504": adding 0x1000 and converting with round-toward-zero does exactly that — RZ truncates the low
+// bits and never rounds a finite value to infinity (satfinite also clips an infinite input) — at 1.5
+// instructions per value.
+__device__ __forceinline__ uint32_t cvt_rz_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rz.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint2 fq_half4_pack(float a, float b, float c, float d) {
+    if (!fq_half4_all_normal(a, b, c, d)) {
+        const float4 r = fq_half4_rare(a, b, c, d);           // exactly representable: any rounding mode
+        return make_uint2(cvt_rz_f16x2(r.x, r.y), cvt_rz_f16x2(r.z, r.w));
+    }
+    return make_uint2(cvt_rz_f16x2(__uint_as_float(__float_as_uint(a) + 0x1000u), __uint_as_float(__float_as_uint(b) + 0x1000u)),
+                      cvt_rz_f16x2(__uint_as_float(__float_as_uint(c) + 0x1000u), __uint_as_float(__float_as_uint(d) + 0x1000u)));
+}
+
 // fixed_point_quantize for one element: floor(a * 2^fl + r) * 2^-fl, then clamp.
 // Nearest passes r = 0.5 (QPyTorch's CUDA kernel: ties toward +inf).
 __device__ __forceinline__ float fixed_quantize_elem(float a, float r, float scale_up,
