@@ -188,6 +188,16 @@ typedef struct {
 int mv_adamw_step(const mv_adamw_tensor* tensors_dev, int n_tensors, int total_chunks,
                   const float* hyper_dev, void* stream);
 
+/* ---------------------------------------------------------------- segmentation loss
+ * Fused nn.Upsample(size=(H, W), mode='bilinear', align_corners=False) + CrossEntropyLoss (reduction
+ * 'mean', ignore_index) of the reference's segmentation head and train step (models/vit.py:355-371,
+ * segmentation/train.py:188, 261), forward and backward in one pass; the [B, C, H, W] logits are never
+ * materialised.  y, dy: fp32 [B, gh*gw, C] (patch-major, the decoder Linear's own output layout);
+ * labels: int64 [B, H, W]; acc: fp32 [2], acc[0] += sum of pixel losses, acc[1] += non-ignored pixels;
+ * dy += d(sum of pixel losses)/dy.  The caller zeroes dy / acc and divides by acc[1]. */
+int mv_upsample_ce(const float* y, const int64_t* labels, float* dy, float* acc, int B, int C, int gh, int gw,
+                   int H, int W, int64_t ignore_index, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

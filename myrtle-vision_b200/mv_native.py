@@ -350,6 +350,25 @@ def widen_transpose(x2d, *, want_copy=False, want_t=True, mul=1.0):
     return out, out_t
 
 
+def upsample_ce(y, labels, ignore_index=-100):
+    """Fused bilinear upsample + cross entropy (mv_upsample_ce).  y fp32 [B, gh*gw, C] patch logits,
+    labels int64 [B, H, W] -> (acc fp32 [2] = (sum of pixel losses, valid pixels), dy = d sum / dy)."""
+    _need_cuda(y, labels)
+    assert y.dtype == torch.float32 and labels.dtype == torch.int64 and y.dim() == 3 and labels.dim() == 3
+    y, labels = y.contiguous(), labels.contiguous()
+    B, hw, C = y.shape
+    H, W = labels.shape[1:]
+    gh = int(round((hw * H / W) ** 0.5))
+    gw = hw // max(gh, 1)
+    if gh * gw != hw or labels.shape[0] != B:
+        raise MvError("upsample_ce: %d patches do not form a grid matching labels %s" % (hw, tuple(labels.shape)))
+    dy = torch.zeros_like(y)
+    acc = torch.zeros(2, dtype=torch.float32, device=y.device)
+    _check(lib().mv_upsample_ce(_ptr(y), _ptr(labels), _ptr(dy), _ptr(acc), B, C, gh, gw, H, W,
+                                ctypes.c_int64(ignore_index), _stream()), "mv_upsample_ce")
+    return acc, dy
+
+
 # ------------------------------------------------------------------- attention
 def attention_fwd(qkv, B, H, N, *, scale=0.125, q_out=None, out_dtype=torch.float16, out=None,
                   lse=None):

@@ -237,6 +237,8 @@ class ViT(nn.Module):
             return self._linear(dec.linear, self._norm(dec.norm, x[:, 0]))
         if self.task == "segmentation":                                 # vit.py:359-374
             y = self._linear(dec.linear, self._norm(dec.norm, x[:, 1:]))
+            if self.training and getattr(dec, "fused_loss", False):
+                return y                 # [B, gh*gw, C] for models.losses.upsampled_cross_entropy
             b, hw, c = y.size()
             y = y.transpose(1, 2).reshape(b, c, dec.image_size_in_patches, dec.image_size_in_patches)
             return dec.upsample(y)

@@ -51,6 +51,13 @@ def build_datasets(task, data_config, vit_config):
 
 def build_criterion(task, train_config, num_classes, device):
     """-> loss(outputs, targets) returning a scalar."""
+    if task == "segmentation" and train_config.get("fused_seg_loss", True):
+        from myrtle_vision.models.losses import upsampled_cross_entropy
+
+        def seg_loss(outputs, targets):
+            # training: patch logits [B, gh*gw, C] (decoder.fused_loss); validation: the upsampled map
+            return upsampled_cross_entropy(outputs, targets) if outputs.dim() == 3 else F.cross_entropy(outputs, targets)
+        return seg_loss
     if task != "detection":
         return F.cross_entropy
     from myrtle_vision.models.detector import SetCriterion
@@ -118,6 +125,8 @@ def train_deit(rank, num_gpus, config, task=None, max_iterations=None):
 
     vit, _ = get_models(config)
     vit = vit.to(device)
+    if task == "segmentation" and train_config.get("fused_seg_loss", True):
+        vit.decoder.fused_loss = True        # training forward returns patch logits for the fused loss
     net = DataParallel(vit) if num_gpus > 1 else vit
     optimizer_args = get_optimizer_args(train_config)
     optimizer = create_optimizer(optimizer_args, vit)
@@ -127,6 +136,8 @@ def train_deit(rank, num_gpus, config, task=None, max_iterations=None):
                                             lr_scheduler=lr_scheduler)
     use_graph = train_config.get("cuda_graph", task != "detection") and n_batch_accum == 1 \
         and train_config["drop_last_batch"]
+    split_graph = (task == "detection" and train_config.get("cuda_graph", True) and n_batch_accum == 1
+                   and train_config["drop_last_batch"] and num_gpus <= 1)
     iters_per_checkpoint = train_config.get("iters_per_checkpoint", 0)
     iters_per_val = train_config.get("iters_per_val", 0)
     log_every = train_config.get("log_every", 1)
@@ -150,6 +161,14 @@ def train_deit(rank, num_gpus, config, task=None, max_iterations=None):
                 if graphed is None:
                     graphed = GraphedTrainStep(net, criterion, imgs, targets)
                 loss = graphed(imgs, targets)
+            elif split_graph:
+                # detection: the matcher runs on the host between forward and backward, so the model's
+                # forward and backward are two captured graphs around the eager criterion
+                if graphed is None:
+                    graphed = torch.cuda.make_graphed_callables(vit, (imgs,), allow_unused_input=True)
+                vit.zero_grad(set_to_none=True)
+                loss = criterion(graphed(imgs), targets)
+                loss.backward()
             else:
                 if n_accum == 0:
                     vit.zero_grad(set_to_none=True)

@@ -152,3 +152,27 @@ def test_patchify_and_colsum():
     a = torch.randn(8000, 1152, device=dev).half(); o = torch.zeros(1152, device=dev)
     mv.colsum(a, o)
     assert relmax(o, a.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,g,S", [(2, 17, 16, 256), (3, 4, 5, 80), (1, 24, 3, 48), (2, 32, 2, 32), (2, 7, 14, 224)])
+def test_fused_upsample_cross_entropy(B, C, g, S):
+    """mv_upsample_ce against nn.Upsample(bilinear) + CrossEntropyLoss in fp64, incl. ignore_index."""
+    from myrtle_vision.models.losses import upsampled_cross_entropy
+    torch.manual_seed(C)
+    y = (torch.randn(B, g * g, C, device=dev) * 3).requires_grad_(True)
+    labels = torch.randint(0, C, (B, S, S), device=dev)
+    labels[0, : S // 3, S // 2:] = -100
+    loss = upsampled_cross_entropy(y, labels)
+    (loss * 1.7).backward()
+    yr = y.detach().double().requires_grad_(True)
+    up = torch.nn.Upsample(size=S, mode="bilinear")(yr.transpose(1, 2).reshape(B, C, g, g))
+    ref = F.cross_entropy(up, labels)
+    (ref * 1.7).backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert relmax(y.grad, yr.grad) < 1e-4
+    # all pixels ignored: zero loss, zero gradient, no NaN
+    labels[:] = -100
+    y.grad = None
+    l0 = upsampled_cross_entropy(y, labels)
+    l0.backward()
+    assert l0.item() == 0.0 and float(y.grad.abs().max()) == 0.0

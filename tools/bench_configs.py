@@ -1,0 +1,97 @@
+"""Throughput of BASELINE.json configs 4 and 5 (segmentation 256^2 / 17 classes, detection 800^2 / 20
+classes, N = 2501 tokens) on one B200: images/s of zero_grad -> forward -> loss -> backward, with the
+CUDA-event kernel breakdown.  usage: python tools/bench_configs.py [segmentation|detection] [--batch B]
+[--q-format F] [--arch small|tiny]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "myrtle-vision_b200")]
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+import mv_native  # noqa: E402
+from myrtle_vision.datasets.synthetic import SyntheticVision, detection_collate  # noqa: E402
+from myrtle_vision.models.vit import ViT  # noqa: E402
+from myrtle_vision.utils.graph import GraphedTrainStep  # noqa: E402
+from myrtle_vision.utils.trainer import build_criterion, to_device  # noqa: E402
+
+ARCHS = {"small": dict(dim=384, depth=12, heads=6, mlp_dim=1536), "tiny": dict(dim=192, depth=12, heads=3, mlp_dim=768)}
+ap = argparse.ArgumentParser()
+ap.add_argument("task", choices=["segmentation", "detection"])
+ap.add_argument("--batch", type=int, default=None)
+ap.add_argument("--q-format", default="FP16_32")
+ap.add_argument("--arch", default="small")
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--unfused-seg-loss", action="store_true", help="segmentation: upsample + CrossEntropyLoss in PyTorch")
+ap.add_argument("--no-graph", action="store_true")
+args = ap.parse_args()
+size, classes, batch = (256, 17, 256) if args.task == "segmentation" else (800, 20, 8)
+batch = args.batch or batch
+dev = torch.device("cuda")
+torch.manual_seed(1234)
+model = ViT(decoder=args.task, image_size=size, patch_size=16, num_classes=classes, q_format=args.q_format,
+            **ARCHS[args.arch]).to(dev).train()
+ds = SyntheticVision(args.task, 2 * batch, size, classes, seed=1234)
+items = [ds[i] for i in range(2 * batch)]
+if args.task == "detection":
+    batches = [detection_collate(items[:batch]), detection_collate(items[batch:])]
+else:
+    batches = [(torch.stack([a for a, _ in part]), torch.stack([b for _, b in part])) for part in (items[:batch], items[batch:])]
+batches = [(img.to(dev), to_device(t, dev)) for img, t in batches]
+train_cfg = {"loss_ce": 1.0, "class_error": 0.0, "loss_bbox": 5.0, "loss_giou": 2.0, "cardinality_error": 0.0, "eos_coef": 0.1}
+train_cfg["fused_seg_loss"] = not args.unfused_seg_loss
+criterion = build_criterion(args.task, train_cfg, classes, dev)
+if args.task == "segmentation" and not args.unfused_seg_loss:
+    model.decoder.fused_loss = True
+
+
+def eager(img, tgt):
+    model.zero_grad(set_to_none=True)
+    loss = criterion(model(img), tgt)
+    loss.backward()
+    return loss
+
+
+for i in range(3):
+    eager(*batches[i % 2])
+torch.cuda.synchronize()
+mv_native.enable_timing(True)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(args.steps):
+    eager(*batches[i % 2])
+e1.record(); torch.cuda.synchronize()
+ms_eager = e0.elapsed_time(e1) / args.steps
+kern = {k: round(v[1] / args.steps, 3) for k, v in sorted(mv_native.timing_summary().items(), key=lambda kv: -kv[1][1])}
+mv_native.enable_timing(False)
+ms = ms_eager
+graph = not args.no_graph
+if graph and args.task == "segmentation":
+    gs = GraphedTrainStep(model, criterion, *batches[0])
+    run = lambda img, tgt: gs(img, tgt)
+elif graph:
+    # detection: the Hungarian matcher runs on the host between forward and backward, so the model's
+    # forward and backward are captured as two separate graphs around it
+    gm = torch.cuda.make_graphed_callables(model, (batches[0][0],), allow_unused_input=True)
+
+    def run(img, tgt):
+        model.zero_grad(set_to_none=True)
+        loss = criterion(gm(img), tgt)
+        loss.backward()
+        return loss
+if graph:
+    for i in range(3):
+        run(*batches[i % 2])
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        run(*batches[i % 2])
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+n_tok = (size // 16) ** 2 + 1
+print(json.dumps({"task": args.task, "arch": args.arch, "q_format": args.q_format, "batch": batch, "tokens": n_tok,
+                  "images_per_s": batch / ms * 1e3, "ms_per_step": ms, "eager_ms_per_step": ms_eager,
+                  "cuda_graph": graph, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                  "top_kernels_ms_per_step": dict(list(kern.items())[:8])}))
