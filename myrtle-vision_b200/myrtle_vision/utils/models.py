@@ -71,3 +71,64 @@ def get_optimizer_args(train_config):
         warmup_lr=cfg["warmup_lr"], min_lr=cfg["min_lr"], epochs=cfg["epochs"], decay_epochs=cfg["decay_epochs"],
         warmup_epochs=cfg["warmup_epochs"], cooldown_epochs=cfg["cooldown_epochs"],
         patience_epochs=cfg["patience_epochs"], decay_rate=cfg["decay_rate"])
+
+
+# ---- pretrained-backbone key mapping (reference utils/models.py:144-223)
+_TIMM_RULES = [
+    (r"pos_embed", r"pos_embedding"),
+    (r"patch_embed\.proj\.(weight|bias)", r"patch_to_embedding.\1"),
+    (r"blocks\.([0-9]+)\.norm1\.(weight|bias)", r"transformer.layers.\1.0.fn.norm.\2"),
+    (r"blocks\.([0-9]+)\.attn\.qkv\.(weight|bias)", r"transformer.layers.\1.0.fn.fn.to_qkv.\2"),
+    (r"blocks\.([0-9]+)\.attn\.proj\.(weight|bias)", r"transformer.layers.\1.0.fn.fn.to_out.0.\2"),
+    (r"blocks\.([0-9]+)\.norm2\.(weight|bias)", r"transformer.layers.\1.1.fn.norm.\2"),
+    (r"blocks\.([0-9]+)\.mlp\.fc1\.(weight|bias)", r"transformer.layers.\1.1.fn.fn.net.0.\2"),
+    (r"blocks\.([0-9]+)\.mlp\.fc2\.(weight|bias)", r"transformer.layers.\1.1.fn.fn.net.3.\2"),
+]
+_TIMM_HEAD = (r"norm\.weight", r"norm\.bias", r"head\.weight", r"head\.bias")
+
+
+def apply_rules(name, rules):
+    """Apply the first matching rule (regex substitution) to name."""
+    import re
+    for pattern, replacement in rules:
+        if re.match(pattern, name) is not None:
+            return re.sub(pattern, replacement, name)
+    return name
+
+
+def rename_timm_state_dict(timm_model_name, vit_config, num_classes, q_format=None):
+    """State dict of a pretrained timm ViT under this package's parameter names.
+
+    `timm_model_name`: a timm model name (needs timm, as in the reference) or an already loaded
+    timm-style state dict.  The classifier head (`norm.*`, `head.*`) is dropped; the Conv2d patch
+    embedding `(O, I, H, W)` becomes the Linear weight `(O, (H, W, I))`.  `q_format` (default: the
+    config's) selects the key layout: quantised models wrap every Linear / LayerNorm in
+    `Sequential(stub, module)`, so their parameters live under `<name>.1.<param>` — the
+    reference maps to the unwrapped names only, which silently loads nothing into a quantised
+    model."""
+    import re
+    if isinstance(timm_model_name, str):
+        try:
+            import timm
+        except ImportError as e:
+            raise ImportError("rename_timm_state_dict(<model name>) needs timm; pass a timm-style "
+                              "state dict instead") from e
+        source = timm.create_model(timm_model_name, pretrained=True, num_classes=num_classes).state_dict()
+    else:
+        source = timm_model_name
+    fmt = q_format if q_format is not None else vit_config.get("q_format", "FP32")
+    fmt = QFormat[fmt] if isinstance(fmt, str) else fmt
+    wrapped = fmt != QFormat.FP32
+    out = {}
+    for key, value in source.items():
+        if any(re.match(pat, key) for pat in _TIMM_HEAD):
+            continue
+        new_key = apply_rules(key, _TIMM_RULES)
+        if new_key.startswith("patch_to_embedding.weight") and value.dim() == 4:
+            value = value.permute(0, 2, 3, 1).reshape(vit_config["embed_dim"],
+                                                      vit_config["patch_size"] ** 2 * value.shape[1])
+        if wrapped and new_key != key and not new_key.startswith("pos_embedding"):
+            stem, param = new_key.rsplit(".", 1)
+            new_key = f"{stem}.1.{param}"
+        out[new_key] = value
+    return out

@@ -158,3 +158,32 @@ def test_optimizer_groups_and_cosine_schedule():
     assert opt.param_groups[0]["lr"] == 1e-5
     with pytest.raises(NotImplementedError):
         create_optimizer(argparse.Namespace(opt="lamb", weight_decay=0.0, lr=1e-3, opt_eps=None), m)
+
+
+@pytest.mark.parametrize("fmt", ["FP32", "FP16_32", "FP16_16"])
+def test_rename_timm_state_dict_loads_into_every_key_layout(fmt):
+    """pretrained-backbone key mapping incl. the quantised `<name>.1.<param>` layout."""
+    from myrtle_vision.utils.models import rename_timm_state_dict
+    D, depth, M, P = 128, 2, 256, 16
+    g = torch.Generator().manual_seed(0)
+    timm_sd = {"cls_token": torch.randn(1, 1, D, generator=g), "pos_embed": torch.randn(1, 197, D, generator=g),
+               "patch_embed.proj.weight": torch.randn(D, 3, P, P, generator=g), "patch_embed.proj.bias": torch.randn(D, generator=g),
+               "norm.weight": torch.ones(D), "norm.bias": torch.zeros(D),
+               "head.weight": torch.randn(5, D, generator=g), "head.bias": torch.zeros(5)}
+    for i in range(depth):
+        for name, shape in (("norm1.weight", (D,)), ("norm1.bias", (D,)), ("attn.qkv.weight", (3 * D, D)),
+                            ("attn.qkv.bias", (3 * D,)), ("attn.proj.weight", (D, D)), ("attn.proj.bias", (D,)),
+                            ("norm2.weight", (D,)), ("norm2.bias", (D,)), ("mlp.fc1.weight", (M, D)),
+                            ("mlp.fc1.bias", (M,)), ("mlp.fc2.weight", (D, M)), ("mlp.fc2.bias", (D,))):
+            timm_sd["blocks.%d.%s" % (i, name)] = torch.randn(*shape, generator=g)
+    cfg = {"embed_dim": D, "patch_size": P, "q_format": fmt}
+    sd = rename_timm_state_dict(timm_sd, cfg, 5)
+    m = make("classification", fmt, image_size=224)
+    res = m.load_state_dict(sd, strict=False)
+    assert res.unexpected_keys == []
+    assert sorted(res.missing_keys) == sorted(k for k in m.state_dict() if k.startswith("decoder.") or "det" in k)
+    pe = m.state_dict()["patch_to_embedding.1.weight" if fmt != "FP32" else "patch_to_embedding.weight"]
+    w = timm_sd["patch_embed.proj.weight"]
+    assert pe.shape == (D, 3 * P * P) and torch.equal(pe[7, (3 * P + 5) * 3 + 2], w[7, 2, 3, 5])   # (O,(H,W,I))
+    qkv_key = "transformer.layers.1.0.fn.fn.to_qkv%s.weight" % (".1" if fmt != "FP32" else "")
+    assert torch.equal(m.state_dict()[qkv_key], timm_sd["blocks.1.attn.qkv.weight"])
