@@ -122,7 +122,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (fake-quantised to fp16 values)", "data": "synthetic",
-        "config": {"workload": "ViT-Small cls 256x256 q_format=%s, CPU sample batch %d" % (args.q_format, batch)},
+        "config": {"workload": "ViT-Small cls 256x256x3, 45 classes, q_format=%s, batch %d/GPU, fwd+CE+bwd"
+                               % (args.q_format, args.batch),
+                   "sample": "each step is batch %d of that workload on the host cores (bounded CPU sample)" % batch,
+                   "parallelism": "cpu, %d threads" % threads},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": "%d steps of batch %d (same model/input shape), host cores=%d" % (steps, batch, os.cpu_count())},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
