@@ -143,6 +143,11 @@ int mv_convert_f32(const float* in, void* out, int out_dtype, int64_t n, void* s
  * widens the fp16 attention tensors. */
 int mv_widen_transpose(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out,
                        float* out_t, int64_t ld_t, float mul, void* stream);
+/* 3xTF32 operand split for q_format FP32: in fp32 [rows, cols] (row pitch ld) -> out fp32 [rows, 3*cols] =
+ * [hi | lo | hi] (mode 0, the A operand) or [hi | hi | lo] (mode 1, the B operand), hi = tf32 truncation of
+ * x, lo = x - hi.  mv_gemm over the concatenated K computes hi*hi + lo*hi + hi*lo with fp32 accumulation
+ * (product error ~2^-21), i.e. an fp32-grade Linear on the kind::tf32 tensor-core path. */
+int mv_split_tf32(const float* in, int64_t ld, int rows, int cols, float* out, int mode, void* stream);
 
 /* Library-wide switches (testing / A-B measurement).  "attn_sn": 1 (default) = sequences of at most
  * 272 keys use the resident-K/V short-sequence attention kernels, 0 = always the blocked kernels. */

@@ -493,6 +493,25 @@ __global__ void widen_transpose_kernel(const InT* __restrict__ in, int64_t ld, i
     }
 }
 
+// 3xTF32 operand preparation (q_format FP32): x = hi + lo with hi = the tf32 the tensor core would see
+// (low 13 mantissa bits cleared) and lo = x - hi (exact in fp32).  A GEMM over the K-concatenated
+// operands A' = [hi | lo | hi], B' = [hi | hi | lo] accumulates hi*hi + lo*hi + hi*lo in fp32: the
+// product error drops from 2^-11 to ~2^-21 relative, using the unchanged kind::tf32 kernel.
+__global__ void split_tf32_kernel(const float* __restrict__ in, int64_t ld, int rows, int cols,
+                                  float* __restrict__ out, int mode) {
+    const int64_t n = int64_t(rows) * cols;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const int r = int(i / cols), c = int(i % cols);
+        const float x = in[int64_t(r) * ld + c];
+        const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        const float lo = x - hi;
+        float* o = out + int64_t(r) * 3 * cols + c;
+        o[0] = hi;
+        o[cols] = mode == 0 ? lo : hi;
+        o[2 * cols] = mode == 0 ? hi : lo;
+    }
+}
+
 }  // namespace mv
 
 using namespace mv;
@@ -613,4 +632,14 @@ extern "C" int mv_widen_transpose(const void* in, int in_dtype, int64_t ld, int 
     else MV_CHECK(false, "mv_widen_transpose: bad dtype");
     g_launches++;
     return check_cuda(cudaGetLastError(), "widen transpose launch");
+}
+
+extern "C" int mv_split_tf32(const float* in, int64_t ld, int rows, int cols, float* out, int mode, void* stream) {
+    MV_CHECK(in && out && rows > 0 && cols > 0 && (mode == 0 || mode == 1), "mv_split_tf32: bad arguments");
+    const int64_t n = int64_t(rows) * cols;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    split_tf32_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, ld, rows, cols, out, mode);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "split tf32 launch");
 }

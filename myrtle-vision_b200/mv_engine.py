@@ -50,6 +50,11 @@ class EncoderEngine:
         # contractions as kind::tf32 on fp32 containers — what the reference's torch 1.11 does with its
         # default allow_tf32 matmuls; (8,10) values are exact tf32 operands.
         self.wide = plan.inp != (5, 10)
+        # FP32 (no quantisers at all): fp32-grade arithmetic.  Linears run as 3xTF32 — operands split into
+        # tf32 hi + lo parts concatenated along K (mv_split_tf32), so the kind::tf32 kernel accumulates
+        # hi*hi + lo*hi + hi*lo — and attention / GELU, which have no quantiser to fuse with in this format,
+        # use torch's fp32 ops.  This is the reference's "plumbing" configuration, not a performance path.
+        self.exact = plan.inp is None
         if cfg.dim != cfg.heads * 64:
             raise ValueError("dim must equal heads * 64 (dim_head is fixed at 64, models/vit.py:178)")
         self.fmt = plan.inp
@@ -93,6 +98,9 @@ class EncoderEngine:
             w = self.params[i].detach()
             old = self._wq.get(i) if self._wq else None
             e, m = self.fmt if self.fmt else (0, 0)
+            if self.exact:
+                wq[i] = (mv.split_tf32(w, 1), mv.split_tf32(w.t().contiguous(), 1))
+                continue
             q, qt = mv.quantize_weight(w, e, m, out=old[0] if old else None,
                                        out_t=old[1] if old else None,
                                        out_dtype=torch.float32 if self.wide else torch.float16)
@@ -246,11 +254,13 @@ class EncoderEngine:
         wq = self.quantised_weights()
         f16, f32 = torch.float16, torch.float32
         dev = img.device
+        ex = self.exact
+        A_ = (lambda t: mv.split_tf32(t, 0)) if ex else (lambda t: t)        # A operand of a Linear
 
         patches = mv.patchify_q(img, P, q_in=fmt, out_dtype=f32, cls_slot=True)
         x = torch.empty(M, D, dtype=f32, device=dev)
         pos32 = pos_full.detach().reshape(N, D).contiguous()
-        mv.gemm(patches, wq[0][0], x, bias=prm[1], q_out=plan.out, residual=pos32, q_res=plan.ff,
+        mv.gemm(A_(patches), wq[0][0], x, bias=prm[1], q_out=plan.out, residual=pos32, q_res=plan.ff,
                 rows_per_img=N)
         mv.cls_rows(cls_token.detach().reshape(D).contiguous(), pos32, x, B, N, D, q_ff=plan.ff)
 
@@ -259,24 +269,49 @@ class EncoderEngine:
             b0 = 2 + PER_LAYER * l
             xn1, mean1, rstd1 = mv.layernorm_q_fwd(x, prm[b0], prm[b0 + 1], q_in=fmt, q_post=fmt,
                                                    out_dtype=f32)
-            qkv = torch.empty(M, 3 * D, dtype=f16, device=dev)
-            mv.gemm(xn1, wq[b0 + 2][0], qkv, bias=prm[b0 + 3], q_out=plan.out)
-            att16, lse = mv.attention_fwd(qkv, B, H, N, scale=0.125, q_out=fmt)
-            att, _ = mv.widen_transpose(att16, want_copy=True, want_t=False)
+            qkv = torch.empty(M, 3 * D, dtype=f32 if ex else f16, device=dev)
+            mv.gemm(A_(xn1), wq[b0 + 2][0], qkv, bias=prm[b0 + 3], q_out=plan.out)
+            if ex:
+                att, lse = self._attention_exact_fwd(qkv, B, H, N)           # lse slot holds the probabilities
+                att16 = att
+            else:
+                att16, lse = mv.attention_fwd(qkv, B, H, N, scale=0.125, q_out=fmt)
+                att, _ = mv.widen_transpose(att16, want_copy=True, want_t=False)
             x1 = torch.empty(M, D, dtype=f32, device=dev)
-            mv.gemm(att, wq[b0 + 4][0], x1, bias=prm[b0 + 5], q_out=plan.out, residual=x, q_res=plan.ff)
+            mv.gemm(A_(att), wq[b0 + 4][0], x1, bias=prm[b0 + 5], q_out=plan.out, residual=x, q_res=plan.ff)
             xn2, mean2, rstd2 = mv.layernorm_q_fwd(x1, prm[b0 + 6], prm[b0 + 7], q_in=fmt, q_post=fmt,
                                                    out_dtype=f32)
-            gd = torch.empty(M, Mm, dtype=f16, device=dev)                  # gelu'(u)
             h = torch.empty(M, Mm, dtype=f32, device=dev)
-            mv.gemm(xn2, wq[b0 + 8][0], h, bias=prm[b0 + 9], q_out=plan.out, aux=gd,
-                    epilogue=mv.EPI_GELU, q_res=fmt)
+            if ex:
+                gd = torch.empty(M, Mm, dtype=f32, device=dev)               # u (pre-GELU), fp32
+                mv.gemm(A_(xn2), wq[b0 + 8][0], gd, bias=prm[b0 + 9])
+                h = torch.nn.functional.gelu(gd)
+            else:
+                gd = torch.empty(M, Mm, dtype=f16, device=dev)               # gelu'(u)
+                mv.gemm(xn2, wq[b0 + 8][0], h, bias=prm[b0 + 9], q_out=plan.out, aux=gd,
+                        epilogue=mv.EPI_GELU, q_res=fmt)
             x2 = torch.empty(M, D, dtype=f32, device=dev)
-            mv.gemm(h, wq[b0 + 10][0], x2, bias=prm[b0 + 11], q_out=plan.out, residual=x1, q_res=plan.ff)
+            mv.gemm(A_(h), wq[b0 + 10][0], x2, bias=prm[b0 + 11], q_out=plan.out, residual=x1, q_res=plan.ff)
             if save:
                 saved["layers"].append((x, xn1, mean1, rstd1, qkv, att16, lse, x1, xn2, mean2, rstd2, gd, h))
             x = x2
         return x.view(B, N, D), saved
+
+    @staticmethod
+    def _attention_exact_fwd(qkv, B, H, N):
+        q, k, v = qkv.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+        prob = torch.softmax(torch.matmul(q, k.transpose(-2, -1)) * 0.125, dim=-1)
+        return torch.matmul(prob, v).transpose(1, 2).reshape(B * N, H * 64), prob
+
+    @staticmethod
+    def _attention_exact_bwd(qkv, prob, d_att, B, H, N):
+        q, k, v = qkv.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+        do = d_att.view(B, N, H, 64).transpose(1, 2)
+        dv = torch.matmul(prob.transpose(-2, -1), do)
+        dp = torch.matmul(do, v.transpose(-2, -1))
+        ds = prob * (dp - (dp * prob).sum(-1, keepdim=True)) * 0.125
+        dq, dk = torch.matmul(ds, k), torch.matmul(ds.transpose(-2, -1), q)
+        return torch.stack((dq, dk, dv), dim=0).permute(1, 3, 0, 2, 4).reshape(B * N, 3 * H * 64)
 
     def _backward_wide(self, saved, gx):
         cfg, fmt = self.cfg, self.fmt
@@ -288,9 +323,14 @@ class EncoderEngine:
         dev = gx.device
         f16, f32 = torch.float16, torch.float32
 
+        ex = self.exact
+        A_ = (lambda t: mv.split_tf32(t, 0)) if ex else (lambda t: t)
+
         def wgrad(dy, act, out):                       # out[o, i] += sum_m dy[m, o] act[m, i]
-            _, dy_t = mv.widen_transpose(dy)
-            _, act_t = mv.widen_transpose(act)
+            _, dy_t = mv.widen_transpose(dy, padded=ex)
+            _, act_t = mv.widen_transpose(act, padded=ex)
+            if ex:
+                dy_t, act_t = mv.split_tf32(dy_t, 0), mv.split_tf32(act_t, 1)
             mv.gemm(dy_t, act_t, out, accumulate=True)
 
         # the fp16 attention backward wants its gradient operand inside fp16's range: same
@@ -308,10 +348,16 @@ class EncoderEngine:
             x, xn1, mean1, rstd1, qkv, att16, lse, x1, xn2, mean2, rstd2, gd, h = saved["layers"][l]
             # ---- FeedForward
             du = torch.empty(M, Mm, dtype=f32, device=dev)
-            mv.gemm(dx, wq[b0 + 10][1], du, aux=gd, epilogue=mv.EPI_DGELU)
+            if ex:
+                mv.gemm(A_(dx), wq[b0 + 10][1], du)
+                u = gd                                                       # gelu'(u) = Phi(u) + u phi(u)
+                du.mul_(0.5 * (1.0 + torch.erf(u * 0.7071067811865476))
+                        + u * torch.exp(-0.5 * u * u) * 0.3989422804014327)
+            else:
+                mv.gemm(dx, wq[b0 + 10][1], du, aux=gd, epilogue=mv.EPI_DGELU)
             wgrad(dx, h, g[b0 + 10])
             dxn2 = torch.empty(M, D, dtype=f32, device=dev)
-            mv.gemm(du, wq[b0 + 8][1], dxn2, tag="dgrad")
+            mv.gemm(A_(du), wq[b0 + 8][1], dxn2, tag="dgrad")
             wgrad(du, xn2, g[b0 + 8])
             mv.colsum(du, g[b0 + 9].view(-1))
             del du
@@ -319,14 +365,20 @@ class EncoderEngine:
                                         dgamma=g[b0 + 6], dbeta=g[b0 + 7], dbias_prev=g[b0 + 5],
                                         want_f16=False)
             # ---- Attention
-            datt = torch.empty(M, D, dtype=f16, device=dev)
-            mv.gemm(dx1, wq[b0 + 4][1], datt, tag="dgrad")
+            datt = torch.empty(M, D, dtype=f32 if ex else f16, device=dev)
+            mv.gemm(A_(dx1), wq[b0 + 4][1], datt, tag="dgrad")
             wgrad(dx1, att16, g[b0 + 4])
-            dqkv16 = mv.attention_bwd(qkv, att16, datt, lse, B, H, N, scale=0.125)
-            dqkv, dqkv_t = mv.widen_transpose(dqkv16, want_copy=True)
+            if ex:
+                dqkv16 = dqkv = self._attention_exact_bwd(qkv, lse, datt, B, H, N)
+                _, dqkv_t = mv.widen_transpose(dqkv, padded=True)
+            else:
+                dqkv16 = mv.attention_bwd(qkv, att16, datt, lse, B, H, N, scale=0.125)
+                dqkv, dqkv_t = mv.widen_transpose(dqkv16, want_copy=True)
             dxn1 = dxn2
-            mv.gemm(dqkv, wq[b0 + 2][1], dxn1, tag="dgrad")
-            _, xn1_t = mv.widen_transpose(xn1)
+            mv.gemm(A_(dqkv), wq[b0 + 2][1], dxn1, tag="dgrad")
+            _, xn1_t = mv.widen_transpose(xn1, padded=ex)
+            if ex:
+                dqkv_t, xn1_t = mv.split_tf32(dqkv_t, 0), mv.split_tf32(xn1_t, 1)
             mv.gemm(dqkv_t, xn1_t, g[b0 + 2], accumulate=True)
             mv.colsum(dqkv16, g[b0 + 3].view(-1))
             prev_bias = g[b0 - 1] if l > 0 else None

@@ -333,7 +333,7 @@ def convert_f32(x, out_dtype=torch.float16, out=None):
     return out
 
 
-def widen_transpose(x2d, *, want_copy=False, want_t=True, mul=1.0):
+def widen_transpose(x2d, *, want_copy=False, want_t=True, mul=1.0, padded=False):
     """fp16/fp32 [rows, cols] -> (fp32 copy or None, fp32 transpose [cols, rows] or None).  The
     transpose is a view of a buffer whose row pitch is padded to 16 bytes (TMA global stride rule)."""
     _need_cuda(x2d)
@@ -341,13 +341,25 @@ def widen_transpose(x2d, *, want_copy=False, want_t=True, mul=1.0):
     rows, cols = x2d.shape
     out = torch.empty(rows, cols, dtype=torch.float32, device=x2d.device) if want_copy else None
     pitch = (rows + 3) // 4 * 4
-    out_t = (torch.empty(cols, pitch, dtype=torch.float32, device=x2d.device)[:, :rows]
-             if want_t else None)
+    alloc = torch.empty if pitch == rows else torch.zeros      # pad columns may be read as K (3xTF32 split)
+    base_t = alloc(cols, pitch, dtype=torch.float32, device=x2d.device) if want_t else None
+    out_t = base_t[:, :rows] if want_t else None
     _check(lib().mv_widen_transpose(_ptr(x2d), _DT[x2d.dtype], ctypes.c_int64(x2d.stride(0)), rows, cols,
                                     _ptr(out), _ptr(out_t), ctypes.c_int64(pitch), ctypes.c_float(mul),
                                     _stream()),
            "mv_widen_transpose")
-    return out, out_t
+    return out, (base_t if padded else out_t)
+
+
+def split_tf32(x2d, mode):
+    """fp32 [rows, cols] -> fp32 [rows, 3*cols]: [hi|lo|hi] (mode 0, A operand) or [hi|hi|lo] (mode 1, B)."""
+    _need_cuda(x2d)
+    assert x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.dtype == torch.float32
+    rows, cols = x2d.shape
+    out = torch.empty(rows, 3 * cols, dtype=torch.float32, device=x2d.device)
+    _check(lib().mv_split_tf32(_ptr(x2d), ctypes.c_int64(x2d.stride(0)), rows, cols, _ptr(out), int(mode),
+                               _stream()), "mv_split_tf32")
+    return out
 
 
 def upsample_ce(y, labels, ignore_index=-100):
