@@ -500,10 +500,58 @@ constexpr int kSnOffQ = 4 * kSnTile;
 constexpr int kSnOffDO = kSnOffQ + kSnQBytes;
 constexpr int kSnOffDS = kSnOffDO + kSnQBytes;
 constexpr int kSnOffVec = kSnOffDS + 4 * kSnTile;      // L[272], Delta[272], dQ tail accumulators [16][64]
-constexpr int kSnOffBar = kSnOffVec + (2 * kSnMaxKeys + 16 * 64) * 4;
+constexpr int kSnStgPitch = 80;                                 // bytes per staged row (64 B + pad: conflict-free 16 B stores)
+constexpr int kSnOffStg = kSnOffVec + (2 * kSnMaxKeys + 16 * 64) * 4;   // 8 math warps x 32 rows x kSnStgPitch
+constexpr int kSnOffVec2 = kSnOffStg + 8 * 32 * kSnStgPitch;           // L / Delta of the next pair (double buffer)
+constexpr int kSnOffBar = kSnOffVec2 + 2 * kSnMaxKeys * 4;
 constexpr int kSnBwdSmem = kSnOffBar + 256 + 1024;
 
+// Debug timeline (tools/trace_attn_bwd.py): when a trace buffer is registered, CTA 0 stamps clock64() at
+// the hand-offs between the MMA issuer and the math groups.  Record = {event, index, clock}.
+static unsigned long long* g_sn_trace = nullptr;
+extern "C" int mv_debug_set_attn_trace(void* dev_buf) { g_sn_trace = static_cast<unsigned long long*>(dev_buf); return 0; }
+#ifndef MV_SN_TRACE
+#define SN_TRACE(cond, region, ev, idx) do { } while (0)
+#else
+#define SN_TRACE(cond, region, ev, idx)                                                        \
+    do {                                                                                       \
+        if (p.trace != nullptr && blockIdx.x == 0 && (cond)) {                                 \
+            unsigned long long* t_ = p.trace + (region) * 3072 + 3 * (trace_n++ % 1024);       \
+            t_[0] = (ev); t_[1] = (unsigned long long)(idx); t_[2] = clock64();                \
+        }                                                                                      \
+    } while (0)
+#endif
+
+// Accumulator rows leave TMEM one row per thread; written like that, every 16-byte store instruction of a
+// warp touches 32 different lines and the LSU serialises them (3000+ cycles per epilogue, measured with
+// the clock64 timeline).  Each warp parks half a row per lane (32 fp16) in its private staging tile and
+// writes it back with four lanes per row: 8 rows x 64 contiguous bytes per store instruction.
+// v0 / v1: columns 0..31 / 32..63 of this lane's row (fp32 bits).  dst0: row 0 of the warp's 32 rows.
+__device__ __forceinline__ void sn_store_rows(uint8_t* stg, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+                                              __half* dst0, int64_t ld, int nvalid, int lane) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t (&v)[32] = half == 0 ? v0 : v1;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            *reinterpret_cast<uint4*>(stg + lane * kSnStgPitch + i * 16) = make_uint4(
+                pack_h2_satf(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                pack_h2_satf(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                pack_h2_satf(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                pack_h2_satf(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int row = it * 8 + (lane >> 2), chunk = lane & 3;
+            const uint4 w = *reinterpret_cast<const uint4*>(stg + row * kSnStgPitch + chunk * 16);
+            if (row < nvalid) *reinterpret_cast<uint4*>(dst0 + row * ld + half * 32 + chunk * 8) = w;
+        }
+        __syncwarp();
+    }
+}
+
 struct SnBwdDev {
+    unsigned long long* trace;
     int B, H, N, D;
     int n_pass;                 // 128-key tiles
     int n_reg;                  // regular 64-row blocks per pass (2 per 128 query rows below 256)
@@ -526,9 +574,10 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     uint8_t* sQ = smem + kSnOffQ;                         // rows 0..271
     uint8_t* sdO = smem + kSnOffDO;
     uint8_t* sdS = smem + kSnOffDS;                       // ring of 4 dS^T tiles [128 keys][64 rows]
-    float* sL = reinterpret_cast<float*>(smem + kSnOffVec);
-    float* sDelta = sL + kSnMaxKeys;
-    float* sdQt = sDelta + kSnMaxKeys;
+    float* sLD0 = reinterpret_cast<float*>(smem + kSnOffVec);     // L[272], Delta[272] of even pairs
+    float* sLD1 = reinterpret_cast<float*>(smem + kSnOffVec2);    // ... of odd pairs
+    float* sdQt = sLD0 + 2 * kSnMaxKeys;
+    uint8_t* sStg = smem + kSnOffStg;                            // per math warp: 32 rows x kSnStgPitch
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSnOffBar);
     uint64_t* kv_full = bars;           // [2]
     uint64_t* kv_empty = bars + 2;      // [2]
@@ -543,6 +592,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int trace_n = 0;
     const int n_bh = p.B * p.H;
     const int n_local = blockIdx.x < n_bh ? (n_bh - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int nblk = p.n_reg + (p.tail_w > 0 ? 1 : 0);           // blocks per pass
@@ -612,78 +662,95 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             const uint32_t idesc_tt = make_idesc(0, 0, 1, 1, 128, 64);     // A MN-major, B MN-major, N = 64
             const uint32_t idesc_s64 = make_idesc(0, 0, 0, 0, 128, 64);
             const uint32_t idesc_stail = make_idesc(0, 0, 0, 0, 128, p.tail_w > 0 ? p.tail_w : 16);
-            int gb0 = 0, pc0 = 0;
-            for (int n = 0; n < n_local; n++, gb0 += nb_bh, pc0 += p.n_pass) {
+            // This one lane is on the critical path of every block (the math groups wait for its MMAs and it
+            // waits for theirs): the schedule is walked with counters instead of divisions and every
+            // descriptor is a base built once plus a small offset.
+            const uint64_t dK0 = make_smem_desc_sw128(aK, 16, 1024), dV0 = make_smem_desc_sw128(aV, 16, 1024);
+            const uint64_t dQ0 = make_smem_desc_sw128(aQ, 16, 1024), dD0 = make_smem_desc_sw128(adO, 16, 1024);
+            const uint64_t bD0 = make_smem_desc_sw128(adO, 8192, 1024), bQ0 = make_smem_desc_sw128(aQ, 8192, 1024);
+            const uint64_t bK0 = make_smem_desc_sw128(aK, 8192, 1024), aS0 = make_smem_desc_sw128(adS, kSnTile, 1024);
+            constexpr uint64_t kTileOff = kSnTile >> 4;            // one 16 KB tile further, in descriptor units
+            int gb_pre = 0, gb_post = 0;                           // global block counters (parity = math group)
+            int pc0 = 0;
+            for (int n = 0; n < n_local; n++, pc0 += p.n_pass) {
                 mbar_wait(qdo_full, n & 1);
-                // Descriptors are built once per block and advanced with one 64-bit add per MMA: this lane
-                // issues ~25 MMAs of 32 tensor-pipe cycles each per block and must not be the bottleneck.
-                auto pre = [&](int lb) {
-                    const int gb = gb0 + lb, g = gb & 1, j = lb / nblk, c = lb % nblk;
+                int j_pre = 0, c_pre = 0, j_post = 0, c_post = 0, rb_post = 0;     // rb: regular blocks before this one
+                auto pre = [&]() {
+                    const int gb = gb_pre, g = gb & 1, j = j_pre, c = c_pre;
                     const int pc = pc0 + j, st = pc & 1;
                     if (c == 0) mbar_wait(&kv_full[st], (pc >> 1) & 1);
                     tc_fence_after();
                     const bool regular = c < p.n_reg;
-                    const int row0 = regular ? 64 * c : 256;
+                    const uint64_t roff = uint64_t(regular ? 64 * c : 256) * 8;          // row0 * 128 B >> 4
                     const uint32_t idesc = regular ? idesc_s64 : idesc_stail;
                     const uint32_t tS = tmem_base + g * 128, tdP = tS + 64;
-                    const uint64_t dk = make_smem_desc_sw128(aK + st * kSnTile, 16, 1024);
-                    const uint64_t dv = make_smem_desc_sw128(aV + st * kSnTile, 16, 1024);
-                    const uint64_t dq = make_smem_desc_sw128(aQ + row0 * 128, 16, 1024);
-                    const uint64_t dd = make_smem_desc_sw128(adO + row0 * 128, 16, 1024);
+                    const uint64_t dk = dK0 + st * kTileOff, dv = dV0 + st * kTileOff;
+                    const uint64_t dq = dQ0 + roff, dd = dD0 + roff;
                     if (leader) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) umma_f16(tS, dk + 2 * k, dq + 2 * k, idesc, k > 0);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) umma_f16(tdP, dv + 2 * k, dd + 2 * k, idesc, k > 0);
+                        for (int k = 0; k < 4; k++) {
+                            umma_f16(tS, dk + 2 * k, dq + 2 * k, idesc, k > 0);
+                            umma_f16(tdP, dv + 2 * k, dd + 2 * k, idesc, k > 0);
+                        }
                         umma_commit(&sdp_full[g]);
+                        SN_TRACE(true, 0, 1, gb);                       // pre MMAs issued
                     }
+                    gb_pre++;
+                    if (++c_pre == nblk) { c_pre = 0; j_pre++; }
                     __syncwarp();
                 };
-                auto post = [&](int lb) {
-                    const int gb = gb0 + lb, g = gb & 1, j = lb / nblk, c = lb % nblk;
+                auto post = [&]() {
+                    const int gb = gb_post, g = gb & 1, j = j_post, c = c_post;
                     const int pc = pc0 + j, st = pc & 1;
                     const bool regular = c < p.n_reg;
-                    const int row0 = regular ? 64 * c : 256;
+                    const uint64_t roff = uint64_t(regular ? 64 * c : 256) * 8;
                     const uint32_t tS = tmem_base + g * 128, tdP = tS + 64;
-                    const uint64_t bdo = make_smem_desc_sw128(adO + row0 * 128, 8192, 1024);     // B = dO rows, MN-major
-                    const uint64_t bq = make_smem_desc_sw128(aQ + row0 * 128, 8192, 1024);
+                    const uint64_t bdo = bD0 + roff, bq = bQ0 + roff;                     // B = dO / Q rows, MN-major
                     mbar_wait(&pds_full[g], (gb >> 1) & 1);
+                    SN_TRACE(leader, 0, 3, gb);                             // math of block gb done (seen by issuer)
                     if (c == 0 && pc > 0) mbar_wait(acc_empty, (pc - 1) & 1);       // dV / dK of the previous pass were read
+                    if (c == 1 && j == 0 && n > 0) mbar_wait(dq_empty, (n - 1) & 1);  // dQ of the previous pair was read
                     tc_fence_after();
                     const uint32_t acc0 = c > 0 ? 1u : 0u;
-                    if (regular && (c & 1) && j == 0 && (c >> 1) == 0 && n > 0) { mbar_wait(dq_empty, (n - 1) & 1); tc_fence_after(); }
-                    if (!leader) { __syncwarp(); return; }
-                    if (regular) {
+                    if (leader) {
+                        if (regular) {
+                            const bool with_dq = (c & 1) != 0;
+                            // dQ_i += dS_i K_j for the block pair (c-1, c): A = the pair's dS^T tiles in shared memory
+                            // (M = 2 x 64 rows, K = 128 keys).  dV, dK, dQ are independent accumulators: round-robin.
+                            const uint64_t ads = aS0 + uint64_t((rb_post - 1) & 3) * kTileOff;
+                            const uint64_t bk = bK0 + st * kTileOff;
+                            const uint32_t accq = j > 0 ? 1u : 0u;
+                            const uint32_t tq = tdQ + (c >> 1) * 64;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) umma_f16_ts(tdV, tS + k * 8, bdo + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
-#pragma unroll
-                        for (int k = 0; k < 4; k++) umma_f16_ts(tdK, tdP + k * 8, bq + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
-                    } else {
-                        for (int k = 0; k < (p.tail_w >> 4); k++) umma_f16_ts(tdV, tS + k * 8, bdo + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
-                        for (int k = 0; k < (p.tail_w >> 4); k++) umma_f16_ts(tdK, tdP + k * 8, bq + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                            for (int k = 0; k < 4; k++) {
+                                umma_f16_ts(tdV, tS + k * 8, bdo + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                                umma_f16_ts(tdK, tdP + k * 8, bq + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                                if (with_dq) {
+                                    umma_f16(tq, ads + 128 * (2 * k), bk + 128 * (2 * k), idesc_tt, accq | uint32_t(k > 0));
+                                    umma_f16(tq, ads + 128 * (2 * k + 1), bk + 128 * (2 * k + 1), idesc_tt, 1u);
+                                }
+                            }
+                        } else {
+                            for (int k = 0; k < (p.tail_w >> 4); k++) umma_f16_ts(tdV, tS + k * 8, bdo + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                            for (int k = 0; k < (p.tail_w >> 4); k++) umma_f16_ts(tdK, tdP + k * 8, bq + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                        }
+                        SN_TRACE(true, 0, 4, gb);                               // post MMAs issued
+                        if (c == nblk - 1) {
+                            umma_commit(acc_full);
+                            umma_commit(&kv_empty[st]);
+                            if (j == p.n_pass - 1) { umma_commit(dq_full); umma_commit(qdo_empty); }
+                        }
                     }
-                    if (regular && (c & 1)) {
-                        // dQ_i += dS_i K_j: A = the pair's dS^T tiles (M = 2 x 64 rows, K = 128 keys)
-                        const int i = c >> 1;
-                        const int buf = (j * p.n_reg + c - 1) & 3;
-                        const uint64_t ads = make_smem_desc_sw128(adS + buf * kSnTile, kSnTile, 1024);
-                        const uint64_t bk = make_smem_desc_sw128(aK + st * kSnTile, 8192, 1024);
-                        const uint32_t accq = j > 0 ? 1u : 0u;
-#pragma unroll
-                        for (int k = 0; k < 8; k++) umma_f16(tdQ + i * 64, ads + 128 * k, bk + 128 * k, idesc_tt, accq | uint32_t(k > 0));
-                    }
-                    if (c == nblk - 1) {
-                        umma_commit(acc_full);
-                        umma_commit(&kv_empty[st]);
-                        if (j == p.n_pass - 1) { umma_commit(dq_full); umma_commit(qdo_empty); }
-                    }
+                    gb_post++;
+                    if (regular) rb_post++;
+                    if (++c_post == nblk) { c_post = 0; j_post++; }
                     __syncwarp();
                 };
-                pre(0);
-                if (nb_bh > 1) pre(1);
+                pre();
+                if (nb_bh > 1) pre();
                 for (int lb = 0; lb < nb_bh; lb++) {
-                    post(lb);
-                    if (lb + 2 < nb_bh) pre(lb + 2);
+                    post();
+                    if (lb + 2 < nb_bh) pre();
                 }
             }
         }
@@ -699,29 +766,54 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         for (int n = 0; n < n_local; n++, gb0 += nb_bh, pc0 += p.n_pass) {
             const int bh = blockIdx.x + n * gridDim.x;
             const int b = bh / p.H, h = bh % p.H;
-            // per-row statistics of this pair; rows >= N get L = +inf so that their P is exactly 0
-            for (int r = mt; r < kSnMaxKeys; r += 256) {
-                float Lr = INFINITY, dl = 0.f;
-                if (r < p.N) {
-                    Lr = p.lse[(int64_t(b) * p.H + h) * p.N + r];
-                    const uint4* a = reinterpret_cast<const uint4*>(p.d_o + (int64_t(b) * p.N + r) * p.D + h * 64);
-                    const uint4* c4 = reinterpret_cast<const uint4*>(p.o + (int64_t(b) * p.N + r) * p.D + h * 64);
+            // Per-row statistics (L from the forward, Delta = rowsum(dO * O)); rows >= N get L = +inf so that
+            // their P is exactly 0.  They are double-buffered: the first pair's are computed here, every
+            // later pair's during the previous pair's pass-boundary waits (stats_rows below), so the cold
+            // global reads never sit on the critical path.
+            float* sL = (n & 1) ? sLD1 : sLD0;
+            float* sDelta = sL + kSnMaxKeys;
+            float* nL = (n & 1) ? sLD0 : sLD1;
+            const int bh_next = bh + gridDim.x;
+            // Eight lanes share a row (one 16-byte chunk of the head's 128 B each), so a warp instruction reads
+            // four whole lines instead of one sector from each of 32 rows; three row groups are in flight.
+            auto stats_rows = [&](int bh_t, int base, float* dL) {
+                const int sub = mt >> 3, ch = mt & 7;
+                const int b_t = bh_t / p.H, h_t = bh_t % p.H;
+                uint4 xa[3], ya[3];
+                float Lr[3];
 #pragma unroll
-                    for (int t = 0; t < 8; t++) {
-                        const uint4 x = a[t], y = c4[t];
-                        const __half2* xh = reinterpret_cast<const __half2*>(&x);
-                        const __half2* yh = reinterpret_cast<const __half2*>(&y);
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const float2 fx = __half22float2(xh[u]), fy = __half22float2(yh[u]);
-                            dl = fmaf(fx.x, fy.x, dl); dl = fmaf(fx.y, fy.y, dl);
-                        }
+                for (int u = 0; u < 3; u++) {
+                    const int r = base + u * 32 + sub;
+                    xa[u] = make_uint4(0u, 0u, 0u, 0u); ya[u] = xa[u]; Lr[u] = INFINITY;
+                    if (r < p.N) {
+                        xa[u] = reinterpret_cast<const uint4*>(p.d_o + (int64_t(b_t) * p.N + r) * p.D + h_t * 64)[ch];
+                        ya[u] = reinterpret_cast<const uint4*>(p.o + (int64_t(b_t) * p.N + r) * p.D + h_t * 64)[ch];
+                        if (ch == 0) Lr[u] = p.lse[(int64_t(b_t) * p.H + h_t) * p.N + r];
                     }
                 }
-                sL[r] = Lr;
-                sDelta[r] = dl;
-            }
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int r = base + u * 32 + sub;
+                    const __half2* xh = reinterpret_cast<const __half2*>(&xa[u]);
+                    const __half2* yh = reinterpret_cast<const __half2*>(&ya[u]);
+                    float dl = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float2 fx = __half22float2(xh[q]), fy = __half22float2(yh[q]);
+                        dl = fmaf(fx.x, fy.x, dl); dl = fmaf(fx.y, fy.y, dl);
+                    }
+                    dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+                    dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+                    dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+                    if (ch == 0 && r < kSnMaxKeys) { dL[r] = Lr[u]; dL[kSnMaxKeys + r] = dl; }
+                }
+            };
+            SN_TRACE(quad == 0 && lane == 0, 1 + g, 19, n);                 // pair starts
+            if (n == 0)
+                for (int base = 0; base < kSnMaxKeys; base += 96) stats_rows(bh, base, sL);
+            int next_base = 0;                                              // rows of the next pair done so far
             for (int i = mt; i < 16 * 64; i += 256) sdQt[i] = 0.f;
+            SN_TRACE(quad == 0 && lane == 0, 1 + g, 11, n);                 // statistics of the pair computed
             named_bar_sync(1, 256);
             for (int j = 0; j < p.n_pass; j++) {
                 const int pc = pc0 + j, st = pc & 1;
@@ -733,7 +825,9 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     const bool regular = c < p.n_reg;
                     const int width = regular ? 64 : p.tail_w;
                     const int row0 = regular ? 64 * c : 256;
+                    SN_TRACE(quad == 0 && lane == 0, 1 + g, 5, gb);         // math group starts waiting for S^T / dP^T
                     mbar_wait(&sdp_full[g], (gb >> 1) & 1);
+                    SN_TRACE(quad == 0 && lane == 0, 1 + g, 6, gb);         // S^T / dP^T ready
                     tc_fence_after();
                     if (warp_live) {
                         uint8_t* ds_row = sdS + ((j * p.n_reg + c) & 3) * kSnTile + lr * 128;
@@ -813,9 +907,17 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&pds_full[g]);
+                    SN_TRACE(quad == 0 && lane == 0, 1 + g, 7, gb);         // P^T / dS^T written
                 }
                 // ---- pass epilogue: group 0 stores dV_j, group 1 stores dK_j
+                SN_TRACE(quad == 0 && lane == 0, 1 + g, 8, pc);
+                if (n + 1 < n_local) {
+                    // the last post-MMAs of the pass are still in flight: next pair's statistics, a share per pass
+                    const int upto = (j + 1 == p.n_pass) ? kSnMaxKeys : ((j + 1) * kSnMaxKeys / p.n_pass);
+                    for (; next_base < upto; next_base += 96) stats_rows(bh_next, next_base, nL);
+                }
                 mbar_wait(acc_full, pc & 1);
+                SN_TRACE(quad == 0 && lane == 0, 1 + g, 9, pc);             // dV / dK of the pass complete
                 tc_fence_after();
                 {
                     uint32_t v0[32], v1[32];
@@ -826,26 +928,16 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty);
-                    if (key < p.N) {
-                        __half* dst = p.dqkv + (int64_t(b) * p.N + key) * p.ld_dqkv + (g == 0 ? 2 : 1) * p.D + h * 64;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            reinterpret_cast<uint4*>(dst)[i] = make_uint4(
-                                pack_h2_satf(__uint_as_float(v0[8 * i]), __uint_as_float(v0[8 * i + 1])),
-                                pack_h2_satf(__uint_as_float(v0[8 * i + 2]), __uint_as_float(v0[8 * i + 3])),
-                                pack_h2_satf(__uint_as_float(v0[8 * i + 4]), __uint_as_float(v0[8 * i + 5])),
-                                pack_h2_satf(__uint_as_float(v0[8 * i + 6]), __uint_as_float(v0[8 * i + 7])));
-                            reinterpret_cast<uint4*>(dst)[4 + i] = make_uint4(
-                                pack_h2_satf(__uint_as_float(v1[8 * i]), __uint_as_float(v1[8 * i + 1])),
-                                pack_h2_satf(__uint_as_float(v1[8 * i + 2]), __uint_as_float(v1[8 * i + 3])),
-                                pack_h2_satf(__uint_as_float(v1[8 * i + 4]), __uint_as_float(v1[8 * i + 5])),
-                                pack_h2_satf(__uint_as_float(v1[8 * i + 6]), __uint_as_float(v1[8 * i + 7])));
-                        }
+                    {
+                        const int key0 = j * 128 + quad * 32;            // first key row of this warp
+                        __half* dst0 = p.dqkv + (int64_t(b) * p.N + key0) * p.ld_dqkv + (g == 0 ? 2 : 1) * p.D + h * 64;
+                        sn_store_rows(sStg + (warp - 2) * 32 * kSnStgPitch, v0, v1, dst0, p.ld_dqkv, p.N - key0, lane);
                     }
                 }
             }
             // ---- pair epilogue: group g stores dQ of query rows [128 g, 128 g + 128)
             mbar_wait(dq_full, n & 1);
+            SN_TRACE(quad == 0 && lane == 0, 1 + g, 10, n);
             tc_fence_after();
             {
                 uint32_t v0[32], v1[32];
@@ -858,32 +950,23 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(dq_empty);
-                const int row = g * 128 + lr;
-                if (have && row < p.N) {
-                    __half* dst = p.dqkv + (int64_t(b) * p.N + row) * p.ld_dqkv + h * 64;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        reinterpret_cast<uint4*>(dst)[i] = make_uint4(
-                            pack_h2_satf(__uint_as_float(v0[8 * i]), __uint_as_float(v0[8 * i + 1])),
-                            pack_h2_satf(__uint_as_float(v0[8 * i + 2]), __uint_as_float(v0[8 * i + 3])),
-                            pack_h2_satf(__uint_as_float(v0[8 * i + 4]), __uint_as_float(v0[8 * i + 5])),
-                            pack_h2_satf(__uint_as_float(v0[8 * i + 6]), __uint_as_float(v0[8 * i + 7])));
-                        reinterpret_cast<uint4*>(dst)[4 + i] = make_uint4(
-                            pack_h2_satf(__uint_as_float(v1[8 * i]), __uint_as_float(v1[8 * i + 1])),
-                            pack_h2_satf(__uint_as_float(v1[8 * i + 2]), __uint_as_float(v1[8 * i + 3])),
-                            pack_h2_satf(__uint_as_float(v1[8 * i + 4]), __uint_as_float(v1[8 * i + 5])),
-                            pack_h2_satf(__uint_as_float(v1[8 * i + 6]), __uint_as_float(v1[8 * i + 7])));
-                    }
+                if (have) {
+                    const int row0 = g * 128 + quad * 32;
+                    __half* dst0 = p.dqkv + (int64_t(b) * p.N + row0) * p.ld_dqkv + h * 64;
+                    sn_store_rows(sStg + (warp - 2) * 32 * kSnStgPitch, v0, v1, dst0, p.ld_dqkv, p.N - row0, lane);
                 }
             }
             // rows >= 256: dQ from the shared-memory accumulators
+            SN_TRACE(quad == 0 && lane == 0, 1 + g, 16, n);                 // dQ rows stored
             named_bar_sync(1, 256);
+            SN_TRACE(quad == 0 && lane == 0, 1 + g, 17, n);
             for (int i = mt; i < (p.N - 256) * 32; i += 256) {
                 const int r = i >> 5, l2 = i & 31;
                 *reinterpret_cast<uint32_t*>(p.dqkv + (int64_t(b) * p.N + 256 + r) * p.ld_dqkv + h * 64 + 2 * l2) =
                     pack_h2_satf(sdQt[r * 64 + 2 * l2], sdQt[r * 64 + 2 * l2 + 1]);
             }
             named_bar_sync(1, 256);
+            SN_TRACE(quad == 0 && lane == 0, 1 + g, 18, n);                 // pair finished
         }
     }
     tc_fence_before();
@@ -955,6 +1038,7 @@ int mv_attention_bwd_sn(const void* qkv, const void* o, const void* d_o, const f
     if (make_tmap_3d(&d16, d_o, MV_F16, D, N, B, D, uint64_t(N) * D, 64, 16, 1)) return 1;
     (void)delta;                                   // Delta is computed inside the kernel
     SnBwdDev p;
+    p.trace = g_sn_trace;
     p.B = B; p.H = H; p.N = N; p.D = D;
     p.n_pass = (N + 127) / 128;
     p.n_reg = 2 * (((N < 256 ? N : 256) + 127) / 128);

@@ -35,6 +35,7 @@ def build(force=False, verbose=False):
     flags = [f for f in flags if f != "--use_fast_math=false"]
     if verbose:
         flags += ["-Xptxas", "-v"]
+    flags += os.environ.get("MV_NVCC_FLAGS", "").split()      # e.g. -DMV_SN_TRACE for tools/trace_attn_bwd.py
     procs = []
     for src in sources():
         obj = src[:-3] + ".o"

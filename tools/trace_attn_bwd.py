@@ -1,0 +1,33 @@
+"""Timeline of the short-sequence attention backward (debug): CTA 0 stamps clock64() at every hand-off
+between the MMA issuer and the two math groups (mv_debug_set_attn_trace).  Prints per-event gaps in cycles."""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "myrtle-vision_b200")); sys.path.insert(0, ROOT)
+import torch
+import mv_native as mv
+B, H, N = 256, 6, 257
+D = H * 64
+torch.manual_seed(0)
+qkv = torch.randn(B * N, 3 * D, device="cuda").half()
+do = torch.randn(B * N, D, device="cuda").half()
+out, lse = mv.attention_fwd(qkv, B, H, N, q_out=(5, 10))
+for _ in range(2):
+    mv.attention_bwd(qkv, out, do, lse, B, H, N)
+buf = torch.zeros(3 * 3072, dtype=torch.int64, device="cuda")
+mv.lib().mv_debug_set_attn_trace(ctypes.c_void_p(buf.data_ptr()))
+mv.attention_bwd(qkv, out, do, lse, B, H, N)
+torch.cuda.synchronize()
+mv.lib().mv_debug_set_attn_trace(None)
+t = buf.cpu().view(3, 1024, 3)
+names = {1: "pre issued", 2: "issuer waits math", 3: "issuer sees math done", 4: "post issued", 5: "math waits S", 6: "S ready",
+         7: "math done", 16: "dq stored", 17: "bar after dq", 18: "pair finished", 19: "stats start", 12: "pre enter", 13: "pre fenced", 14: "pre 2 MMAs issued", 15: "pre 8 MMAs issued", 8: "waits acc", 9: "acc ready", 10: "dq ready", 11: "stats done"}
+ev = []
+for r in range(3):
+    for e, i, c in t[r].tolist():
+        if e:
+            ev.append((c, r, e, i))
+ev.sort()
+t0 = ev[0][0]
+# first two (image, head) pairs of CTA 0
+for c, r, e, i in ev[:260]:
+    print("%8d  %-7s %-22s %d" % (c - t0, ["issuer", "math g0", "math g1"][r], names[e], i))
