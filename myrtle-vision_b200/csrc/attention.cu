@@ -30,6 +30,7 @@ extern int64_t g_launches;
 
 constexpr int kAttThreads = 192;
 constexpr int kTile = 16384;          // 128 rows x 128 B
+constexpr int kStgPitchF = 36;        // floats per staged fp32 row chunk (32 + 4 pad: conflict-free 16 B accesses)
 constexpr uint32_t kIdescS = make_idesc(0, 0, 0, 0, 128, 128);     // A K-major, B K-major, N=128
 constexpr uint32_t kIdescPV = make_idesc(0, 0, 0, 1, 128, 64);     // A K-major, B MN-major, N=64
 constexpr uint32_t kIdescTT = make_idesc(0, 0, 1, 1, 128, 64);     // A MN-major, B MN-major, N=64
@@ -536,6 +537,7 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_co
     uint8_t* sK = smem + 4 * kTile;            // resident K_j  [64 keys][64 d] (8 KB)
     uint8_t* sV = smem + 4 * kTile + 8192;     // resident V_j
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTile);
+    float* sStg = reinterpret_cast<float*>(smem + 5 * kTile + 256);      // [4 math warps][32 rows][kStgPitchF]
     uint64_t* res_full = bars;
     uint64_t* ring_full = bars + 1;
     uint64_t* ring_empty = bars + 2;
@@ -662,19 +664,31 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_co
             mbar_wait(dq_full, it & 1);
             tc_fence_after();
             if (nchunk > 0) {
-                float* dst = p.dq_accum + (int64_t(b) * p.N + qrow) * p.D + h * 64;
+                // One TMEM lane = one query row per thread: reduced straight from registers, every red.add of a
+                // warp would touch 32 different lines.  The rows go through the warp's staging tile so that
+                // eight lanes add one row's 128 contiguous bytes: 4 full lines per instruction.
+                const int qrow0 = qrow - lane;                              // first row of this warp
+                float* dst0 = p.dq_accum + (int64_t(b) * p.N + qrow0) * p.D + h * 64;
+                float* stg = sStg + quad * (32 * kStgPitchF);
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
                     uint32_t v[32];
                     tmem_ld_32x32(tdQ + lane_off + c * 32, v);
                     tmem_ld_wait();
-                    if (q_ok) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++)
-                            atomicAdd(reinterpret_cast<float4*>(dst + c * 32) + i,
-                                      make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                    for (int i = 0; i < 8; i++)
+                        *reinterpret_cast<float4*>(stg + lane * kStgPitchF + 4 * i) =
+                            make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                        __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int row = i * 4 + (lane >> 3), chunk = lane & 7;
+                        const float4 w = *reinterpret_cast<const float4*>(stg + row * kStgPitchF + 4 * chunk);
+                        if (qrow0 + row < p.N)
+                            atomicAdd(reinterpret_cast<float4*>(dst0 + int64_t(row) * p.D + c * 32) + chunk, w);
                     }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -711,7 +725,7 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_co
     if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem_base); }
 }
 
-constexpr int kAttnBwd64Smem = 5 * kTile + 1024 + 256;
+constexpr int kAttnBwd64Smem = 5 * kTile + 1024 + 256 + 4 * 32 * kStgPitchF * 4;
 
 // dq fp32 [rows, D] -> fp16 into the q columns of dqkv [rows, ld]
 __global__ void __launch_bounds__(256)

@@ -170,6 +170,33 @@ __device__ __forceinline__ void sn_tail_row_fwd(const SnFwdDev& p, const uint8_t
     __syncwarp();
 }
 
+constexpr int kSnStgPitch = 80;                 // bytes per staged row (64 B + pad: conflict-free 16 B stores)
+// One TMEM lane = one output row per thread: stored directly, each 16-byte store instruction of a warp
+// touches 32 different lines and the LSU serialises them.  Each warp parks half a row per lane (32 fp16)
+// in its private staging tile and writes it back with four lanes per row — 8 rows x 64 contiguous bytes
+// per store instruction.  o: this lane's 64 output values; dst0: row 0 of the warp's 32 rows.
+__device__ __forceinline__ void sn_store_rows_f(uint8_t* stg, const float (&o)[64], __half* dst0, int64_t ld,
+                                                int nvalid, int lane) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            *reinterpret_cast<uint4*>(stg + lane * kSnStgPitch + i * 16) = make_uint4(
+                pack_h2_satf(o[32 * half + 8 * i], o[32 * half + 8 * i + 1]),
+                pack_h2_satf(o[32 * half + 8 * i + 2], o[32 * half + 8 * i + 3]),
+                pack_h2_satf(o[32 * half + 8 * i + 4], o[32 * half + 8 * i + 5]),
+                pack_h2_satf(o[32 * half + 8 * i + 6], o[32 * half + 8 * i + 7]));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int row = it * 8 + (lane >> 2), chunk = lane & 3;
+            const uint4 w = *reinterpret_cast<const uint4*>(stg + row * kSnStgPitch + chunk * 16);
+            if (row < nvalid) *reinterpret_cast<uint4*>(dst0 + row * ld + half * 32 + chunk * 8) = w;
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(kSnFwdThreads, 1)
 attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant__ CUtensorMap tmap16,
                    const __grid_constant__ SnFwdDev p) {
@@ -179,7 +206,8 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
     uint8_t* sV = smem + 2 * kSnKVBytes;
     uint8_t* sQ = smem + 4 * kSnKVBytes;                  // ring of 2 query tiles
     float* s_tail = reinterpret_cast<float*>(smem + 4 * kSnKVBytes + 2 * kSnTile);   // [2 warps][64 + kSnMaxKeys]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail + kSnTailWarps * (64 + kSnMaxKeys));
+    uint8_t* sStg = reinterpret_cast<uint8_t*>(s_tail + kSnTailWarps * (64 + kSnMaxKeys));   // [8 math warps][32 rows][kSnStgPitch]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + kSnMathWarps * 32 * kSnStgPitch);
     uint64_t* k_full = bars;            // [2]
     uint64_t* k_empty = bars + 2;       // [2]
     uint64_t* v_full = bars + 4;        // [2]
@@ -429,8 +457,9 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&v_empty[s]);
-            if (row < p.N) {
-                const float inv = 1.0f / l;
+            {
+                const bool live = row < p.N;
+                const float inv = live ? 1.0f / l : 0.f;
                 const int64_t grow = int64_t(b) * p.N + row;
                 if (mode == 1) {
 #pragma unroll
@@ -440,19 +469,16 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
                     for (int i = 0; i < 64; i++) o[i] = fq_apply(o[i] * inv, mode, p.q_out);
                 }
                 if (p.out_dtype == MV_F16) {
-                    __half* dst = reinterpret_cast<__half*>(p.out) + grow * p.ld_out + h * 64;
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        reinterpret_cast<uint4*>(dst)[i] =
-                            make_uint4(pack_h2_satf(o[8 * i], o[8 * i + 1]), pack_h2_satf(o[8 * i + 2], o[8 * i + 3]),
-                                       pack_h2_satf(o[8 * i + 4], o[8 * i + 5]), pack_h2_satf(o[8 * i + 6], o[8 * i + 7]));
-                } else {
+                    const int row0 = row - lane;                             // first row of this warp
+                    __half* dst0 = reinterpret_cast<__half*>(p.out) + (int64_t(b) * p.N + row0) * p.ld_out + h * 64;
+                    sn_store_rows_f(sStg + (warp - 2) * 32 * kSnStgPitch, o, dst0, p.ld_out, p.N - row0, lane);
+                } else if (live) {
                     float* dst = reinterpret_cast<float*>(p.out) + grow * p.ld_out + h * 64;
 #pragma unroll
                     for (int i = 0; i < 16; i++)
                         reinterpret_cast<float4*>(dst)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                 }
-                if (p.lse != nullptr) p.lse[(int64_t(b) * p.H + h) * p.N + row] = m + log2f(l);
+                if (live && p.lse != nullptr) p.lse[(int64_t(b) * p.H + h) * p.N + row] = m + log2f(l);
             }
         }
     } else {
@@ -478,7 +504,8 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
     if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
 }
 
-constexpr int kSnFwdSmem = 4 * kSnKVBytes + 2 * kSnTile + kSnTailWarps * (64 + kSnMaxKeys) * 4 + 256 + 1024;
+constexpr int kSnFwdSmem = 4 * kSnKVBytes + 2 * kSnTile + kSnTailWarps * (64 + kSnMaxKeys) * 4 +
+                           kSnMathWarps * 32 * kSnStgPitch + 256 + 1024;
 
 
 // =====================================================================================
@@ -500,7 +527,6 @@ constexpr int kSnOffQ = 4 * kSnTile;
 constexpr int kSnOffDO = kSnOffQ + kSnQBytes;
 constexpr int kSnOffDS = kSnOffDO + kSnQBytes;
 constexpr int kSnOffVec = kSnOffDS + 4 * kSnTile;      // L[272], Delta[272], dQ tail accumulators [16][64]
-constexpr int kSnStgPitch = 80;                                 // bytes per staged row (64 B + pad: conflict-free 16 B stores)
 constexpr int kSnOffStg = kSnOffVec + (2 * kSnMaxKeys + 16 * 64) * 4;   // 8 math warps x 32 rows x kSnStgPitch
 constexpr int kSnOffVec2 = kSnOffStg + 8 * 32 * kSnStgPitch;           // L / Delta of the next pair (double buffer)
 constexpr int kSnOffBar = kSnOffVec2 + 2 * kSnMaxKeys * 4;
