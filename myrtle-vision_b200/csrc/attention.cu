@@ -31,7 +31,6 @@ extern int64_t g_launches;
 constexpr int kAttThreads = 192;
 constexpr int kTile = 16384;          // 128 rows x 128 B
 constexpr int kStgPitchF = 36;        // floats per staged fp32 row chunk (32 + 4 pad: conflict-free 16 B accesses)
-constexpr uint32_t kIdescS = make_idesc(0, 0, 0, 0, 128, 128);     // A K-major, B K-major, N=128
 constexpr uint32_t kIdescPV = make_idesc(0, 0, 0, 1, 128, 64);     // A K-major, B MN-major, N=64
 constexpr uint32_t kIdescTT = make_idesc(0, 0, 1, 1, 128, 64);     // A MN-major, B MN-major, N=64
 

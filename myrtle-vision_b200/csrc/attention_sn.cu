@@ -618,7 +618,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int trace_n = 0;
+    [[maybe_unused]] int trace_n = 0;
     const int n_bh = p.B * p.H;
     const int n_local = blockIdx.x < n_bh ? (n_bh - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int nblk = p.n_reg + (p.tail_w > 0 ? 1 : 0);           // blocks per pass
@@ -843,7 +843,6 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             named_bar_sync(1, 256);
             for (int j = 0; j < p.n_pass; j++) {
                 const int pc = pc0 + j, st = pc & 1;
-                const int key = j * 128 + lr;
                 const bool warp_live = j * 128 + quad * 32 < p.N;      // some key of this warp exists
                 for (int c = 0; c < nblk; c++) {
                     const int gb = gb0 + j * nblk + c;

@@ -24,6 +24,12 @@ constexpr int kLnWarps = 8;
 constexpr int kLnMaxVec = 8;     // float4 per lane: D <= 32*4*8 = 1024
 
 __device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+// two fp32 -> packed fp16x2, round-to-nearest, clipped to +-65504 in the conversion itself
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -256,9 +262,8 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
                 acc[2 * nvec + c] = ps;
                 __stcs(reinterpret_cast<float4*>(dxr) + c, o);
                 if (dx_lp != nullptr) {
-                    __half2 lo = __floats2half2_rn(sat16(o.x), sat16(o.y)), hi = __floats2half2_rn(sat16(o.z), sat16(o.w));
                     __stcs(reinterpret_cast<uint2*>(dx_lp + int64_t(row) * ld_lp) + c,
-                           make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi)));
+                           make_uint2(pack_h2_sat(o.x, o.y), pack_h2_sat(o.z, o.w)));
                 }
             }
         }
