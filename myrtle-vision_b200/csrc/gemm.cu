@@ -839,9 +839,15 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     p.kb_total = (a->K + BK - 1) / BK;
     int splits = 1;
     if (a->accumulate) {
-        splits = (kNumSMs / 2) / (p.m_tiles * p.n_tiles);
-        if (splits < 1) splits = 1;
-        if (splits > p.kb_total) splits = p.kb_total;
+        // split K so that the work units fill whole rounds of the 74 clusters: the split count (at most two
+        // rounds' worth) with the best units / (rounds * clusters); ties go to fewer splits (fewer red.adds)
+        const int tiles = p.m_tiles * p.n_tiles, clusters = kNumSMs / 2;
+        double best = -1.0;
+        for (int sp = 1; sp <= p.kb_total && sp * tiles <= 2 * clusters; sp++) {
+            const int units = sp * tiles;
+            const double eff = double(units) / double(((units + clusters - 1) / clusters) * clusters);
+            if (eff > best + 1e-9) { best = eff; splits = sp; }
+        }
     }
     p.kb_per_split = (p.kb_total + splits - 1) / splits;
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
