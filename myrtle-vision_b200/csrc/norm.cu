@@ -210,6 +210,7 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
         const int nrow = row + rstride;
         if (nrow < rows) load_row(nrow, nxt);
         const float mean = mean_in[row], rstd = rstd_in[row];
+        const float nmr = -mean * rstd;
         float4 xh[NV], gy[NV];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -225,8 +226,8 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
                     xv.x = fq_apply(xv.x, mi, q_in); xv.y = fq_apply(xv.y, mi, q_in);
                     xv.z = fq_apply(xv.z, mi, q_in); xv.w = fq_apply(xv.w, mi, q_in);
                 }
-                xv.x = (xv.x - mean) * rstd; xv.y = (xv.y - mean) * rstd;
-                xv.z = (xv.z - mean) * rstd; xv.w = (xv.w - mean) * rstd;
+                xv.x = fmaf(xv.x, rstd, nmr); xv.y = fmaf(xv.y, rstd, nmr);       // (x - mean) * rstd
+                xv.z = fmaf(xv.z, rstd, nmr); xv.w = fmaf(xv.w, rstd, nmr);
                 xh[i] = xv;
                 float4 a = acc[c];
                 a.x = fmaf(d.x, xv.x, a.x); a.y = fmaf(d.y, xv.y, a.y); a.z = fmaf(d.z, xv.z, a.z); a.w = fmaf(d.w, xv.w, a.w);
@@ -244,15 +245,16 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         }
-        const float m1 = s1 * inv_d, m2 = s2 * inv_d;
+        // dx = rstd * (gy - mean(gy) - xhat * mean(gy * xhat))  as two FMAs per value
+        const float cb = -rstd * (s2 * inv_d), cc = -rstd * (s1 * inv_d);
         float* dxr = dx + int64_t(row) * ld_dx;
 #pragma unroll
         for (int i = 0; i < NV; i++) {
             const int c = lane + 32 * i;
             if (c < nvec) {
                 float4 o;
-                o.x = rstd * (gy[i].x - m1 - xh[i].x * m2); o.y = rstd * (gy[i].y - m1 - xh[i].y * m2);
-                o.z = rstd * (gy[i].z - m1 - xh[i].z * m2); o.w = rstd * (gy[i].w - m1 - xh[i].w * m2);
+                o.x = fmaf(gy[i].x, rstd, fmaf(xh[i].x, cb, cc)); o.y = fmaf(gy[i].y, rstd, fmaf(xh[i].y, cb, cc));
+                o.z = fmaf(gy[i].z, rstd, fmaf(xh[i].z, cb, cc)); o.w = fmaf(gy[i].w, rstd, fmaf(xh[i].w, cb, cc));
                 if (dres != nullptr) {
                     const float4 r = cur.dres[i];
                     o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;

@@ -95,17 +95,17 @@ __device__ __forceinline__ bool fq_half4_all_normal(float a, float b, float c, f
     // all four at or above fp16's lowest normal binade (2^-14); zeros take the rare path
     return fminf(fminf(fabsf(a), fabsf(b)), fminf(fabsf(c), fabsf(d))) >= 6.103515625e-05f;
 }
-// fp32 results (the value feeds more fp32 math)
+__device__ __forceinline__ bool fq_half4_none_saturates(float a, float b, float c, float d) {
+    // |x| < 65520 rounds to at most 65504 (the half-ulp point of the top binade is 65520)
+    return fmaxf(fmaxf(fabsf(a), fabsf(b)), fmaxf(fabsf(c), fabsf(d))) < 65520.0f;
+}
+// fp32 results (the value feeds more fp32 math): one range test for the group, then add-and-mask per value
 __device__ __forceinline__ float4 fq_half4_f32(float4 v) {
-    if (fq_half4_all_normal(v.x, v.y, v.z, v.w)) {
-        uint32_t q[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t t = q[j];
-            q[j] = (t + 0x1000u) & 0xFFFFE000u;
-            if ((q[j] & 0x7FFFFFFFu) > 0x477FE000u) q[j] = (t & 0x80000000u) | 0x477FE000u;
-        }
-        return make_float4(__uint_as_float(q[0]), __uint_as_float(q[1]), __uint_as_float(q[2]), __uint_as_float(q[3]));
+    if (fq_half4_all_normal(v.x, v.y, v.z, v.w) && fq_half4_none_saturates(v.x, v.y, v.z, v.w)) {
+        return make_float4(__uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u),
+                           __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u),
+                           __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u),
+                           __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u));
     }
     return fq_half4_rare(v.x, v.y, v.z, v.w);
 }
