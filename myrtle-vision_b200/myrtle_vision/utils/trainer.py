@@ -83,14 +83,25 @@ def to_device(targets, device):
 
 @torch.no_grad()
 def validation(task, loader, device, criterion, vit):
+    """-> (mean loss, metric): accuracy (classification), mIoU (segmentation, reference
+    segmentation/train.py:35-71), 0 for detection (COCO evaluation is outside the hot path)."""
     vit.eval()
     total, metric, n = 0.0, 0.0, max(1, len(loader))
+    miou = None
+    if task == "segmentation":
+        from myrtle_vision.utils.miou import MIoU
+        miou = MIoU(vit.decoder.linear[1].out_features if isinstance(vit.decoder.linear, torch.nn.Sequential)
+                    else vit.decoder.linear.out_features, device)
     for imgs, targets in loader:
         imgs, targets = imgs.to(device), to_device(targets, device)
         out = vit(imgs)
         total += float(criterion(out, targets)) / n
-        if task != "detection":
+        if task == "classification":
             metric += float((out.argmax(dim=1) == targets).float().mean()) / n
+        elif miou is not None:
+            miou.add_img(out.argmax(dim=1), targets)
+    if miou is not None:
+        metric = miou.get_miou()
     vit.train()
     return total, metric
 

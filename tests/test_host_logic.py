@@ -187,3 +187,23 @@ def test_rename_timm_state_dict_loads_into_every_key_layout(fmt):
     assert pe.shape == (D, 3 * P * P) and torch.equal(pe[7, (3 * P + 5) * 3 + 2], w[7, 2, 3, 5])   # (O,(H,W,I))
     qkv_key = "transformer.layers.1.0.fn.fn.to_qkv%s.weight" % (".1" if fmt != "FP32" else "")
     assert torch.equal(m.state_dict()[qkv_key], timm_sd["blocks.1.attn.qkv.weight"])
+
+
+def test_miou_matches_the_histogram_definition():
+    """utils/miou.py: confusion-matrix mIoU equals the reference's histc formulation (restated inline)."""
+    from myrtle_vision.utils.miou import MIoU
+    g = torch.Generator().manual_seed(5)
+    C = 6
+    m = MIoU(C, "cpu")
+    ti, tu = torch.zeros(C, dtype=torch.float64), torch.zeros(C, dtype=torch.float64)
+    for _ in range(3):
+        pred = torch.randint(0, C, (2, 40, 40), generator=g)
+        lab = torch.randint(0, C, (2, 40, 40), generator=g)
+        m.add_img(pred, lab)
+        inter = torch.histc(pred[pred == lab].float(), bins=C, min=0, max=C - 1)
+        ap = torch.histc(pred.float(), bins=C, min=0, max=C - 1)
+        al = torch.histc(lab.float(), bins=C, min=0, max=C - 1)
+        ti += inter
+        tu += ap + al - inter
+    assert torch.allclose(m.get_per_class_iou(), ti / tu)
+    assert abs(m.get_miou() - float((ti / tu).mean())) < 1e-12
