@@ -96,6 +96,11 @@ def cpu_port_throughput(batch, steps, warmup, q_format):
     bwd on `batch` images per step, all host threads torch wants to use."""
     import torch
     from oracle import vit_oracle
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     torch.manual_seed(1234)
     P = vit_oracle.init_params(decoder="classification", num_classes=CLASSES, seed=1234, **ARCH)
     g = torch.Generator().manual_seed(1234)
