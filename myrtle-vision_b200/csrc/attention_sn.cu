@@ -856,35 +856,49 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     tc_fence_after();
                     if (warp_live) {
                         uint8_t* ds_row = sdS + ((j * p.n_reg + c) & 3) * kSnTile + lr * 128;
-                        for (int c0 = 0; c0 < width; c0 += 32) {
-                            if (c0 + 32 <= width) {
-                                uint32_t sv[32], dv[32], wp[16], wd[16];
-                                tmem_ld_32x32(tS + c0, sv);
-                                tmem_ld_32x32(tdP + c0, dv);
-                                tmem_ld_wait();
+                        // 16 columns (query rows) of S^T / dP^T -> P^T / dS^T (fp16, in place in TMEM; dS^T also to
+                        // shared memory for the dQ MMA).  The TMEM loads of the next 16 columns are issued before
+                        // the arithmetic of the current ones, so their latency hides behind it.
+                        auto math16 = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int c0) {
+                            uint32_t wp[8], wd[8];
 #pragma unroll
-                                for (int q4 = 0; q4 < 8; q4++) {
-                                    const float4 L4 = *reinterpret_cast<const float4*>(sL + row0 + c0 + 4 * q4);
-                                    const float4 D4 = *reinterpret_cast<const float4*>(sDelta + row0 + c0 + 4 * q4);
-                                    const float Ls[4] = {L4.x, L4.y, L4.z, L4.w}, Ds[4] = {D4.x, D4.y, D4.z, D4.w};
-                                    float pe[4], de[4];
+                            for (int q4 = 0; q4 < 4; q4++) {
+                                const float4 L4 = *reinterpret_cast<const float4*>(sL + row0 + c0 + 4 * q4);
+                                const float4 D4 = *reinterpret_cast<const float4*>(sDelta + row0 + c0 + 4 * q4);
+                                const float Ls[4] = {L4.x, L4.y, L4.z, L4.w}, Ds[4] = {D4.x, D4.y, D4.z, D4.w};
+                                float pe[4], de[4];
 #pragma unroll
-                                    for (int u = 0; u < 4; u++) {
-                                        pe[u] = ex2_fast(fmaf(__uint_as_float(sv[4 * q4 + u]), p.scale_log2, -Ls[u]));
-                                        de[u] = pe[u] * (__uint_as_float(dv[4 * q4 + u]) - Ds[u]) * p.scale;
-                                    }
-                                    wp[2 * q4] = pack_h2_rn(pe[0], pe[1]); wp[2 * q4 + 1] = pack_h2_rn(pe[2], pe[3]);
-                                    wd[2 * q4] = pack_h2_satf(de[0], de[1]); wd[2 * q4 + 1] = pack_h2_satf(de[2], de[3]);
+                                for (int u = 0; u < 4; u++) {
+                                    pe[u] = ex2_fast(fmaf(__uint_as_float(sv[4 * q4 + u]), p.scale_log2, -Ls[u]));
+                                    de[u] = pe[u] * (__uint_as_float(dv[4 * q4 + u]) - Ds[u]) * p.scale;
                                 }
-                                tmem_st_32x16(tS + (c0 >> 1), wp);
-                                tmem_st_32x16(tdP + (c0 >> 1), wd);
-                                if (regular) {
+                                wp[2 * q4] = pack_h2_rn(pe[0], pe[1]); wp[2 * q4 + 1] = pack_h2_rn(pe[2], pe[3]);
+                                wd[2 * q4] = pack_h2_satf(de[0], de[1]); wd[2 * q4 + 1] = pack_h2_satf(de[2], de[3]);
+                            }
+                            tmem_st_32x8(tS + (c0 >> 1), wp);
+                            tmem_st_32x8(tdP + (c0 >> 1), wd);
 #pragma unroll
-                                    for (int t = 0; t < 4; t++)
-                                        *reinterpret_cast<uint4*>(ds_row + ((((c0 >> 3) + t) ^ (lr & 7)) << 4)) =
-                                            make_uint4(wd[4 * t], wd[4 * t + 1], wd[4 * t + 2], wd[4 * t + 3]);
-                                }
-                            } else {
+                            for (int t = 0; t < 2; t++)
+                                *reinterpret_cast<uint4*>(ds_row + ((((c0 >> 3) + t) ^ (lr & 7)) << 4)) =
+                                    make_uint4(wd[4 * t], wd[4 * t + 1], wd[4 * t + 2], wd[4 * t + 3]);
+                        };
+                        if (regular) {
+                            uint32_t sA[16], dA[16], sB[16], dB[16];
+                            tmem_ld_32x16(tS, sA); tmem_ld_32x16(tdP, dA);
+                            tmem_ld_wait();
+                            tmem_ld_32x16(tS + 16, sB); tmem_ld_32x16(tdP + 16, dB);
+                            math16(sA, dA, 0);
+                            tmem_ld_wait();
+                            tmem_ld_32x16(tS + 32, sA); tmem_ld_32x16(tdP + 32, dA);
+                            math16(sB, dB, 16);
+                            tmem_ld_wait();
+                            tmem_ld_32x16(tS + 48, sB); tmem_ld_32x16(tdP + 48, dB);
+                            math16(sA, dA, 32);
+                            tmem_ld_wait();
+                            math16(sB, dB, 48);
+                        }
+                        for (int c0 = 0; c0 < (regular ? 0 : width); c0 += 16) {
+                            {
                                 // 16-wide tail block: rows 256 .. 271
                                 uint32_t sv[16], dv[16], wp[8], wd[8];
                                 tmem_ld_32x16(tS + c0, sv);
