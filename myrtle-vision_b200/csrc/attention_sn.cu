@@ -27,6 +27,7 @@ constexpr int kSnMaxKeys = 272;                 // padded keys (multiple of 16) 
 constexpr int kSnTailMax = 2;                   // tail query rows (N mod 128) handled by the SIMT warp
 constexpr int kSnKVBytes = kSnMaxKeys * 128;    // one K or V stage: 272 rows x 128 B
 constexpr int kSnTile = 16384;                  // 128 rows x 128 B
+constexpr int kSnStgPitch = 80;                 // bytes per staged row (64 B + pad: conflict-free 16 B stores)
 constexpr int kSnExtraMax = 2;                  // keys beyond the last multiple of 16 folded in on the CUDA cores
 constexpr int kSnMathWarps = 8;                 // two groups of four: one thread per query row
 constexpr int kSnTailWarps = 2;
@@ -51,7 +52,52 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
                  : "memory");
 }
 
+// Debug timeline (tools/trace_attn_bwd.py): when a trace buffer is registered, CTA 0 stamps clock64() at
+// the hand-offs between the MMA issuer and the math groups.  Record = {event, index, clock}.
+static unsigned long long* g_sn_trace = nullptr;
+extern "C" int mv_debug_set_attn_trace(void* dev_buf) { g_sn_trace = static_cast<unsigned long long*>(dev_buf); return 0; }
+#ifndef MV_SN_TRACE
+#define SN_TRACE(cond, region, ev, idx) do { } while (0)
+#else
+#define SN_TRACE(cond, region, ev, idx)                                                        \
+    do {                                                                                       \
+        if (p.trace != nullptr && blockIdx.x == 0 && (cond)) {                                 \
+            unsigned long long* t_ = p.trace + (region) * 3072 + 3 * (trace_n++ % 1024);       \
+            t_[0] = (ev); t_[1] = (unsigned long long)(idx); t_[2] = clock64();                \
+        }                                                                                      \
+    } while (0)
+#endif
+
+// Accumulator rows leave TMEM one row per thread; written like that, every 16-byte store instruction of a
+// warp touches 32 different lines and the LSU serialises them (3000+ cycles per epilogue, measured with
+// the clock64 timeline).  Each warp parks half a row per lane (32 fp16) in its private staging tile and
+// writes it back with four lanes per row: 8 rows x 64 contiguous bytes per store instruction.
+// v0 / v1: columns 0..31 / 32..63 of this lane's row (fp32 bits).  dst0: row 0 of the warp's 32 rows.
+__device__ __forceinline__ void sn_store_rows(uint8_t* stg, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+                                              __half* dst0, int64_t ld, int nvalid, int lane) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t (&v)[32] = half == 0 ? v0 : v1;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            *reinterpret_cast<uint4*>(stg + lane * kSnStgPitch + i * 16) = make_uint4(
+                pack_h2_satf(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                pack_h2_satf(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                pack_h2_satf(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                pack_h2_satf(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int row = it * 8 + (lane >> 2), chunk = lane & 3;
+            const uint4 w = *reinterpret_cast<const uint4*>(stg + row * kSnStgPitch + chunk * 16);
+            if (row < nvalid) *reinterpret_cast<uint4*>(dst0 + row * ld + half * 32 + chunk * 8) = w;
+        }
+        __syncwarp();
+    }
+}
+
 struct SnFwdDev {
+    unsigned long long* trace;
     int B, H, N, D;
     int Nk;                     // keys multiplied on the tensor cores (multiple of 16, <= 256)
     int n_extra;                // keys [Nk, N) (at most kSnExtraMax) folded in by the math threads (SIMT)
@@ -170,7 +216,6 @@ __device__ __forceinline__ void sn_tail_row_fwd(const SnFwdDev& p, const uint8_t
     __syncwarp();
 }
 
-constexpr int kSnStgPitch = 80;                 // bytes per staged row (64 B + pad: conflict-free 16 B stores)
 // One TMEM lane = one output row per thread: stored directly, each 16-byte store instruction of a warp
 // touches 32 different lines and the LSU serialises them.  Each warp parks half a row per lane (32 fp16)
 // in its private staging tile and writes it back with four lanes per row — 8 rows x 64 contiguous bytes
@@ -186,6 +231,30 @@ __device__ __forceinline__ void sn_store_rows_f(uint8_t* stg, const float (&o)[6
                 pack_h2_satf(o[32 * half + 8 * i + 2], o[32 * half + 8 * i + 3]),
                 pack_h2_satf(o[32 * half + 8 * i + 4], o[32 * half + 8 * i + 5]),
                 pack_h2_satf(o[32 * half + 8 * i + 6], o[32 * half + 8 * i + 7]));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int row = it * 8 + (lane >> 2), chunk = lane & 3;
+            const uint4 w = *reinterpret_cast<const uint4*>(stg + row * kSnStgPitch + chunk * 16);
+            if (row < nvalid) *reinterpret_cast<uint4*>(dst0 + row * ld + half * 32 + chunk * 8) = w;
+        }
+        __syncwarp();
+    }
+}
+
+// Same store, with the softmax normalisation and the (5,10) output quantiser folded into the packing:
+// four values per range test, cvt.rz on the half-ulp-biased word (quant_dev.cuh: fq_half4_pack).
+__device__ __forceinline__ void sn_store_rows_q16(uint8_t* stg, const float (&o)[64], float inv, __half* dst0,
+                                                  int64_t ld, int nvalid, int lane) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float* v = &o[32 * half + 8 * i];
+            const uint2 lo = fq_half4_pack(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv);
+            const uint2 hi = fq_half4_pack(v[4] * inv, v[5] * inv, v[6] * inv, v[7] * inv);
+            *reinterpret_cast<uint4*>(stg + lane * kSnStgPitch + i * 16) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        }
         __syncwarp();
 #pragma unroll
         for (int it = 0; it < 4; it++) {
@@ -221,6 +290,7 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    [[maybe_unused]] int trace_n = 0;
     const int n_bh = p.B * p.H;
     const int n_local = blockIdx.x < n_bh ? (n_bh - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // pairs of this CTA
     const int total_tiles = n_local * p.n_tiles;
@@ -278,21 +348,29 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
             const uint32_t idesc_s = make_idesc(0, 0, 0, 0, 128, p.Nk);
             const uint32_t idesc_pv = make_idesc(0, 0, 0, 1, 128, 64);     // A (TMEM) K-major, B = V MN-major
             const int ksteps = p.Nk >> 4;
-            auto issue_s = [&](int g) {
-                const int n = g / p.n_tiles, t = g % p.n_tiles, s = n & 1, grp = g & 1;
+            // This lane sits between the two math groups on every tile: walk the schedule with counters (no
+            // divisions) and build every descriptor as a base plus a small offset.
+            const uint64_t dQ0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+            const uint64_t dK0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+            const uint64_t dV0 = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
+            constexpr uint64_t kQOff = kSnTile >> 4, kKVOff = kSnKVBytes >> 4;
+            int gs = 0, ns = 0, ts = 0;                                      // S schedule: tile, pair, tile in pair
+            auto issue_s = [&]() {
+                const int g = gs, n = ns, t = ts, s = n & 1, grp = g & 1;
                 const uint32_t tS = tmem_base + grp * 256;
                 if (g >= 2) mbar_wait(&o_empty[grp], ((g - 2) >> 1) & 1);   // O(g-2) (inside this region) has been read
                 if (t == 0) mbar_wait(&k_full[s], (n >> 1) & 1);
                 mbar_wait(&q_full[g & 1], (g >> 1) & 1);
                 tc_fence_after();
-                const uint32_t aQ = smem_u32(sQ + (g & 1) * kSnTile), aK = smem_u32(sK + s * kSnKVBytes);
+                const uint64_t dq = dQ0 + (g & 1) * kQOff, dk = dK0 + s * kKVOff;
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    umma_f16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024),
-                             make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k > 0);
+                for (int k = 0; k < 4; k++) umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
                 umma_commit(&s_full[grp]);
+                SN_TRACE(true, 0, 1, g);                                    // S MMAs issued
                 umma_commit(&q_empty[g & 1]);
                 if (t == p.n_tiles - 1) umma_commit(&k_empty[s]);
+                gs++;
+                if (++ts == p.n_tiles) { ts = 0; ns++; }
             };
             if (p.n_tiles == 0) {
                 for (int n = 0; n < n_local; n++) {
@@ -300,20 +378,29 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
                     mbar_wait(&v_full[n & 1], (n >> 1) & 1); mbar_arrive(&v_empty[n & 1]);
                 }
             } else {
-                if (total_tiles > 0) issue_s(0);
-                if (total_tiles > 1) issue_s(1);
+                if (total_tiles > 0) issue_s();
+                if (total_tiles > 1) issue_s();
+                int n = 0, t = 0;
                 for (int g = 0; g < total_tiles; g++) {
-                    const int n = g / p.n_tiles, t = g % p.n_tiles, s = n & 1, grp = g & 1;
+                    const int s = n & 1, grp = g & 1;
                     const uint32_t tP = tmem_base + grp * 256, tO = tP + 128;
                     if (t == 0) mbar_wait(&v_full[s], (n >> 1) & 1);
+                    SN_TRACE(true, 0, 2, g);
                     mbar_wait(&p_full[grp], (g >> 1) & 1);
+                    SN_TRACE(true, 0, 3, g);                                // softmax of tile g done (seen by issuer)
                     tc_fence_after();
-                    const uint32_t aV = smem_u32(sV + s * kSnKVBytes);
-                    for (int k = 0; k < ksteps; k++)
-                        umma_f16_ts(tO, tP + k * 8, make_smem_desc_sw128(aV + k * 2048, 8192, 1024), idesc_pv, k > 0);
+                    uint64_t dv = dV0 + s * kKVOff;
+                    uint32_t ta = tP;
+                    umma_f16_ts(tO, ta, dv, idesc_pv, 0u);
+                    for (int k = 1; k < ksteps; k++) {
+                        dv += 128; ta += 8;                                  // 16 keys further: 2048 B of V, 8 columns of P
+                        umma_f16_ts(tO, ta, dv, idesc_pv, 1u);
+                    }
                     umma_commit(&o_full[grp]);
+                    SN_TRACE(true, 0, 4, g);                                // PV MMAs issued
                     if (t == p.n_tiles - 1) umma_commit(&v_empty[s]);
-                    if (g + 2 < total_tiles) issue_s(g + 2);
+                    if (g + 2 < total_tiles) issue_s();
+                    if (++t == p.n_tiles) { t = 0; n++; }
                 }
             }
         }
@@ -343,7 +430,9 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
                 sx[e] = e < p.n_extra ? sn_dot64(sQ + (g & 1) * kSnTile, rl, cK, p.Nk + e) : -INFINITY;
             __syncwarp();
             if (lane == 0) { mbar_arrive(&q_empty[g & 1]); mbar_arrive(&k_empty[s]); }
+            SN_TRACE(quad == 0 && lane == 0, 1 + grp, 5, g);
             mbar_wait(&s_full[grp], (g >> 1) & 1);
+            SN_TRACE(quad == 0 && lane == 0, 1 + grp, 6, g);                 // S ready
             tc_fence_after();
             // pass 1: row max
             float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -374,6 +463,7 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
                 }
             }
             const float m = fmaxf(mx0, mx1) * p.scale_log2;
+            SN_TRACE(quad == 0 && lane == 0, 1 + grp, 12, g);                // max pass done
             // pass 2: P = exp2(s * c - m) -> fp16, written over the S columns already consumed
             float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll 1
@@ -424,10 +514,12 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[grp]);
+            SN_TRACE(quad == 0 && lane == 0, 1 + grp, 7, g);                 // P written
             const float l = sum0 + sum1;
             // O = P V (+ the extra keys' p * v)
             mbar_wait(&v_full[s], (n >> 1) & 1);
             mbar_wait(&o_full[grp], (g >> 1) & 1);
+            SN_TRACE(quad == 0 && lane == 0, 1 + grp, 9, g);                 // O ready
             tc_fence_after();
             float o[64];
             {
@@ -461,24 +553,30 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
                 const bool live = row < p.N;
                 const float inv = live ? 1.0f / l : 0.f;
                 const int64_t grow = int64_t(b) * p.N + row;
-                if (mode == 1) {
-#pragma unroll
-                    for (int i = 0; i < 64; i++) o[i] = fq_half_fast(o[i] * inv);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 64; i++) o[i] = fq_apply(o[i] * inv, mode, p.q_out);
-                }
-                if (p.out_dtype == MV_F16) {
-                    const int row0 = row - lane;                             // first row of this warp
+                const int row0 = row - lane;                                 // first row of this warp
+                if (p.out_dtype == MV_F16 && mode == 1) {
                     __half* dst0 = reinterpret_cast<__half*>(p.out) + (int64_t(b) * p.N + row0) * p.ld_out + h * 64;
-                    sn_store_rows_f(sStg + (warp - 2) * 32 * kSnStgPitch, o, dst0, p.ld_out, p.N - row0, lane);
-                } else if (live) {
-                    float* dst = reinterpret_cast<float*>(p.out) + grow * p.ld_out + h * 64;
+                    sn_store_rows_q16(sStg + (warp - 2) * 32 * kSnStgPitch, o, inv, dst0, p.ld_out, p.N - row0, lane);
+                } else {
+                    if (mode == 1) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++)
-                        reinterpret_cast<float4*>(dst)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                        for (int i = 0; i < 64; i++) o[i] = fq_half_fast(o[i] * inv);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 64; i++) o[i] = fq_apply(o[i] * inv, mode, p.q_out);
+                    }
+                    if (p.out_dtype == MV_F16) {
+                        __half* dst0 = reinterpret_cast<__half*>(p.out) + (int64_t(b) * p.N + row0) * p.ld_out + h * 64;
+                        sn_store_rows_f(sStg + (warp - 2) * 32 * kSnStgPitch, o, dst0, p.ld_out, p.N - row0, lane);
+                    } else if (live) {
+                        float* dst = reinterpret_cast<float*>(p.out) + grow * p.ld_out + h * 64;
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            reinterpret_cast<float4*>(dst)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    }
                 }
                 if (live && p.lse != nullptr) p.lse[(int64_t(b) * p.H + h) * p.N + row] = m + log2f(l);
+                SN_TRACE(quad == 0 && lane == 0, 1 + grp, 16, g);            // output rows stored
             }
         }
     } else {
@@ -531,50 +629,6 @@ constexpr int kSnOffStg = kSnOffVec + (2 * kSnMaxKeys + 16 * 64) * 4;   // 8 mat
 constexpr int kSnOffVec2 = kSnOffStg + 8 * 32 * kSnStgPitch;           // L / Delta of the next pair (double buffer)
 constexpr int kSnOffBar = kSnOffVec2 + 2 * kSnMaxKeys * 4;
 constexpr int kSnBwdSmem = kSnOffBar + 256 + 1024;
-
-// Debug timeline (tools/trace_attn_bwd.py): when a trace buffer is registered, CTA 0 stamps clock64() at
-// the hand-offs between the MMA issuer and the math groups.  Record = {event, index, clock}.
-static unsigned long long* g_sn_trace = nullptr;
-extern "C" int mv_debug_set_attn_trace(void* dev_buf) { g_sn_trace = static_cast<unsigned long long*>(dev_buf); return 0; }
-#ifndef MV_SN_TRACE
-#define SN_TRACE(cond, region, ev, idx) do { } while (0)
-#else
-#define SN_TRACE(cond, region, ev, idx)                                                        \
-    do {                                                                                       \
-        if (p.trace != nullptr && blockIdx.x == 0 && (cond)) {                                 \
-            unsigned long long* t_ = p.trace + (region) * 3072 + 3 * (trace_n++ % 1024);       \
-            t_[0] = (ev); t_[1] = (unsigned long long)(idx); t_[2] = clock64();                \
-        }                                                                                      \
-    } while (0)
-#endif
-
-// Accumulator rows leave TMEM one row per thread; written like that, every 16-byte store instruction of a
-// warp touches 32 different lines and the LSU serialises them (3000+ cycles per epilogue, measured with
-// the clock64 timeline).  Each warp parks half a row per lane (32 fp16) in its private staging tile and
-// writes it back with four lanes per row: 8 rows x 64 contiguous bytes per store instruction.
-// v0 / v1: columns 0..31 / 32..63 of this lane's row (fp32 bits).  dst0: row 0 of the warp's 32 rows.
-__device__ __forceinline__ void sn_store_rows(uint8_t* stg, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
-                                              __half* dst0, int64_t ld, int nvalid, int lane) {
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const uint32_t (&v)[32] = half == 0 ? v0 : v1;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            *reinterpret_cast<uint4*>(stg + lane * kSnStgPitch + i * 16) = make_uint4(
-                pack_h2_satf(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
-                pack_h2_satf(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
-                pack_h2_satf(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
-                pack_h2_satf(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int row = it * 8 + (lane >> 2), chunk = lane & 3;
-            const uint4 w = *reinterpret_cast<const uint4*>(stg + row * kSnStgPitch + chunk * 16);
-            if (row < nvalid) *reinterpret_cast<uint4*>(dst0 + row * ld + half * 32 + chunk * 8) = w;
-        }
-        __syncwarp();
-    }
-}
 
 struct SnBwdDev {
     unsigned long long* trace;
@@ -1043,6 +1097,7 @@ int mv_attention_fwd_sn(const void* qkv, void* out, int out_dtype, float* lse, i
     if (make_tmap_3d(&t128, qkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 128, 1)) return 1;
     if (make_tmap_3d(&t16, qkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 16, 1)) return 1;
     SnFwdDev p;
+    p.trace = g_sn_trace;
     p.B = B; p.H = H; p.N = N; p.D = D;
     sn_key_split(N, &p.Nk, &p.n_extra);
     p.Nld = p.Nk + (p.n_extra > 0 ? 16 : 0);

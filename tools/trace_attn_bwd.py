@@ -15,12 +15,12 @@ for _ in range(2):
     mv.attention_bwd(qkv, out, do, lse, B, H, N)
 buf = torch.zeros(3 * 3072, dtype=torch.int64, device="cuda")
 mv.lib().mv_debug_set_attn_trace(ctypes.c_void_p(buf.data_ptr()))
-mv.attention_bwd(qkv, out, do, lse, B, H, N)
+(mv.attention_fwd(qkv, B, H, N, q_out=(5, 10)) if "fwd" in sys.argv else mv.attention_bwd(qkv, out, do, lse, B, H, N))
 torch.cuda.synchronize()
 mv.lib().mv_debug_set_attn_trace(None)
 t = buf.cpu().view(3, 1024, 3)
 names = {1: "pre issued", 2: "issuer waits math", 3: "issuer sees math done", 4: "post issued", 5: "math waits S", 6: "S ready",
-         7: "math done", 16: "dq stored", 17: "bar after dq", 18: "pair finished", 19: "stats start", 12: "pre enter", 13: "pre fenced", 14: "pre 2 MMAs issued", 15: "pre 8 MMAs issued", 8: "waits acc", 9: "acc ready", 10: "dq ready", 11: "stats done"}
+         7: "math done", 12: "max pass done (fwd)", 16: "dq stored", 17: "bar after dq", 18: "pair finished", 19: "stats start", 12: "pre enter", 13: "pre fenced", 14: "pre 2 MMAs issued", 15: "pre 8 MMAs issued", 8: "waits acc", 9: "acc ready", 10: "dq ready", 11: "stats done"}
 ev = []
 for r in range(3):
     for e, i, c in t[r].tolist():
