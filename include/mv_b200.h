@@ -203,6 +203,14 @@ int mv_adamw_step(const mv_adamw_tensor* tensors_dev, int n_tensors, int total_c
 int mv_upsample_ce(const float* y, const int64_t* labels, float* dy, float* acc, int B, int C, int gh, int gw,
                    int H, int W, int64_t ignore_index, void* stream);
 
+/* ---------------------------------------------------------------- debug timelines
+ * Only active in a library built with -DMV_SN_TRACE / -DMV_GEMM_TRACE (MV_NVCC_FLAGS for csrc/build.py):
+ * CTA 0 of the short-sequence attention kernels / the CTA-pair GEMM writes {event, index, clock64} records
+ * into dev_buf (int64 [3][1024][3]) at the hand-offs between its MMA issuer and its math / epilogue warps
+ * (tools/trace_attn_bwd.py, tools/trace_gemm.py).  NULL switches recording off; no effect otherwise. */
+int mv_debug_set_attn_trace(void* dev_buf);
+int mv_debug_set_gemm_trace(void* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,7 +30,24 @@ template <int BN> struct GemmCfg {
     static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Debug timeline (tools/trace_gemm.py, library built with MV_NVCC_FLAGS=-DMV_GEMM_TRACE): CTA 0 stamps
+// clock64() at the hand-offs between the MMA issuer and two of its epilogue warps.  Record = {event, index, clock}.
+static unsigned long long* g_gemm_trace = nullptr;
+extern "C" int mv_debug_set_gemm_trace(void* dev_buf) { g_gemm_trace = static_cast<unsigned long long*>(dev_buf); return 0; }
+#ifndef MV_GEMM_TRACE
+#define GEMM_TRACE(cond, region, ev, idx) do { } while (0)
+#else
+#define GEMM_TRACE(cond, region, ev, idx)                                                      \
+    do {                                                                                       \
+        if (p.trace != nullptr && blockIdx.x == 0 && (cond)) {                                 \
+            unsigned long long* t_ = p.trace + (region) * 3072 + 3 * (trace_n++ % 1024);       \
+            t_[0] = (ev); t_[1] = (unsigned long long)(idx); t_[2] = clock64();                \
+        }                                                                                      \
+    } while (0)
+#endif
+
 struct GemmDev {
+    unsigned long long* trace;
     int M, N, K;
     int m_tiles, n_tiles, splits, kb_total, kb_per_split;
     int a_major, b_major;
@@ -661,6 +678,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int rank = int(cluster_ctarank());
+    [[maybe_unused]] int trace_n = 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -726,11 +744,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 const int split = u % p.splits;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                GEMM_TRACE(true, 0, 1, u);                     // issuer: waits for a free accumulator
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                GEMM_TRACE(true, 0, 2, u);                     // accumulator free
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (kb == kb0) GEMM_TRACE(true, 0, 3, u);  // first operand stage landed
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
                     const uint32_t sb = sa + kATileBytes;
@@ -744,6 +765,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit_cg2(&tmem_full[acc], 3);           // both CTAs' epilogues may read accumulator acc
+                GEMM_TRACE(true, 0, 4, u);                     // all MMAs of the tile issued
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -761,7 +783,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const int tile = u / p.splits;
             const int mrow0 = (tile / p.n_tiles) * 256 + rank * 128 + quad * 32;
             const int n0 = (tile % p.n_tiles) * BN;
+            GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 5, u);    // epilogue warp waits for the tile
             mbar_wait(&tmem_full[acc], acc_phase);
+            GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 6, u);    // accumulator complete
             tc_fence_after();
 #pragma unroll 1
             for (int c = cg; c < BN / 32; c += kEpi2Warps / 4) {
@@ -785,6 +809,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     default: epi_chunk<MV_F32, MV_EPI_NONE, 2, 1, 1, false>(p, w, taddr, release, mrow0, nc0); break;
                 }
             }
+            GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 7, u);    // this warp's chunks done
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -833,6 +858,7 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     else                 { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->K, a->N, a->ldb, BK, 64)) return 1; }
 
     GemmDev p;
+    p.trace = g_gemm_trace;
     p.M = a->M; p.N = a->N; p.K = a->K;
     p.m_tiles = (a->M + 255) / 256;
     p.n_tiles = (a->N + BN - 1) / BN;
@@ -930,6 +956,7 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     else                 { if (make_tmap_2d(&tb, a->B, a->b_dtype, a->K, a->N, a->ldb, BK, 128 / esz)) return 1; }
 
     GemmDev p;
+    p.trace = nullptr;
     p.M = a->M; p.N = a->N; p.K = a->K;
     p.m_tiles = (a->M + BM - 1) / BM;
     p.n_tiles = (a->N + BN - 1) / BN;
