@@ -527,10 +527,23 @@ __device__ __forceinline__ void store_out4(void* base, int dtype, int64_t row, i
 
 // ---- epilogue of the CTA-pair kernel ----------------------------------------------------------
 struct EpiWarp {
+    unsigned long long* tr;     // debug timeline slot of this warp (MV_GEMM_TRACE), else unused
     float* stg;                 // this warp's 32 x kStgPitch fp32 staging tile
+    uint32_t stg_s;             // ... as a shared-space address
     int lane, lr, lc;           // row-contiguous layout: row = 4*it + lr, columns lc .. lc+3 of the chunk
     int mode_out, mode_res;
 };
+
+// explicit shared-space accesses: through the EpiWarp struct the compiler loses the address space and emits
+// generic LD / ST for the staging tile, which go down the global-memory path (long scoreboard)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // accumulator chunk (32 TMEM lanes x 32 columns): thread = row -> padded shared memory; optionally
 // release the accumulator buffer (arrive on the leader's tmem_empty barrier) right after the read
@@ -538,11 +551,11 @@ __device__ __forceinline__ void stage_chunk(const EpiWarp& w, uint32_t taddr, ui
     uint32_t r[32];
     tmem_ld_32x32(taddr, r);
     tmem_ld_wait();
-    float4* srow = reinterpret_cast<float4*>(w.stg + w.lane * kStgPitch);
+    const uint32_t srow = w.stg_s + w.lane * (kStgPitch * 4);
 #pragma unroll
     for (int j = 0; j < 8; j++)
-        srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        sts128(srow + 16 * j, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
     if (release != 0u) {
         tc_fence_before();
         __syncwarp();
@@ -576,12 +589,18 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
     }
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!kAcc && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#ifdef MV_GEMM_TRACE
+    if (w.tr != nullptr && w.lane == 0) { w.tr[0] = 20; w.tr[1] = nc0; w.tr[2] = clock64(); }
+#endif
     stage_chunk(w, taddr, release);
-    const float* sp = w.stg + w.lr * kStgPitch + w.lc;
+#ifdef MV_GEMM_TRACE
+    if (w.tr != nullptr && w.lane == 0) { w.tr[3] = 21; w.tr[4] = nc0; w.tr[5] = clock64(); }
+#endif
+    const uint32_t sp = w.stg_s + (w.lr * kStgPitch + w.lc) * 4;
 #pragma unroll
     for (int it = 0; it < 8; it++) {
         const int m = m_first + it * 4;
-        const float4 a4 = *reinterpret_cast<const float4*>(sp + it * 4 * kStgPitch);
+        const float4 a4 = lds128(sp + it * 4 * kStgPitch * 4);
         float v[4] = {a4.x, a4.y, a4.z, a4.w};
         if (kAcc) {
             red_add_v4(reinterpret_cast<float*>(p.out) + int64_t(m) * p.ld_out + n, v[0], v[1], v[2], v[3]);
@@ -607,6 +626,9 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
         else
             *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + int64_t(m) * p.ld_out + n) = pack4_f16_sat(v);
     }
+#ifdef MV_GEMM_TRACE
+    if (w.tr != nullptr && w.lane == 0) { w.tr[6] = 22; w.tr[7] = nc0; w.tr[8] = clock64(); }
+#endif
     __syncwarp();                                      // staging is rewritten by the next chunk
 }
 
@@ -775,7 +797,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int cg = (warp - 2) >> 2;                        // chunks cg, cg+4, ... of the tile's 32-column chunks
         EpiWarp w;
         w.stg = staging + (warp - 2) * (32 * kStgPitch);
+        w.stg_s = smem_u32(w.stg);
         w.lane = lane; w.lr = lane >> 3; w.lc = (lane & 7) * 4;
+        w.tr = nullptr;
         w.mode_out = fq_mode(p.q_out); w.mode_res = fq_mode(p.q_res);
         const uint32_t lead_empty0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
         int acc = 0; uint32_t acc_phase = 0;
@@ -794,6 +818,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 const uint32_t release = (c + kEpi2Warps / 4 >= BN / 32) ? lead_empty0 + acc * 8 : 0u;
                 const int nc0 = n0 + c * 32;
                 const bool fast = p.variant != 0 && mrow0 + 32 <= p.M && nc0 + 32 <= p.N;
+#ifdef MV_GEMM_TRACE
+                if (p.trace != nullptr && blockIdx.x == 0 && warp == 2) { w.tr = p.trace + 3072 + 3 * (trace_n % 1021); trace_n += 3; }
+#endif
                 if (!fast) { epi_chunk_generic(p, w, taddr, release, mrow0, nc0); continue; }
                 switch (p.variant) {
                     //                 out     epilogue      res qo qr acc

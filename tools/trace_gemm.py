@@ -24,7 +24,7 @@ mv.lib().mv_debug_set_gemm_trace(ctypes.c_void_p(buf.data_ptr()))
 run(); torch.cuda.synchronize()
 mv.lib().mv_debug_set_gemm_trace(None)
 names = {1: "issuer waits accumulator", 2: "accumulator free", 3: "first stage landed", 4: "tile MMAs issued",
-         5: "epi waits tile", 6: "tile complete", 7: "epi chunks done"}
+         5: "epi waits tile", 6: "tile complete", 7: "epi chunks done", 20: "chunk: loads issued", 21: "chunk: staged", 22: "chunk: rows stored"}
 ev = sorted((c, r, e, i) for r in range(3) for e, i, c in buf.cpu().view(3, 1024, 3)[r].tolist() if e)
 t0 = ev[0][0]
 for c, r, e, i in ev[:150]:
