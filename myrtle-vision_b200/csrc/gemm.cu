@@ -803,42 +803,58 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         w.mode_out = fq_mode(p.q_out); w.mode_res = fq_mode(p.q_res);
         const uint32_t lead_empty0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int u = unit0; u < total_units; u += unit_stride) {
-            const int tile = u / p.splits;
-            const int mrow0 = (tile / p.n_tiles) * 256 + rank * 128 + quad * 32;
-            const int n0 = (tile % p.n_tiles) * BN;
-            GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 5, u);    // epilogue warp waits for the tile
-            mbar_wait(&tmem_full[acc], acc_phase);
-            GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 6, u);    // accumulator complete
-            tc_fence_after();
+        // The epilogue variant is chosen ONCE, outside the tile / chunk loops (a per-chunk switch costs an
+        // indirect branch and an instruction-cache excursion on every chunk): `walk` is the loop nest, `chunk`
+        // the compile-time epilogue of a chunk that lies inside [M, N].
+        auto walk = [&](auto chunk) {
+            for (int u = unit0; u < total_units; u += unit_stride) {
+                const int tile = u / p.splits;
+                const int mrow0 = (tile / p.n_tiles) * 256 + rank * 128 + quad * 32;
+                const int n0 = (tile % p.n_tiles) * BN;
+                GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 5, u);    // epilogue warp waits for the tile
+                mbar_wait(&tmem_full[acc], acc_phase);
+                GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 6, u);    // accumulator complete
+                tc_fence_after();
 #pragma unroll 1
-            for (int c = cg; c < BN / 32; c += kEpi2Warps / 4) {
-                const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32;
-                // last TMEM read of this tile by this warp: hand the accumulator back to the MMA issuer
-                const uint32_t release = (c + kEpi2Warps / 4 >= BN / 32) ? lead_empty0 + acc * 8 : 0u;
-                const int nc0 = n0 + c * 32;
-                const bool fast = p.variant != 0 && mrow0 + 32 <= p.M && nc0 + 32 <= p.N;
+                for (int c = cg; c < BN / 32; c += kEpi2Warps / 4) {
+                    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32;
+                    // last TMEM read of this tile by this warp: hand the accumulator back to the MMA issuer
+                    const uint32_t release = (c + kEpi2Warps / 4 >= BN / 32) ? lead_empty0 + acc * 8 : 0u;
+                    const int nc0 = n0 + c * 32;
+                    const bool fast = p.variant != 0 && mrow0 + 32 <= p.M && nc0 + 32 <= p.N;
 #ifdef MV_GEMM_TRACE
-                if (p.trace != nullptr && blockIdx.x == 0 && warp == 2) { w.tr = p.trace + 3072 + 3 * (trace_n % 1021); trace_n += 3; }
+                    if (p.trace != nullptr && blockIdx.x == 0 && warp == 2) { w.tr = p.trace + 3072 + 3 * (trace_n % 1021); trace_n += 3; }
 #endif
-                if (!fast) { epi_chunk_generic(p, w, taddr, release, mrow0, nc0); continue; }
-                switch (p.variant) {
-                    //                 out     epilogue      res qo qr acc
-                    case 1: epi_chunk<MV_F16, MV_EPI_NONE, 0, 0, 0, false>(p, w, taddr, release, mrow0, nc0); break;
-                    case 2: epi_chunk<MV_F16, MV_EPI_NONE, 0, 1, 0, false>(p, w, taddr, release, mrow0, nc0); break;
-                    case 3: epi_chunk<MV_F32, MV_EPI_NONE, 1, 0, 0, false>(p, w, taddr, release, mrow0, nc0); break;
-                    case 4: epi_chunk<MV_F32, MV_EPI_NONE, 1, 1, 1, false>(p, w, taddr, release, mrow0, nc0); break;
-                    case 5: epi_chunk<MV_F16, MV_EPI_GELU, 0, 0, 1, false>(p, w, taddr, release, mrow0, nc0); break;
-                    case 6: epi_chunk<MV_F16, MV_EPI_DGELU, 0, 0, 0, false>(p, w, taddr, release, mrow0, nc0); break;
-                    case 7: epi_chunk<MV_F32, MV_EPI_NONE, 2, 0, 0, false>(p, w, taddr, release, mrow0, nc0); break;
-                    case 8: epi_chunk<MV_F32, MV_EPI_NONE, 0, 0, 0, true>(p, w, taddr, release, mrow0, nc0); break;
-                    case 9: epi_chunk<MV_F16, MV_EPI_GELU, 0, 1, 1, false>(p, w, taddr, release, mrow0, nc0); break;
-                    default: epi_chunk<MV_F32, MV_EPI_NONE, 2, 1, 1, false>(p, w, taddr, release, mrow0, nc0); break;
+                    if (fast) chunk(taddr, release, mrow0, nc0);
+                    else epi_chunk_generic(p, w, taddr, release, mrow0, nc0);
                 }
+                GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 7, u);    // this warp's chunks done
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 7, u);    // this warp's chunks done
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        };
+#define MV_EPI_CASE(id, ...)                                                                                   \
+    case id:                                                                                                   \
+        walk([&](uint32_t taddr, uint32_t release, int mrow0, int nc0) {                                       \
+            epi_chunk<__VA_ARGS__>(p, w, taddr, release, mrow0, nc0);                                          \
+        });                                                                                                    \
+        break;
+        switch (p.variant) {
+            //              out     epilogue      res qo qr acc
+            MV_EPI_CASE(1, MV_F16, MV_EPI_NONE, 0, 0, 0, false)
+            MV_EPI_CASE(2, MV_F16, MV_EPI_NONE, 0, 1, 0, false)
+            MV_EPI_CASE(3, MV_F32, MV_EPI_NONE, 1, 0, 0, false)
+            MV_EPI_CASE(4, MV_F32, MV_EPI_NONE, 1, 1, 1, false)
+            MV_EPI_CASE(5, MV_F16, MV_EPI_GELU, 0, 0, 1, false)
+            MV_EPI_CASE(6, MV_F16, MV_EPI_DGELU, 0, 0, 0, false)
+            MV_EPI_CASE(7, MV_F32, MV_EPI_NONE, 2, 0, 0, false)
+            MV_EPI_CASE(8, MV_F32, MV_EPI_NONE, 0, 0, 0, true)
+            MV_EPI_CASE(9, MV_F16, MV_EPI_GELU, 0, 1, 1, false)
+            MV_EPI_CASE(10, MV_F32, MV_EPI_NONE, 2, 1, 1, false)
+            default:       // variant 0: every chunk takes the generic path (`fast` is false)
+                walk([&](uint32_t, uint32_t, int, int) {});
+                break;
         }
+#undef MV_EPI_CASE
     }
     tc_fence_before();
     __syncthreads();
