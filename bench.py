@@ -283,7 +283,7 @@ def run_b200(args):
             "attn_fwd": ("tensor", 4.0 * B * H * n_tok * n_tok * 64),
             "attn_bwd": ("tensor", 10.0 * B * H * n_tok * n_tok * 64),
             "ln_fwd": ("hbm", M * D * 6.0),
-            "ln_bwd": ("hbm", M * D * 18.0),
+            "ln_bwd": ("hbm", M * D * 16.0),      # x 4 + dy 2 (fp16) + dres 4 read, dx 4 + fp16 copy 2 written
         }
         return table.get(name, (None, None))
 

@@ -69,7 +69,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdDev p
     // 80 KB of shared memory and 256 TMEM columns per CTA: two CTAs share an SM, so one CTA's
     // softmax (CUDA cores) overlaps the other's MMAs and TMA loads.
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; offset arithmetic keeps the shared address space
     uint8_t* sQ = smem;
     uint8_t* sK = smem + kTile;
     uint8_t* sV = smem + 2 * kTile;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kAttThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const AttnBwdDev p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; offset arithmetic keeps the shared address space
     uint8_t* sR0 = smem;                       // resident: K_j (KV) | Q_i (Q)
     uint8_t* sR1 = smem + kTile;               // resident: V_j (KV) | dO_i (Q)
     uint8_t* sRing = smem + 2 * kTile;         // [2 stages][X, Y]: (Q_i, dO_i) (KV) | (K_j, V_j) (Q)
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(kAttThreads, 2)
 attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv64,
                   const __grid_constant__ CUtensorMap tmap_do, const AttnBwdDev p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; offset arithmetic keeps the shared address space
     // order matters: the MN-major M=128 A descriptors of P / dS step one tile (LBO) past their own
     // 64-key tile for the unused upper 64 rows; that neighbour must hold finite data (dS, then Q)
     uint8_t* sP = smem;                        // [128 q][64 keys] fp16

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kSnFwdThreads, 1)
 attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant__ CUtensorMap tmap16,
                    const __grid_constant__ SnFwdDev p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; offset arithmetic keeps the shared address space
     uint8_t* sK = smem;                                   // [2 stages][272 x 128 B]
     uint8_t* sV = smem + 2 * kSnKVBytes;
     uint8_t* sQ = smem + 4 * kSnKVBytes;                  // ring of 2 query tiles
@@ -648,7 +648,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                    const __grid_constant__ CUtensorMap tm_do128, const __grid_constant__ CUtensorMap tm_do16,
                    const __grid_constant__ SnBwdDev p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; offset arithmetic keeps the shared address space
     uint8_t* sK = smem;                                   // [2 stages][128 x 128 B]
     uint8_t* sV = smem + 2 * kSnTile;
     uint8_t* sQ = smem + kSnOffQ;                         // rows 0..271

@@ -214,7 +214,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr int kMnBoxBytes = BK * 128;      // one MN-major TMA box: BK k-rows of 128 bytes
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; offset arithmetic keeps the shared address space
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
@@ -689,7 +689,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     constexpr int BNH = BN / 2;                // B rows staged by each CTA
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; offset arithmetic keeps the shared address space
     float* staging = reinterpret_cast<float*>(smem + kStages * kStageBytes);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + Cfg::kStagingBytes);
     uint64_t* empty_bar = full_bar + kStages;

@@ -163,7 +163,7 @@ __device__ __forceinline__ float4 unpack_dy(const uint2& u) {
 }
 
 template <int NV, typename DyT>
-__global__ void __launch_bounds__(kLnWarps * 32, 3)
+__global__ void __launch_bounds__(kLnWarps * 32, 2)
 ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x, int64_t ld_x,
               const float* __restrict__ dres, int64_t ld_dres, const float* __restrict__ gamma,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
@@ -455,7 +455,7 @@ static int launch_ln_bwd(const void* dy, int dy_dtype, int64_t ld_dy, const floa
                          float* dx, int64_t ld_dx, void* dx_lp, int64_t ld_lp, float* dgamma, float* dbeta,
                          float* dbias_prev, int rows, int D, FloatFmt q_in, cudaStream_t st) {
     int grid = (rows + kLnWarps - 1) / kLnWarps;
-    const int cap = kNumSMs * 3;
+    const int cap = kNumSMs * 2;
     if (grid > cap) grid = cap;
     const size_t smem = size_t(kLnWarps) * 3 * D * sizeof(float);
     static bool attr_done = false;
