@@ -479,14 +479,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // 32 x 32 fp32 chunk TMEM -> registers -> padded shared memory and then works in a row-contiguous
 // layout (8 lanes x 16 B per row, 4 rows per instruction): every bias / residual / aux load and
 // every store covers whole 32-byte sectors of consecutive addresses.
-constexpr int kEpi2Warps = 16;
-constexpr int kGemm2Threads = 64 + 32 * kEpi2Warps;
+// Epilogue warps per CTA, a launch-time choice between two instantiations.  18 warps (16 + producer + issuer)
+// put five warps on one scheduler's 16 K registers, which caps every thread at 96 registers and makes the
+// epilogues with residual / aux prefetch spill; 14 warps (12 + 2) allow 128.  The elementwise-heavy GELU /
+// gelu' epilogues (N = 1536 outputs) are bound by issue slots and latency and run faster on 16 warps; every
+// other epilogue runs faster on 12 spill-free ones (measured per shape, gpurun_out/probe_gemm2*.log).
 constexpr int kStgPitch = 36;                                  // floats per staged row: 32 + 4 pad
 constexpr int kStgBytesPerWarp = 32 * kStgPitch * 4;           // 4608
-template <int BN> struct Gemm2Cfg {
+template <int BN, int EW> struct Gemm2Cfg {
+    static constexpr int kThreads = 64 + 32 * EW;
     static constexpr int kBHalfBytes = (BN / 2) * 128;
     static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
-    static constexpr int kStagingBytes = kEpi2Warps * kStgBytesPerWarp;
+    static constexpr int kStagingBytes = EW * kStgBytesPerWarp;
     static constexpr int kStages = (232448 - kStagingBytes - 1024 - 256) / kStageBytes;
     static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + 256;
     static constexpr int kTmemCols = 2 * BN <= 256 ? 256 : 512;
@@ -677,11 +681,12 @@ __device__ __forceinline__ void epi_chunk_generic(const GemmDev& p, const EpiWar
     __syncwarp();
 }
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
+template <int BN, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ GemmDev p) {
-    using Cfg = Gemm2Cfg<BN>;
+    using Cfg = Gemm2Cfg<BN, EW>;
+    constexpr int kEpi2Warps = EW;
     constexpr int kStages = Cfg::kStages;
     constexpr int kStageBytes = Cfg::kStageBytes;
     constexpr int BK = 64, UMMA_K = 16;
@@ -865,14 +870,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
 }
 
-template <int BN>
+template <int BN, int EW>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
+    using Cfg = Gemm2Cfg<BN, EW>;
     static bool attr_done = false;
     if (!attr_done) {
-        MV_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::kSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
         attr_done = true;
     }
-    gemm2_kernel<BN><<<grid, kGemm2Threads, Gemm2Cfg<BN>::kSmem, st>>>(ta, tb, p);
+    gemm2_kernel<BN, EW><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, p);
     return 0;
 }
 
@@ -959,9 +965,10 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     const int grid = 2 * (units < kNumSMs / 2 ? units : kNumSMs / 2);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
-    if (BN == 256) rc = launch_gemm2<256>(ta, tb, p, grid, st);
-    else if (BN == 192) rc = launch_gemm2<192>(ta, tb, p, grid, st);
-    else rc = launch_gemm2<128>(ta, tb, p, grid, st);
+    const bool heavy = a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU;       // 16 epilogue warps
+    if (BN == 256) rc = heavy ? launch_gemm2<256, 16>(ta, tb, p, grid, st) : launch_gemm2<256, 12>(ta, tb, p, grid, st);
+    else if (BN == 192) rc = heavy ? launch_gemm2<192, 16>(ta, tb, p, grid, st) : launch_gemm2<192, 12>(ta, tb, p, grid, st);
+    else rc = heavy ? launch_gemm2<128, 16>(ta, tb, p, grid, st) : launch_gemm2<128, 12>(ta, tb, p, grid, st);
     if (rc) return rc;
     g_launches++;
     return check_cuda(cudaGetLastError(), "gemm2 launch");
