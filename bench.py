@@ -68,15 +68,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock and throttle reasons of the samples taken inside [t0, t1] (host times around the
+        timed region).  nvidia-smi needs a few hundred ms to deliver its first row, so the sampler is
+        started before the warm-up; if the timed region itself is shorter than the sampling period the
+        window is widened to the warm-up steps right before it (same load)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        rows = self.rows
+        if t0 is not None:
+            inside = [r for ts, r in rows if t0 <= ts <= t1 + 0.15]
+            if len(inside) < 2:
+                inside = [r for ts, r in rows if t0 - 1.0 <= ts <= t1 + 0.25]
+            rows = inside
+        else:
+            rows = [r for _, r in rows]
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
             except (ValueError, IndexError):
@@ -209,20 +221,22 @@ def run_b200(args):
         run_step = lambda img, y: gstep(img, y)
     else:
         run_step = step
-    for i in range(args.warmup):
-        run_step(*resident[i % 2])
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                     # before the warm-up: the first nvidia-smi row takes a while
+    for i in range(max(args.warmup, 25)):   # >= 0.5 s of the same load ahead of the timed region
+        run_step(*resident[i % 2])
     barrier()
+    t_wall0 = time.time()
     e0.record()
     for i in range(args.steps):
         run_step(*resident[i % 2])
     e1.record()
     barrier()
+    t_wall1 = time.time()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     launches = launches_per_step * args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
     # ---- timed region 2 (e2e): every step copies its batch from pinned host memory (prefetched one
     # step ahead on a copy stream) and reads the loss back to the host

@@ -12,6 +12,8 @@
 // or one 32x32 tile of a weight matrix (so the transposed operand is written coalesced through
 // shared memory).  Hyper-parameters that change between steps live in device memory: a captured
 // CUDA graph replays the same launch with new values.
+#include <type_traits>
+
 #include "common.cuh"
 #include "quant_dev.cuh"
 #include "../../include/mv_b200.h"
@@ -33,21 +35,6 @@ __device__ __forceinline__ float adamw_elem(float p, float g, float& m, float& v
     const float denom = sqrtf(v) * h.bc2_rsqrt + h.eps;
     p *= 1.f - lr * wd;
     return p - (lr / h.bc1) * (m / denom);
-}
-
-template <typename OutT>
-__device__ __forceinline__ void emit_tile(const mv_adamw_tensor& t, float (*tile)[33], int r0, int c0) {
-    OutT* wq = static_cast<OutT*>(t.wq);
-    OutT* wq_t = static_cast<OutT*>(t.wq_t);
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-        const int r = r0 + j, c = c0 + threadIdx.x;
-        if (r < t.rows && c < t.cols) wq[int64_t(r) * t.cols + c] = opt_cvt<OutT>(tile[j][threadIdx.x]);
-    }
-    if (wq_t == nullptr) return;
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-        const int c = c0 + j, r = r0 + threadIdx.x;
-        if (r < t.rows && c < t.cols) wq_t[int64_t(c) * t.rows + r] = opt_cvt<OutT>(tile[threadIdx.x][j]);
-    }
 }
 
 // hyper (device): [0] beta1 [1] beta2 [2] eps [3] step (float, >= 1) [4] inv_scale (gradient un-scale)
@@ -104,8 +91,21 @@ adamw_kernel(const mv_adamw_tensor* __restrict__ tensors, int n_tensors, int tot
                 tile[j][threadIdx.x] = p;
             }
             __syncthreads();
-            if (t.wq_dtype == MV_F16) emit_tile<__half>(t, tile, r0, c0);
-            else emit_tile<float>(t, tile, r0, c0);
+            // q(W) row-major and q(W)^T through the tile, both coalesced (inline: keeps `tile` in the shared space)
+            auto emit = [&](auto* wq, auto* wq_t) {
+                using OutT = typename std::remove_pointer<decltype(wq)>::type;
+                for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+                    const int r = r0 + j, c = c0 + threadIdx.x;
+                    if (r < t.rows && c < t.cols) wq[int64_t(r) * t.cols + c] = opt_cvt<OutT>(tile[j][threadIdx.x]);
+                }
+                if (wq_t == nullptr) return;
+                for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+                    const int c = c0 + j, r = r0 + threadIdx.x;
+                    if (r < t.rows && c < t.cols) wq_t[int64_t(c) * t.rows + r] = opt_cvt<OutT>(tile[threadIdx.x][j]);
+                }
+            };
+            if (t.wq_dtype == MV_F16) emit(static_cast<__half*>(t.wq), static_cast<__half*>(t.wq_t));
+            else emit(static_cast<float*>(t.wq), static_cast<float*>(t.wq_t));
         }
     }
 }
