@@ -51,3 +51,35 @@ def test_entry_point_trains(task, fmt, size, classes, tmp_path):
     from myrtle_vision.utils.trainer import train_deit
     more = train_deit(0, 1, cfg2, max_iterations=12)
     assert len(more) == 2 and more[-1] < history[0]
+
+
+def test_ptq_eval_flow_from_an_fp32_checkpoint(tmp_path):
+    """classification/test_quantize.py — FP32 checkpoint -> prepare_qat -> convert -> eval."""
+    import importlib.util
+    import torch.nn as nn
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = config("classification", tmp_path, "FP32", 80, 5)
+    cfg["train_config"]["epochs"] = 6
+    from myrtle_vision.utils.trainer import train_deit
+    train_deit(0, 1, copy.deepcopy(cfg), max_iterations=6)
+    ckpt = os.path.join(cfg["train_config"]["output_directory"], "vit_000005")
+    assert os.path.exists(ckpt)
+    spec = importlib.util.spec_from_file_location(
+        "test_quantize_cli", os.path.join(root, "myrtle-vision_b200", "classification", "test_quantize.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ev = copy.deepcopy(cfg)
+    ev["train_config"]["checkpoint_path"] = ckpt
+    ev["vit_config"]["q_format"] = "FP16_32"
+    acc = mod.test_deit(ev, calib_steps=1, quantized_ckpt=False)
+    assert 0.0 <= acc <= 1.0
+    # the converted model's Linear weights and LayerNorm gammas sit on the fp16 grid
+    from myrtle_vision.utils.models import get_models, prepare_model_and_load_ckpt
+    vit, _ = get_models(copy.deepcopy({**ev, "vit_config": {**ev["vit_config"], "q_format": "FP32"}}))
+    vit = vit.cuda()
+    prepare_model_and_load_ckpt(train_config=ev["train_config"], model=vit)
+    vit.quantizer.prepare_qat("FP16_32")
+    vit.convert()
+    for m in vit.modules():
+        if isinstance(m, (nn.Linear, nn.LayerNorm)):
+            assert torch.equal(m.weight, m.weight.half().float())
