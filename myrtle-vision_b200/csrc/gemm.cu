@@ -965,7 +965,8 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     const int grid = 2 * (units < kNumSMs / 2 ? units : kNumSMs / 2);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
-    const bool heavy = a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU;       // 16 epilogue warps
+    // 16 epilogue warps only where 12 would be unbalanced: BN = 256 is 8 chunks over 3 column groups (3 / 3 / 2)
+    const bool heavy = (a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU) && BN == 256;
     if (BN == 256) rc = heavy ? launch_gemm2<256, 16>(ta, tb, p, grid, st) : launch_gemm2<256, 12>(ta, tb, p, grid, st);
     else if (BN == 192) rc = heavy ? launch_gemm2<192, 16>(ta, tb, p, grid, st) : launch_gemm2<192, 12>(ta, tb, p, grid, st);
     else rc = heavy ? launch_gemm2<128, 16>(ta, tb, p, grid, st) : launch_gemm2<128, 12>(ta, tb, p, grid, st);

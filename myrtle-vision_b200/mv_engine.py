@@ -93,22 +93,49 @@ class EncoderEngine:
             return self._wq
         if capturing and getattr(self, "_wq_capture_done", None) == id(torch.cuda.current_stream()):
             return self._wq          # already re-quantised once inside this capture (forward)
-        wq = {}
-        for i in idx:
-            w = self.params[i].detach()
-            old = self._wq.get(i) if self._wq else None
-            e, m = self.fmt if self.fmt else (0, 0)
-            if self.exact:
-                wq[i] = (mv.split_tf32(w, 1), mv.split_tf32(w.t().contiguous(), 1))
-                continue
-            q, qt = mv.quantize_weight(w, e, m, out=old[0] if old else None,
-                                       out_t=old[1] if old else None,
-                                       out_dtype=torch.float32 if self.wide else torch.float16)
-            wq[i] = (q, qt)
+        if self.exact:
+            wq = {i: (mv.split_tf32(self.params[i].detach(), 1),
+                      mv.split_tf32(self.params[i].detach().t().contiguous(), 1)) for i in idx}
+        else:
+            wq = self._requantise_all(idx)
         self._wq, self._wq_versions = wq, versions
         # inside a CUDA-graph capture the re-quantisation must be part of the graph (weights change
         # between replays) but only once per step: backward reuses the forward's operands
         self._wq_capture_done = id(torch.cuda.current_stream()) if capturing else None
+        return wq
+
+    def _requantise_all(self, idx):
+        """q(W) and q(W)^T of every Linear in ONE launch: the multi-tensor optimizer kernel (mv_adamw_step)
+        in its skip mode leaves parameters and moments untouched and only emits the operand tiles, so the
+        per-step weight_fake_quant of 4 * depth + 1 Linears costs one kernel instead of one each."""
+        import ctypes
+        from myrtle_vision.utils.fused_adamw import AdamwTensor
+        dt = torch.float32 if self.wide else torch.float16
+        e, m = self.fmt if self.fmt else (0, 0)
+        key = tuple(self.params[i].data_ptr() for i in idx)
+        tab = getattr(self, "_rq_table", None)
+        if tab is None or tab[0] != key:
+            wq, rows, chunk = {}, [], 0
+            for i in idx:
+                w = self.params[i].detach()
+                r, c = w.shape
+                q = torch.empty(r, c, dtype=dt, device=self.dev)
+                qt = torch.empty(c, r, dtype=dt, device=self.dev)
+                wq[i] = (q, qt)
+                t = AdamwTensor()
+                t.param, t.grad, t.exp_avg, t.exp_avg_sq = w.data_ptr(), w.data_ptr(), w.data_ptr(), w.data_ptr()
+                t.wq, t.wq_t, t.n, t.rows, t.cols = q.data_ptr(), qt.data_ptr(), w.numel(), r, c
+                t.wq_dtype, t.q_exp, t.q_man, t.lr, t.weight_decay, t.chunk0 = mv._DT[dt], e, m, 0.0, 0.0, chunk
+                chunk += ((r + 31) // 32) * ((c + 31) // 32)
+                rows.append(t)
+            arr = (AdamwTensor * len(rows))(*rows)
+            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev)
+            hyper = torch.tensor([0.9, 0.999, 1e-8, 1.0, 1.0, 1.0], dtype=torch.float32, device=self.dev)  # found_inf = 1: skip
+            tab = (key, wq, table, hyper, len(rows), chunk)
+            self._rq_table = tab
+        _, wq, table, hyper, n, chunks = tab
+        mv._check(mv.lib().mv_adamw_step(ctypes.c_void_p(table.data_ptr()), n, chunks, mv._ptr(hyper),
+                                         mv._stream()), "mv_adamw_step (re-quantise)")
         return wq
 
     def mark_weights_fresh(self):
