@@ -203,6 +203,15 @@ int mv_adamw_step(const mv_adamw_tensor* tensors_dev, int n_tensors, int total_c
 int mv_upsample_ce(const float* y, const int64_t* labels, float* dy, float* acc, int B, int C, int gh, int gw,
                    int H, int W, int64_t ignore_index, void* stream);
 
+/* ---------------------------------------------------------------- detection matching
+ * scipy.optimize.linear_sum_assignment of the reference's HungarianMatcher (models/matcher.py:83-86) for a
+ * whole batch in one launch, one warp per image.  cost: fp32 [B, Q, Tmax], image b uses columns
+ * [0, sizes[b]); match: int32 [B, Tmax], match[b, t] = prediction matched to target t, -1 for padding
+ * columns and for targets left over when sizes[b] > Q.  flag (may be NULL): set to 1 if some block has
+ * no finite matching (SciPy raises there).  Q, Tmax <= 1024. */
+int mv_linear_sum_assignment(const float* cost, const int* sizes, int B, int Q, int Tmax, int* match,
+                             int* flag, void* stream);
+
 /* ---------------------------------------------------------------- debug timelines
  * Only active in a library built with -DMV_SN_TRACE / -DMV_GEMM_TRACE (MV_NVCC_FLAGS for csrc/build.py):
  * CTA 0 of the short-sequence attention kernels / the CTA-pair GEMM writes {event, index, clock64} records

@@ -381,6 +381,25 @@ def upsample_ce(y, labels, ignore_index=-100):
     return acc, dy
 
 
+def linear_sum_assignment(cost, sizes, match=None, flag=None):
+    """Batched scipy.optimize.linear_sum_assignment on the device (mv_linear_sum_assignment).
+    cost fp32 [B, Q, Tmax], sizes int32 [B] (valid columns per image) -> match int32 [B, Tmax]:
+    prediction matched to every target, -1 for padding.  flag int32 [1] (optional) is set to 1
+    when a block has no finite matching.  No host synchronisation."""
+    _need_cuda(cost, sizes)
+    assert cost.dtype == torch.float32 and cost.dim() == 3 and sizes.dtype == torch.int32
+    cost, sizes = cost.contiguous(), sizes.contiguous()
+    B, Q, T = cost.shape
+    assert sizes.numel() == B
+    if match is None:
+        match = torch.empty(B, T, dtype=torch.int32, device=cost.device)
+    assert match.dtype == torch.int32 and match.shape == (B, T) and match.is_contiguous()
+    _check(lib().mv_linear_sum_assignment(_ptr(cost), _ptr(sizes), B, Q, T, _ptr(match),
+                                          _ptr(flag) if flag is not None else None, _stream()),
+           "mv_linear_sum_assignment")
+    return match
+
+
 # ------------------------------------------------------------------- attention
 def attention_fwd(qkv, B, H, N, *, scale=0.125, q_out=None, out_dtype=torch.float16, out=None,
                   lse=None):

@@ -6,6 +6,12 @@ constructor, `forward(outputs, targets) -> dict` and loss names (`loss_ce`, `cla
 internal: matched pairs are gathered once and shared by all losses, and the GIoU of matched pairs
 is computed pairwise instead of as the diagonal of an all-pairs matrix (:89-94).
 `num_boxes` is averaged over ranks exactly as the reference does (:134-138).
+
+Padded path: when `targets` is the dict made by `matcher.pad_targets` (fixed
+[B, T] capacity, on the CUDA device), matching runs on the device (`HungarianMatcher.match_padded`)
+and every loss is a masked reduction over the [B, T] pairs, so `forward` contains no host
+synchronisation and no data-dependent shape: the whole detection step is capturable in one CUDA
+graph.  The values equal the list path's (tests/test_gpu_detection.py).
 """
 import torch
 import torch.nn.functional as F
@@ -72,8 +78,46 @@ class SetCriterion(nn.Module):
         assert loss in loss_map, f"do you really want to compute {loss} loss?"
         return loss_map[loss](outputs, targets, indices, num_boxes, **kwargs)
 
+    def forward_padded(self, outputs, padded):
+        logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
+        B, Q, C1 = logits.shape
+        labels, tb, sizes = padded["labels"], padded["boxes"], padded["sizes"]
+        T = labels.shape[1]
+        match = self.matcher.match_padded(outputs, padded)                          # int32 [B, T]
+        m = (torch.arange(T, device=logits.device)[None, :] < sizes[:, None]) & (match >= 0)
+        q = match.clamp(min=0).to(torch.int64)
+        num_boxes = sizes.sum().to(torch.float32)
+        if is_dist_avail_and_initialized():
+            torch.distributed.all_reduce(num_boxes)
+        num_boxes = torch.clamp(num_boxes / get_world_size(), min=1)
+        losses = {}
+        if "labels" in self.losses:
+            classes = torch.full((B, Q + 1), self.num_classes, dtype=torch.int64, device=logits.device)
+            classes.scatter_(1, torch.where(m, q, Q), torch.where(m, labels, self.num_classes))
+            losses["loss_ce"] = F.cross_entropy(logits.transpose(1, 2), classes[:, :Q], self.empty_weight)
+            with torch.no_grad():
+                top = logits.gather(1, q[..., None].expand(B, T, C1)).argmax(-1)
+                pairs = m.sum()
+                hit = ((top == labels) & m).sum().float() * 100.0 / pairs.clamp(min=1)
+                losses["class_error"] = 100 - hit
+        if "cardinality" in self.losses:
+            with torch.no_grad():
+                predicted = (logits.argmax(-1) != C1 - 1).sum(1)
+                losses["cardinality_error"] = F.l1_loss(predicted.float(), sizes.float())
+        if "boxes" in self.losses:
+            src = boxes.gather(1, q[..., None].expand(B, T, 4))
+            zero = torch.zeros((), dtype=src.dtype, device=src.device)
+            giou = generalized_iou(cxcywh_to_xyxy(src), cxcywh_to_xyxy(tb))
+            losses["loss_bbox"] = torch.where(m, (src - tb).abs().sum(-1), zero).sum() / num_boxes
+            losses["loss_giou"] = torch.where(m, 1 - giou, zero).sum() / num_boxes
+        unknown = [k for k in self.losses if k not in ("labels", "cardinality", "boxes")]
+        assert not unknown, f"do you really want to compute {unknown[0]} loss?"
+        return losses
+
     def forward(self, outputs, targets):
         outputs = {k: v for k, v in outputs.items() if k != "aux_outputs"}
+        if isinstance(targets, dict):
+            return self.forward_padded(outputs, targets)
         indices = self.matcher(outputs, targets)
         device = next(iter(outputs.values())).device
         num_boxes = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float,

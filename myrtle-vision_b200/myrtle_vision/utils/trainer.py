@@ -24,6 +24,7 @@ from torch.utils.data import DataLoader
 from torch.utils.data.distributed import DistributedSampler
 
 from myrtle_vision.datasets.synthetic import SyntheticVision, detection_collate
+from myrtle_vision.models.matcher import pad_targets
 from myrtle_vision.utils.graph import GraphedTrainStep
 from myrtle_vision.utils.models import (get_models, get_optimizer_args, prepare_model_and_load_ckpt,
                                         save_checkpoint)
@@ -76,6 +77,8 @@ def build_criterion(task, train_config, num_classes, device):
 
 
 def to_device(targets, device):
+    if isinstance(targets, dict):
+        return {k: v.to(device, non_blocking=True) for k, v in targets.items()}
     if isinstance(targets, list):
         return [{k: v.to(device, non_blocking=True) for k, v in t.items()} for t in targets]
     return targets.to(device, non_blocking=True)
@@ -145,10 +148,15 @@ def train_deit(rank, num_gpus, config, task=None, max_iterations=None):
     criterion = build_criterion(task, train_config, data_config["number_of_classes"], device)
     iteration = prepare_model_and_load_ckpt(train_config=train_config, model=vit, optimizer=optimizer,
                                             lr_scheduler=lr_scheduler)
-    use_graph = train_config.get("cuda_graph", task != "detection") and n_batch_accum == 1 \
+    # detection: targets padded to a fixed [B, capacity] block and matched on the device (csrc/assign.cu),
+    # so the criterion has no host synchronisation and the whole step is one CUDA graph like the other tasks;
+    # "device_matching": false restores the host (SciPy) matcher between two captured graphs
+    device_matching = task == "detection" and train_config.get("device_matching", True)
+    det_capacity = 0
+    use_graph = train_config.get("cuda_graph", task != "detection" or device_matching) and n_batch_accum == 1 \
         and train_config["drop_last_batch"]
-    split_graph = (task == "detection" and train_config.get("cuda_graph", True) and n_batch_accum == 1
-                   and train_config["drop_last_batch"] and num_gpus <= 1)
+    split_graph = (task == "detection" and not device_matching and train_config.get("cuda_graph", True)
+                   and n_batch_accum == 1 and train_config["drop_last_batch"] and num_gpus <= 1)
     iters_per_checkpoint = train_config.get("iters_per_checkpoint", 0)
     iters_per_val = train_config.get("iters_per_val", 0)
     log_every = train_config.get("log_every", 1)
@@ -167,6 +175,11 @@ def train_deit(rank, num_gpus, config, task=None, max_iterations=None):
                                 iteration=iteration, filepath=f"{out_dir}/vit_{iteration:06}")
             if rank == 0 and n_accum == 0 and iters_per_val and iteration % iters_per_val == 0 and len(valset):
                 last_val = validation(task, val_loader, device, criterion, vit)
+            if device_matching:
+                most = max([int(t["boxes"].shape[0]) for t in targets] + [1])
+                if most > det_capacity:                     # grow the padded block: the graph is re-captured
+                    det_capacity, graphed = -(-most // 16) * 16, None
+                targets = pad_targets(targets, capacity=det_capacity)
             imgs, targets = imgs.to(device, non_blocking=True), to_device(targets, device)
             if use_graph:
                 if graphed is None:

@@ -26,6 +26,8 @@ ap.add_argument("--arch", default="small")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--unfused-seg-loss", action="store_true", help="segmentation: upsample + CrossEntropyLoss in PyTorch")
 ap.add_argument("--no-graph", action="store_true")
+ap.add_argument("--host-matcher", action="store_true",
+                help="detection: SciPy assignment on the host between two captured graphs (the round-1e path)")
 args = ap.parse_args()
 size, classes, batch = (256, 17, 256) if args.task == "segmentation" else (800, 20, 8)
 batch = args.batch or batch
@@ -39,6 +41,10 @@ if args.task == "detection":
     batches = [detection_collate(items[:batch]), detection_collate(items[batch:])]
 else:
     batches = [(torch.stack([a for a, _ in part]), torch.stack([b for _, b in part])) for part in (items[:batch], items[batch:])]
+if args.task == "detection" and not args.host_matcher:
+    from myrtle_vision.models.matcher import pad_targets
+    cap = -(-max(int(t["boxes"].shape[0]) for _, ts in batches for t in ts) // 16) * 16
+    batches = [(img, pad_targets(ts, capacity=cap)) for img, ts in batches]      # fixed [B, cap] target block
 batches = [(img.to(dev), to_device(t, dev)) for img, t in batches]
 train_cfg = {"loss_ce": 1.0, "class_error": 0.0, "loss_bbox": 5.0, "loss_giou": 2.0, "cardinality_error": 0.0, "eos_coef": 0.1}
 train_cfg["fused_seg_loss"] = not args.unfused_seg_loss
@@ -68,7 +74,7 @@ kern = {k: round(v[1] / args.steps, 3) for k, v in sorted(mv_native.timing_summa
 mv_native.enable_timing(False)
 ms = ms_eager
 graph = not args.no_graph
-if graph and args.task == "segmentation":
+if graph and (args.task == "segmentation" or not args.host_matcher):
     gs = GraphedTrainStep(model, criterion, *batches[0])
     run = lambda img, tgt: gs(img, tgt)
 elif graph:
@@ -93,5 +99,6 @@ if graph:
 n_tok = (size // 16) ** 2 + 1
 print(json.dumps({"task": args.task, "arch": args.arch, "q_format": args.q_format, "batch": batch, "tokens": n_tok,
                   "images_per_s": batch / ms * 1e3, "ms_per_step": ms, "eager_ms_per_step": ms_eager,
-                  "cuda_graph": graph, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                  "cuda_graph": graph, "matcher": ("host" if args.host_matcher else "device") if args.task == "detection" else None,
+                  "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
                   "top_kernels_ms_per_step": dict(list(kern.items())[:8])}))
