@@ -102,6 +102,9 @@ typedef struct {
     int accumulate;               /* split-K atomic accumulation into fp32 `out` */
     int rows_per_img;             /* residual row = m % rows_per_img when > 0 */
     int tile_n;                   /* 0 = auto; 128 / 192 / 256 forces the tile width (testing) */
+    float* colsum;                /* NULL, or fp32 [N]: colsum[n] += sum over m of the value stored to out[m, n] (fp32, before
+                                   * the container rounding) with red.add — the bias gradient of the Linear whose output
+                                   * gradient this GEMM produces, without a second pass over it.  CTA-pair kernel only. */
     int cluster;                  /* 0 = CTA-pair kernel (tcgen05 cta_group::2, 256 x tile_n cluster tiles; 16-bit operands);
                                    * 1 = single-CTA kernel (always used for tf32); 2 = single-CTA MMAs with the B tile
                                    * TMA-multicast across a CTA pair (kept for comparison) */
@@ -163,9 +166,14 @@ int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float* lse, int 
 /* autograd backward of the above.  o: the saved forward output (fp16), d_o: fp16 gradient w.r.t. it,
  * delta: fp32 [B,H,N] scratch, dqkv: fp16 [B*N, 3*H*64] (dq | dk | dv).
  * dq_accum: fp32 [B*N, H*64] scratch.  Non-NULL: one pass over key blocks, dQ accumulated across
- * key blocks with fp32 red.add (fast path).  NULL: deterministic two-pass variant without atomics. */
+ * key blocks with fp32 red.add (fast path).  NULL: deterministic two-pass variant without atomics.
+ * dbias: NULL or fp32 [3*H*64] (16-byte aligned): += the to_qkv Linear's bias gradient, i.e. the column sums of
+ * dqkv.  The short-sequence kernel fuses it: the q part from the dQ rows it stores; the v part as the column sums
+ * of d_o (sum_k dV[k,:] = sum_q (sum_k P[q,k]) dO[q,:] and the rows of P sum to one); the k part is left untouched
+ * because it is identically zero (sum_k dS[q,k] = 0: a key bias shifts every score of a row alike).  Long
+ * sequences take one mv_colsum pass over dqkv. */
 int mv_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
-                     float* dq_accum, void* dqkv, int B, int H, int N, float scale, void* stream);
+                     float* dq_accum, void* dqkv, float* dbias, int B, int H, int N, float scale, void* stream);
 
 /* ---------------------------------------------------------------- optimizer step
  * Multi-tensor AdamW (torch.optim.AdamW / timm AdamW update rule, reference classification/train.py:

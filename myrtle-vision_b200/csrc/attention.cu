@@ -754,7 +754,7 @@ extern "C" int mv_attention_sn_supported(int N);
 int mv_attention_fwd_sn(const void* qkv, void* out, int out_dtype, float* lse, int B, int H, int N,
                         float scale, int q_out_exp, int q_out_man, void* stream);
 int mv_attention_bwd_sn(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
-                        void* dqkv, int B, int H, int N, float scale, void* stream);
+                        void* dqkv, float* dbias, int B, int H, int N, float scale, void* stream);
 
 extern "C" int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float* lse, int B, int H, int N,
                                 float scale, int q_out_exp, int q_out_man, void* stream) {
@@ -783,10 +783,12 @@ extern "C" int mv_attention_fwd(const void* qkv, void* out, int out_dtype, float
 }
 
 extern "C" int mv_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
-                                float* dq_accum, void* dqkv, int B, int H, int N, float scale, void* stream) {
+                                float* dq_accum, void* dqkv, float* dbias, int B, int H, int N, float scale,
+                                void* stream) {
     MV_CHECK(B > 0 && H > 0 && N > 0 && qkv && o && d_o && lse && delta && dqkv, "mv_attention_bwd: bad arguments");
+    MV_CHECK((reinterpret_cast<uintptr_t>(dbias) & 15) == 0, "mv_attention_bwd: dbias must be 16-byte aligned");
     if (g_opt_attn_sn && N <= 272)
-        return mv_attention_bwd_sn(qkv, o, d_o, lse, delta, dqkv, B, H, N, scale, stream);
+        return mv_attention_bwd_sn(qkv, o, d_o, lse, delta, dqkv, dbias, B, H, N, scale, stream);
     const int D = H * 64;
     static bool attr_done = false;
     if (!attr_done) {
@@ -829,5 +831,8 @@ extern "C" int mv_attention_bwd(const void* qkv, const void* o, const void* d_o,
         attn_bwd_kernel<false><<<grid, kAttThreads, kAttnBwdQSmem, st>>>(tq, td, p);
         g_launches++;
     }
-    return check_cuda(cudaGetLastError(), "attention bwd launch");
+    if (check_cuda(cudaGetLastError(), "attention bwd launch")) return 1;
+    // long sequences: the bias gradient is a separate pass over dqkv (the short-sequence kernel fuses it)
+    if (dbias != nullptr) return mv_colsum(dqkv, MV_F16, 3 * D, B * N, 3 * D, dbias, stream);
+    return 0;
 }

@@ -73,8 +73,18 @@ extern "C" int mv_debug_set_attn_trace(void* dev_buf) { g_sn_trace = static_cast
 // the clock64 timeline).  Each warp parks half a row per lane (32 fp16) in its private staging tile and
 // writes it back with four lanes per row: 8 rows x 64 contiguous bytes per store instruction.
 // v0 / v1: columns 0..31 / 32..63 of this lane's row (fp32 bits).  dst0: row 0 of the warp's 32 rows.
+// kCS: also accumulate the column sums of the stored (fp16-rounded) rows — the fused bias gradient — into the
+// lane's registers: in the write-back phase lane l always owns columns half * 32 + (l & 3) * 8 .. + 7, so
+// acc[half][k] simply grows over every store of the kernel and is reduced over the 8 lanes that share a column
+// chunk only when it is flushed (sn_flush_colsum).  (Reducing per store — shuffles plus global or shared
+// atomics — was measured at +34 / +65 us per launch.)
+__device__ __forceinline__ void sn_red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+template <bool kCS>
 __device__ __forceinline__ void sn_store_rows(uint8_t* stg, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
-                                              __half* dst0, int64_t ld, int nvalid, int lane) {
+                                              __half* dst0, int64_t ld, int nvalid, int lane, float (&acc)[2][8]) {
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         const uint32_t (&v)[32] = half == 0 ? v0 : v1;
@@ -90,9 +100,39 @@ __device__ __forceinline__ void sn_store_rows(uint8_t* stg, const uint32_t (&v0)
         for (int it = 0; it < 4; it++) {
             const int row = it * 8 + (lane >> 2), chunk = lane & 3;
             const uint4 w = *reinterpret_cast<const uint4*>(stg + row * kSnStgPitch + chunk * 16);
-            if (row < nvalid) *reinterpret_cast<uint4*>(dst0 + row * ld + half * 32 + chunk * 8) = w;
+            if (row < nvalid) {
+                *reinterpret_cast<uint4*>(dst0 + row * ld + half * 32 + chunk * 8) = w;
+                if (kCS) {
+                    const __half2* hp = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float2 f = __half22float2(hp[k]);
+                        acc[half][2 * k] += f.x; acc[half][2 * k + 1] += f.y;
+                    }
+                }
+            }
         }
         __syncwarp();
+    }
+}
+// dst: fp32 [64] in global memory, += the warp's accumulated column sums; the accumulators restart from zero
+__device__ __forceinline__ void sn_flush_colsum(float (&acc)[2][8], float* dst, int lane) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float c = acc[half][k];
+            c += __shfl_xor_sync(0xffffffffu, c, 4);
+            c += __shfl_xor_sync(0xffffffffu, c, 8);
+            c += __shfl_xor_sync(0xffffffffu, c, 16);
+            acc[half][k] = c;
+        }
+        if (lane < 4) {
+            sn_red_add_v4(dst + half * 32 + lane * 8, acc[half][0], acc[half][1], acc[half][2], acc[half][3]);
+            sn_red_add_v4(dst + half * 32 + lane * 8 + 4, acc[half][4], acc[half][5], acc[half][6], acc[half][7]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[half][k] = 0.f;
     }
 }
 
@@ -629,6 +669,7 @@ constexpr int kSnOffStg = kSnOffVec + (2 * kSnMaxKeys + 16 * 64) * 4;   // 8 mat
 constexpr int kSnOffVec2 = kSnOffStg + 8 * 32 * kSnStgPitch;           // L / Delta of the next pair (double buffer)
 constexpr int kSnOffBar = kSnOffVec2 + 2 * kSnMaxKeys * 4;
 constexpr int kSnBwdSmem = kSnOffBar + 256 + 1024;
+static_assert(kSnBwdSmem <= 232448, "attention bwd (short sequences): shared memory over the 227 KB limit");
 
 struct SnBwdDev {
     unsigned long long* trace;
@@ -641,6 +682,7 @@ struct SnBwdDev {
     const __half* o;            // forward output and its gradient, [B*N, D]: Delta = rowsum(dO * O) per head
     const __half* d_o;
     __half* dqkv; int ld_dqkv;
+    float* dbias;               // NULL or fp32 [3 * D]: += column sums of dqkv (the to_qkv Linear's bias gradient)
 };
 
 __global__ void __launch_bounds__(kSnBwdThreads, 1)
@@ -676,6 +718,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     const int n_bh = p.B * p.H;
     const int n_local = blockIdx.x < n_bh ? (n_bh - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int nblk = p.n_reg + (p.tail_w > 0 ? 1 : 0);           // blocks per pass
+
     const int nb_bh = p.n_pass * nblk;                            // blocks per (image, head)
 
     if (warp == 0 && lane == 0) {
@@ -843,6 +886,17 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         const uint32_t lane_off = uint32_t(quad * 32) << 16;
         const uint32_t tS = tmem_base + g * 128 + lane_off, tdP = tS + 64;
         int gb0 = 0, pc0 = 0;
+        // Fused to_qkv bias gradient (p.dbias != NULL; the host then sizes the grid so that a CTA stays on one head
+        // and the sums are flushed once, after the last pair):
+        //   q: column sums of the dQ rows this warp stores (cs_q) and, per thread, columns 2 * lane, 2 * lane + 1 of
+        //      the dQ rows >= 256 (cs_t0 / cs_t1);
+        //   k: nothing to add — sum_k dS[q, k] = sum_k P (dP - Delta_q) = 0, the key bias never reaches the softmax;
+        //   v: sum_k dV[k, :] = sum_q (sum_k P[q, k]) dO[q, :] = the column sums of dO, which stats_rows has in
+        //      registers anyway (cs_v: this thread's 16-byte chunk of the head, every row it visits).
+        float cs_q[2][8], cs_v[8], cs_t0 = 0.f, cs_t1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { cs_q[0][k] = cs_q[1][k] = cs_v[k] = 0.f; }
+        const bool do_cs = p.dbias != nullptr;
         for (int n = 0; n < n_local; n++, gb0 += nb_bh, pc0 += p.n_pass) {
             const int bh = blockIdx.x + n * gridDim.x;
             const int b = bh / p.H, h = bh % p.H;
@@ -881,6 +935,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     for (int q = 0; q < 4; q++) {
                         const float2 fx = __half22float2(xh[q]), fy = __half22float2(yh[q]);
                         dl = fmaf(fx.x, fy.x, dl); dl = fmaf(fx.y, fy.y, dl);
+                        cs_v[2 * q] += fx.x; cs_v[2 * q + 1] += fx.y;           // rows >= N contribute zeros
                     }
                     dl += __shfl_xor_sync(0xffffffffu, dl, 1);
                     dl += __shfl_xor_sync(0xffffffffu, dl, 2);
@@ -1024,7 +1079,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     {
                         const int key0 = j * 128 + quad * 32;            // first key row of this warp
                         __half* dst0 = p.dqkv + (int64_t(b) * p.N + key0) * p.ld_dqkv + (g == 0 ? 2 : 1) * p.D + h * 64;
-                        sn_store_rows(sStg + (warp - 2) * 32 * kSnStgPitch, v0, v1, dst0, p.ld_dqkv, p.N - key0, lane);
+                        sn_store_rows<false>(sStg + (warp - 2) * 32 * kSnStgPitch, v0, v1, dst0, p.ld_dqkv, p.N - key0, lane, cs_q);
                     }
                 }
             }
@@ -1046,7 +1101,9 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                 if (have) {
                     const int row0 = g * 128 + quad * 32;
                     __half* dst0 = p.dqkv + (int64_t(b) * p.N + row0) * p.ld_dqkv + h * 64;
-                    sn_store_rows(sStg + (warp - 2) * 32 * kSnStgPitch, v0, v1, dst0, p.ld_dqkv, p.N - row0, lane);
+                    uint8_t* stg = sStg + (warp - 2) * 32 * kSnStgPitch;
+                    if (do_cs) sn_store_rows<true>(stg, v0, v1, dst0, p.ld_dqkv, p.N - row0, lane, cs_q);
+                    else sn_store_rows<false>(stg, v0, v1, dst0, p.ld_dqkv, p.N - row0, lane, cs_q);
                 }
             }
             // rows >= 256: dQ from the shared-memory accumulators
@@ -1055,11 +1112,31 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             SN_TRACE(quad == 0 && lane == 0, 1 + g, 17, n);
             for (int i = mt; i < (p.N - 256) * 32; i += 256) {
                 const int r = i >> 5, l2 = i & 31;
-                *reinterpret_cast<uint32_t*>(p.dqkv + (int64_t(b) * p.N + 256 + r) * p.ld_dqkv + h * 64 + 2 * l2) =
-                    pack_h2_satf(sdQt[r * 64 + 2 * l2], sdQt[r * 64 + 2 * l2 + 1]);
+                const uint32_t pk = pack_h2_satf(sdQt[r * 64 + 2 * l2], sdQt[r * 64 + 2 * l2 + 1]);
+                *reinterpret_cast<uint32_t*>(p.dqkv + (int64_t(b) * p.N + 256 + r) * p.ld_dqkv + h * 64 + 2 * l2) = pk;
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+                cs_t0 += f.x; cs_t1 += f.y;                                 // l2 == lane for every i of this thread
             }
             named_bar_sync(1, 256);
             SN_TRACE(quad == 0 && lane == 0, 1 + g, 18, n);                 // pair finished
+        }
+        if (do_cs && n_local > 0) {
+            const int h = blockIdx.x % p.H;
+            sn_flush_colsum(cs_q, p.dbias + h * 64, lane);
+            if (cs_t0 != 0.f || cs_t1 != 0.f) {
+                atomicAdd(p.dbias + h * 64 + 2 * lane, cs_t0);
+                atomicAdd(p.dbias + h * 64 + 2 * lane + 1, cs_t1);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {                                   // lanes l, l ^ 8, l ^ 16, l ^ 24 share a chunk
+                cs_v[k] += __shfl_xor_sync(0xffffffffu, cs_v[k], 8);
+                cs_v[k] += __shfl_xor_sync(0xffffffffu, cs_v[k], 16);
+            }
+            if (lane < 8) {
+                float* dv = p.dbias + 2 * p.D + h * 64 + lane * 8;
+                sn_red_add_v4(dv, cs_v[0], cs_v[1], cs_v[2], cs_v[3]);
+                sn_red_add_v4(dv + 4, cs_v[4], cs_v[5], cs_v[6], cs_v[7]);
+            }
         }
     }
     tc_fence_before();
@@ -1117,7 +1194,7 @@ int mv_attention_fwd_sn(const void* qkv, void* out, int out_dtype, float* lse, i
 }
 
 int mv_attention_bwd_sn(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta,
-                        void* dqkv, int B, int H, int N, float scale, void* stream) {
+                        void* dqkv, float* dbias, int B, int H, int N, float scale, void* stream) {
     const int D = H * 64;
     static bool attr_done = false;
     if (!attr_done) {
@@ -1142,8 +1219,15 @@ int mv_attention_bwd_sn(const void* qkv, const void* o, const void* d_o, const f
     p.o = reinterpret_cast<const __half*>(o); p.d_o = reinterpret_cast<const __half*>(d_o);
     p.dqkv = reinterpret_cast<__half*>(dqkv); p.ld_dqkv = 3 * D;
     const int n_bh = B * H;
-    const int grid = n_bh < kNumSMs ? n_bh : kNumSMs;
+    // Fused bias gradient: the kernel keeps per-head sums in registers, so a CTA must stay on one head — pair index =
+    // blockIdx + n * grid with the grid a multiple of H (or one pair per CTA).  Same number of rounds as a full grid
+    // whenever ceil(n_bh / grid) does not change (B = 256, H = 6: 11 rounds with 144 or 148 CTAs).
+    const bool fuse = dbias != nullptr && H <= kNumSMs;
+    const int grid = n_bh <= kNumSMs ? n_bh : (fuse ? (kNumSMs / H) * H : kNumSMs);
+    p.dbias = fuse ? dbias : nullptr;
     attn_bwd_sn_kernel<<<grid, kSnBwdThreads, kSnBwdSmem, st>>>(q128, q16, d128, d16, p);
     g_launches++;
-    return check_cuda(cudaGetLastError(), "attention bwd (short-sequence) launch");
+    if (check_cuda(cudaGetLastError(), "attention bwd (short-sequence) launch")) return 1;
+    if (dbias != nullptr && !fuse) return mv_colsum(dqkv, MV_F16, 3 * D, B * N, 3 * D, dbias, stream);
+    return 0;
 }

@@ -62,6 +62,7 @@ struct GemmDev {
     int accumulate;
     int rows_per_img;
     int variant;                // CTA-pair kernel: compile-time epilogue variant (0 = generic), see gemm2_host
+    float* colsum;              // CTA-pair kernel: fp32 [N] += column sums of the stored values (fused bias gradient)
 };
 
 __device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
@@ -571,7 +572,7 @@ __device__ __forceinline__ void stage_chunk(const EpiWarp& w, uint32_t taddr, ui
 // Fast path: the chunk lies inside [M, N], every pointer / pitch is vector-aligned (checked on the
 // host, GemmDev::variant) and the epilogue's shape is a compile-time choice, so the unrolled row
 // loop is a few instructions per 4 outputs.  kRes: 0 none, 1 residual[m, n], 2 residual[m % rows_per_img, n].
-template <int kOut, int kEpi, int kRes, int kQO, int kQR, bool kAcc>
+template <int kOut, int kEpi, int kRes, int kQO, int kQR, bool kAcc, bool kCS = false>
 __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, uint32_t taddr, uint32_t release,
                                           int mrow0, int nc0) {
     const int n = nc0 + w.lc;
@@ -601,6 +602,7 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
     if (w.tr != nullptr && w.lane == 0) { w.tr[3] = 21; w.tr[4] = nc0; w.tr[5] = clock64(); }
 #endif
     const uint32_t sp = w.stg_s + (w.lr * kStgPitch + w.lc) * 4;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int it = 0; it < 8; it++) {
         const int m = m_first + it * 4;
@@ -624,11 +626,21 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
         }
         if (kRes != 0) { v[0] += res4[it].x; v[1] += res4[it].y; v[2] += res4[it].z; v[3] += res4[it].w; }
         if (kQR == 1) fq_half4<kOut == MV_F16>(v);
+        if (kCS) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
         if (kOut == MV_F32)
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + int64_t(m) * p.ld_out + n) =
                 make_float4(v[0], v[1], v[2], v[3]);
         else
             *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + int64_t(m) * p.ld_out + n) = pack4_f16_sat(v);
+    }
+    if (kCS) {
+        // this warp's 32 rows of columns n .. n+3: the 4 lanes that share the columns hold 8 rows each
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+            cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+        }
+        if (w.lr == 0) red_add_v4(p.colsum + n, cs[0], cs[1], cs[2], cs[3]);
     }
 #ifdef MV_GEMM_TRACE
     if (w.tr != nullptr && w.lane == 0) { w.tr[6] = 22; w.tr[7] = nc0; w.tr[8] = clock64(); }
@@ -643,6 +655,7 @@ __device__ __forceinline__ void epi_chunk_generic(const GemmDev& p, const EpiWar
     const int n = nc0 + w.lc;
     const int nvalid = min(4, p.N - n);
     if (nvalid > 0) {
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int it = 0; it < 8; it++) {
             const int row = it * 4 + w.lr;
@@ -674,9 +687,12 @@ __device__ __forceinline__ void epi_chunk_generic(const GemmDev& p, const EpiWar
                 for (int j = 0; j < 4; j++) if (j < nvalid) v[j] += rp[j];
             }
             if (w.mode_res) for (int j = 0; j < 4; j++) v[j] = fq_apply(v[j], w.mode_res, p.q_res);
+            for (int j = 0; j < 4; j++) cs[j] += v[j];
             store_out4(p.out, p.out_dtype, m, p.ld_out, n, v, false, nvalid);
             if (p.out2 != nullptr) store_out4(p.out2, p.out2_dtype, m, p.ld_out2, n, v, false, nvalid);
         }
+        if (p.colsum != nullptr && !p.accumulate)
+            for (int j = 0; j < 4; j++) if (j < nvalid) atomicAdd(p.colsum + n + j, cs[j]);
     }
     __syncwarp();
 }
@@ -855,6 +871,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             MV_EPI_CASE(8, MV_F32, MV_EPI_NONE, 0, 0, 0, true)
             MV_EPI_CASE(9, MV_F16, MV_EPI_GELU, 0, 1, 1, false)
             MV_EPI_CASE(10, MV_F32, MV_EPI_NONE, 2, 1, 1, false)
+            MV_EPI_CASE(11, MV_F16, MV_EPI_DGELU, 0, 0, 0, false, true)
             default:       // variant 0: every chunk takes the generic path (`fast` is false)
                 walk([&](uint32_t, uint32_t, int, int) {});
                 break;
@@ -938,26 +955,30 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     p.q_res = FloatFmt{a->q_res_exp, a->q_res_man};
     p.accumulate = a->accumulate;
     p.rows_per_img = a->rows_per_img;
+    p.colsum = a->accumulate ? nullptr : a->colsum;
     // epilogue variant (epi_chunk<> instantiations in gemm2_kernel); anything else runs the generic path
     {
         auto al = [](const void* q, int bytes) { return (reinterpret_cast<uintptr_t>(q) & (bytes - 1)) == 0; };
         auto qkind = [](int e, int m) { return e == 0 ? 0 : ((e == 5 && m == 10) ? 1 : 2); };
         const int qo = qkind(a->q_out_exp, a->q_out_man), qr = qkind(a->q_res_exp, a->q_res_man);
         const int res = a->residual == nullptr ? 0 : (a->rows_per_img > 0 ? 2 : 1);
+        const int cs = a->colsum != nullptr ? 1 : 0;
         const bool ok = a->out2 == nullptr && (a->ld_out & 3) == 0 && (a->bias == nullptr || al(a->bias, 16)) &&
+                        (cs == 0 || al(a->colsum, 16)) &&
                         (res == 0 || ((a->ld_res & 3) == 0 && al(a->residual, 16))) &&
                         (a->aux == nullptr || ((a->ld_aux & 3) == 0 && al(a->aux, 8))) &&
                         al(a->out, a->out_dtype == MV_F32 ? 16 : 8);
-        struct Row { int id, out, epi, res, qo, qr; };
+        struct Row { int id, out, epi, res, qo, qr, cs; };
         static const Row table[] = {
-            {1, MV_F16, MV_EPI_NONE, 0, 0, 0}, {2, MV_F16, MV_EPI_NONE, 0, 1, 0}, {3, MV_F32, MV_EPI_NONE, 1, 0, 0},
-            {4, MV_F32, MV_EPI_NONE, 1, 1, 1}, {5, MV_F16, MV_EPI_GELU, 0, 0, 1}, {6, MV_F16, MV_EPI_DGELU, 0, 0, 0},
-            {7, MV_F32, MV_EPI_NONE, 2, 0, 0}, {9, MV_F16, MV_EPI_GELU, 0, 1, 1}, {10, MV_F32, MV_EPI_NONE, 2, 1, 1}};
+            {1, MV_F16, MV_EPI_NONE, 0, 0, 0, 0}, {2, MV_F16, MV_EPI_NONE, 0, 1, 0, 0}, {3, MV_F32, MV_EPI_NONE, 1, 0, 0, 0},
+            {4, MV_F32, MV_EPI_NONE, 1, 1, 1, 0}, {5, MV_F16, MV_EPI_GELU, 0, 0, 1, 0}, {6, MV_F16, MV_EPI_DGELU, 0, 0, 0, 0},
+            {7, MV_F32, MV_EPI_NONE, 2, 0, 0, 0}, {9, MV_F16, MV_EPI_GELU, 0, 1, 1, 0}, {10, MV_F32, MV_EPI_NONE, 2, 1, 1, 0},
+            {11, MV_F16, MV_EPI_DGELU, 0, 0, 0, 1}};
         int v = 0;
         if (ok && a->accumulate) v = 8;
         else if (ok)
             for (const Row& r : table)
-                if (r.out == a->out_dtype && r.epi == a->epilogue && r.res == res && r.qo == qo && r.qr == qr) v = r.id;
+                if (r.out == a->out_dtype && r.epi == a->epilogue && r.res == res && r.qo == qo && r.qr == qr && r.cs == cs) v = r.id;
         p.variant = v;
     }
 
@@ -984,6 +1005,7 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     if (a->accumulate) MV_CHECK(a->out_dtype == MV_F32, "mv_gemm: accumulate needs an fp32 output");
     if (a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU) MV_CHECK(a->aux != nullptr, "mv_gemm: GELU epilogues need aux");
     if (!tf32 && a->cluster == 0) return gemm2_host(a, stream);      // CTA-pair kernel (default)
+    MV_CHECK(a->colsum == nullptr, "mv_gemm: colsum is only fused into the CTA-pair kernel (16-bit operands, cluster == 0)");
     const int esz = tf32 ? 4 : 2;
     const int BK = 128 / esz;
     static bool attr_done = false;
@@ -1034,6 +1056,7 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     p.q_res = FloatFmt{a->q_res_exp, a->q_res_man};
     p.accumulate = a->accumulate;
     p.rows_per_img = a->rows_per_img;
+    p.variant = 0; p.colsum = nullptr;
 
     // CTA pairs sharing B through TMA multicast: measured no faster on B200 (the bound is the per-SM
     // L2->SM ingest, which multicast does not reduce), so it is opt-in (cluster == 2)

@@ -216,12 +216,12 @@ class EncoderEngine:
             x, xn1, mean1, rstd1, qkv, att, lse, x1, xn2, mean2, rstd2, u, h = saved["layers"][l]
             # ---- FeedForward
             du = torch.empty(M, Mm, dtype=f16, device=dev)
-            mv.gemm(dx_h, wq[b0 + 10][1], du, aux=u, epilogue=mv.EPI_DGELU)
+            # fc1's bias gradient (column sums of du) rides in the epilogue
+            mv.gemm(dx_h, wq[b0 + 10][1], du, aux=u, epilogue=mv.EPI_DGELU, colsum=g[b0 + 9].view(-1))
             mv.gemm(dx_h, h, g[b0 + 10], a_major=1, b_major=1, accumulate=True)
             dxn2 = torch.empty(M, D, dtype=f16, device=dev)
             mv.gemm(du, wq[b0 + 8][1], dxn2, tag="dgrad")
             mv.gemm(du, xn2, g[b0 + 8], a_major=1, b_major=1, accumulate=True)
-            mv.colsum(du, g[b0 + 9].view(-1))
             del du
             dx1, dx1_h = mv.layernorm_q_bwd(dxn2, x1, prm[b0 + 6], mean2, rstd2, dres=dx, q_in=fmt,
                                             dgamma=g[b0 + 6], dbeta=g[b0 + 7], dbias_prev=g[b0 + 5])
@@ -229,11 +229,11 @@ class EncoderEngine:
             datt = torch.empty(M, D, dtype=f16, device=dev)
             mv.gemm(dx1_h, wq[b0 + 4][1], datt, tag="dgrad")
             mv.gemm(dx1_h, att, g[b0 + 4], a_major=1, b_major=1, accumulate=True)
-            dqkv = mv.attention_bwd(qkv, att, datt, lse, B, H, N, scale=0.125)
+            dqkv = mv.attention_bwd(qkv, att, datt, lse, B, H, N, scale=0.125,
+                                    dbias=g[b0 + 3].view(-1))          # to_qkv's bias gradient fused
             dxn1 = dxn2      # reuse
             mv.gemm(dqkv, wq[b0 + 2][1], dxn1, tag="dgrad")
             mv.gemm(dqkv, xn1, g[b0 + 2], a_major=1, b_major=1, accumulate=True)
-            mv.colsum(dqkv, g[b0 + 3].view(-1))
             prev_bias = g[b0 - 1] if l > 0 else None                       # fc2 bias of block l-1
             dx, dx_h = mv.layernorm_q_bwd(dxn1, x, prm[b0], mean1, rstd1, dres=dx1, q_in=fmt,
                                           dgamma=g[b0], dbeta=g[b0 + 1], dbias_prev=prev_bias,
@@ -399,7 +399,7 @@ class EncoderEngine:
                 dqkv16 = dqkv = self._attention_exact_bwd(qkv, lse, datt, B, H, N)
                 _, dqkv_t = mv.widen_transpose(dqkv, padded=True)
             else:
-                dqkv16 = mv.attention_bwd(qkv, att16, datt, lse, B, H, N, scale=0.125)
+                dqkv16 = mv.attention_bwd(qkv, att16, datt, lse, B, H, N, scale=0.125, dbias=g[b0 + 3].view(-1))
                 dqkv, dqkv_t = mv.widen_transpose(dqkv16, want_copy=True)
             dxn1 = dxn2
             mv.gemm(A_(dqkv), wq[b0 + 2][1], dxn1, tag="dgrad")
@@ -407,7 +407,8 @@ class EncoderEngine:
             if ex:
                 dqkv_t, xn1_t = mv.split_tf32(dqkv_t, 0), mv.split_tf32(xn1_t, 1)
             mv.gemm(dqkv_t, xn1_t, g[b0 + 2], accumulate=True)
-            mv.colsum(dqkv16, g[b0 + 3].view(-1))
+            if ex:
+                mv.colsum(dqkv16, g[b0 + 3].view(-1))
             prev_bias = g[b0 - 1] if l > 0 else None
             dx, _ = mv.layernorm_q_bwd(dxn1, x, prm[b0], mean1, rstd1, dres=dx1, q_in=fmt,
                                        dgamma=g[b0], dbeta=g[b0 + 1], dbias_prev=prev_bias,

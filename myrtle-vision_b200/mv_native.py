@@ -39,6 +39,7 @@ class GemmArgs(ctypes.Structure):
         ("accumulate", ctypes.c_int),
         ("rows_per_img", ctypes.c_int),
         ("tile_n", ctypes.c_int),
+        ("colsum", ctypes.c_void_p),
         ("cluster", ctypes.c_int),
     ]
 
@@ -203,7 +204,7 @@ def quantize_weight(w, exp, man, out_dtype=torch.float16, transpose=True, out=No
 # ------------------------------------------------------------------------ GEMM
 def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out2=None,
          epilogue=EPI_NONE, q_out=None, q_res=None, accumulate=False, rows_per_img=0,
-         M=None, N=None, K=None, tag=None, tile_n=0, cluster=0):
+         M=None, N=None, K=None, tag=None, tile_n=0, cluster=0, colsum=None):
     """out[M,N] = A . B^T over K with the fused epilogue of mv_gemm (include/mv_b200.h).
     a_major/b_major = 0: operand is [M|N, K] (K contiguous); 1: operand is [K, M|N]."""
     _need_cuda(A, B, out)
@@ -237,6 +238,9 @@ def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None,
     a.rows_per_img = rows_per_img
     a.tile_n = tile_n
     a.cluster = cluster
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == N
+        a.colsum = colsum.data_ptr()
     kind = "gemm_wgrad" if accumulate else ("gemm_dgrad" if epilogue == EPI_DGELU or tag == "dgrad"
                                             else "gemm_fwd")
     if _TIMERS is not None:
@@ -419,8 +423,9 @@ def attention_fwd(qkv, B, H, N, *, scale=0.125, q_out=None, out_dtype=torch.floa
 
 
 def attention_bwd(qkv, o, d_o, lse, B, H, N, *, scale=0.125, dqkv=None, delta=None,
-                  deterministic=False, dq_accum=None):
-    """d_o fp16 [B*N, D] -> dqkv fp16 [B*N, 3D] (dq | dk | dv)."""
+                  deterministic=False, dq_accum=None, dbias=None):
+    """d_o fp16 [B*N, D] -> dqkv fp16 [B*N, 3D] (dq | dk | dv).  dbias fp32 [3D] (optional) += column sums
+    of dqkv, the to_qkv bias gradient."""
     _need_cuda(qkv, o, d_o, lse)
     assert qkv.dtype == torch.float16 and o.dtype == torch.float16 and d_o.dtype == torch.float16
     assert o.is_contiguous() and d_o.is_contiguous() and qkv.is_contiguous()
@@ -428,11 +433,13 @@ def attention_bwd(qkv, o, d_o, lse, B, H, N, *, scale=0.125, dqkv=None, delta=No
         dqkv = torch.empty_like(qkv)
     if delta is None:
         delta = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
+    if dbias is not None:
+        assert dbias.dtype == torch.float32 and dbias.is_contiguous() and dbias.numel() == 3 * H * 64
     if not deterministic and dq_accum is None:
         dq_accum = torch.empty(B * N, H * 64, dtype=torch.float32, device=qkv.device)
     with _timed("attn_bwd"):
         rc = lib().mv_attention_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(delta),
-                                    None if deterministic else _ptr(dq_accum), _ptr(dqkv), B,
+                                    None if deterministic else _ptr(dq_accum), _ptr(dqkv), _ptr(dbias), B,
                                     H, N, ctypes.c_float(scale), _stream())
     _check(rc, "mv_attention_bwd")
     return dqkv

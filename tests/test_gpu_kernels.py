@@ -70,6 +70,18 @@ def test_gemm_splitk_accumulate_and_epilogues():
     d = torch.empty(M, N, device=dev, dtype=torch.float16)
     mv.gemm(A, B, d, aux=gp, epilogue=mv.EPI_DGELU)
     assert relmax(d, (A.double() @ B.double().t()) * uu.grad) < 2e-3
+    # ... with the fused bias gradient: colsum += column sums of the stored values.  M = 514 has full tiles
+    # (fast epilogue, red.add.v4 per 32-row group) and a 2-row tail (generic epilogue)
+    for rows in (514, 512, 130):
+        cs = torch.full((N,), 2.0, device=dev)
+        d2 = torch.empty(rows, N, device=dev, dtype=torch.float16)
+        mv.gemm(A[:rows], B, d2, aux=gp[:rows], epilogue=mv.EPI_DGELU, colsum=cs)
+        assert torch.equal(d2, d[:rows])
+        assert relmax(cs - 2.0, ((A[:rows].double() @ B.double().t()) * gp[:rows].double()).sum(0)) < 1e-4
+    cs = torch.zeros(N, device=dev)
+    o3 = torch.empty(M, N, device=dev)
+    mv.gemm(A, B, o3, bias=bias, colsum=cs)              # no compile-time variant: generic epilogue
+    assert relmax(cs, lin.sum(0)) < 1e-5
     # residual broadcast over images (positional embedding)
     pos = torch.randn(257, N, device=dev)
     A2 = torch.randn(2 * 257, K, device=dev).half()
@@ -132,7 +144,12 @@ def test_attention_fwd_bwd(B, H, N, sn, request):
     do = torch.randn(B * N, D, device=dev).half()
     o.backward(do.double())
     for det in (False, True):           # fused dQ red.add pass / deterministic two-pass variant
-        dqkv = mv.attention_bwd(qkv, out, do, lse, B, H, N, deterministic=det)
+        dbias = torch.full((3 * D,), 0.5, device=dev)
+        dqkv = mv.attention_bwd(qkv, out, do, lse, B, H, N, deterministic=det, dbias=dbias)
+        # fused to_qkv bias gradient (+=): q from the stored dQ rows, v from the column sums of dO, k identically
+        # zero in exact arithmetic (short-sequence kernel); column sums of dqkv otherwise
+        ref_b = torch.stack([q.grad, k.grad, v.grad]).sum(dim=(1, 3)).reshape(3 * D)
+        assert relmax(dbias - 0.5, ref_b) < 3e-3
         gq = dqkv.double().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
         for got, ref in zip(gq, (q.grad, k.grad, v.grad)):
             assert relmax(got, ref) < 3e-3
