@@ -101,7 +101,7 @@ typedef struct {
     int q_res_exp, q_res_man;
     int accumulate;               /* split-K atomic accumulation into fp32 `out` */
     int rows_per_img;             /* residual row = m % rows_per_img when > 0 */
-    int tile_n;                   /* 0 = auto; 128 / 192 / 256 forces the tile width (testing) */
+    int tile_n;                   /* 0 = auto; 128 / 192 / 256 / 384 forces the tile width (testing; 384: split-K wgrad only) */
     float* colsum;                /* NULL, or fp32 [N]: colsum[n] += sum over m of the value stored to out[m, n] (fp32, before
                                    * the container rounding) with red.add — the bias gradient of the Linear whose output
                                    * gradient this GEMM produces, without a second pass over it.  CTA-pair kernel only. */

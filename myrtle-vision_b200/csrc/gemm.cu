@@ -52,6 +52,7 @@ struct GemmDev {
     int m_tiles, n_tiles, splits, kb_total, kb_per_split;
     int a_major, b_major;
     uint32_t idesc;
+    uint32_t idesc2;            // CTA-pair kernel, 384-wide tiles: the second (N = 128) MMA of every k step
     const float* bias;
     const float* residual; int ld_res;
     __half* aux; int ld_aux;
@@ -708,6 +709,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     constexpr int BK = 64, UMMA_K = 16;
     constexpr int kMnBoxBytes = BK * 128;      // one MN-major TMA box: 64 k-rows x 128 B (64 elements)
     constexpr int BNH = BN / 2;                // B rows staged by each CTA
+    // BN = 384 (split-K wgrad with MN-major B, outputs 384 wide): two MMAs per k step, N = 256 into accumulator
+    // columns [0, 256) and N = 128 into [256, 384) — a 256 x 128 tile needs 105 GB/s of operands per SM, more
+    // than the L2 delivers (~72 GB/s per SM), a 256 x 384 tile 59 GB/s.  One accumulator buffer (384 of the 512
+    // TMEM columns): the epilogue of these long-K units is a few per cent of their time.
+    constexpr int kAccBufs = 2 * BN <= 512 ? 2 : 1;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; offset arithmetic keeps the shared address space
@@ -749,7 +755,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 const int split = u % p.splits;
                 const int tile = u / p.splits;
                 const int m0 = (tile / p.n_tiles) * 256 + rank * 128;
-                const int n0 = (tile % p.n_tiles) * BN + rank * BNH;
+                const int nbase = (tile % p.n_tiles) * BN;
+                const int n0 = nbase + rank * BNH;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; kb++) {
@@ -769,8 +776,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         tma_load_2d_cg2(sb, &tmap_b, lead_full, kb * BK, n0);
                     } else {
 #pragma unroll
-                        for (int c = 0; c < BNH / 64; c++)
-                            tma_load_2d_cg2(sb + c * kMnBoxBytes, &tmap_b, lead_full, n0 + c * 64, kb * BK);
+                        for (int c = 0; c < BNH / 64; c++) {
+                            // 384-wide tiles: this CTA's half of the N = 256 MMA (2 chunks), then of the N = 128 MMA
+                            const int nc = BN == 384 ? (c < 2 ? nbase + rank * 128 + c * 64 : nbase + 256 + rank * 64)
+                                                     : n0 + c * 64;
+                            tma_load_2d_cg2(sb + c * kMnBoxBytes, &tmap_b, lead_full, nc, kb * BK);
+                        }
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -803,13 +814,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
                         const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
                         umma_f16_cg2(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (BN == 384) {
+                            const uint64_t bdesc2 = make_smem_desc_sw128(sb + 2 * kMnBoxBytes + k * b_kstep, b_lbo, 1024);
+                            umma_f16_cg2(tmem_d + 256, adesc, bdesc2, p.idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit_cg2(&empty_bar[stage], 3);     // stage free in both CTAs when the MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit_cg2(&tmem_full[acc], 3);           // both CTAs' epilogues may read accumulator acc
                 GEMM_TRACE(true, 0, 4, u);                     // all MMAs of the tile issued
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -850,7 +865,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     else epi_chunk_generic(p, w, taddr, release, mrow0, nc0);
                 }
                 GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 7, u);    // this warp's chunks done
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
             }
         };
 #define MV_EPI_CASE(id, ...)                                                                                   \
@@ -916,6 +931,12 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
         const int padded = ((a->N + bn - 1) / bn) * bn;
         if (best < 0 || padded < best) { best = padded; BN = bn; }
     }
+    // split-K wgrad into outputs whose width is a multiple of 384 but not of 256: 256 x 384 tiles (see gemm2_kernel).
+    // Measured at 65792 tokens (tools/probe_gemm_wgrad.py): [1536,384] 88 -> 66 us (1178 TFLOP/s), [1152,384]
+    // 81 -> 62 us, [384,384] 33 -> 28 us; widths that 256 also divides gain nothing ([384,1536] 83 -> 81 us) or lose
+    // to the larger split count ([384,768] 45 -> 55 us) and keep the 256-wide tiles unless tile_n asks for 384.
+    if (a->b_major == 1 && a->accumulate && a->N % 384 == 0 &&
+        (a->tile_n == 384 || (a->tile_n == 0 && a->N % 256 != 0))) { BN = 384; best = a->N; }
     MV_CHECK(best >= 0, "mv_gemm: tile_n %d not available for this operand layout", a->tile_n);
     CUtensorMap ta, tb;
     if (a->a_major == 0) { if (make_tmap_2d(&ta, a->A, a->a_dtype, a->M, a->K, a->lda, BM, BK)) return 1; }
@@ -945,7 +966,8 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.a_major = a->a_major; p.b_major = a->b_major;
     const int fmt = a->a_dtype == MV_BF16 ? 1 : 0;
-    p.idesc = make_idesc(fmt, fmt, a->a_major, a->b_major, 256, BN);
+    p.idesc = make_idesc(fmt, fmt, a->a_major, a->b_major, 256, BN == 384 ? 256 : BN);
+    p.idesc2 = make_idesc(fmt, fmt, a->a_major, a->b_major, 256, 128);
     p.bias = a->bias; p.residual = a->residual; p.ld_res = a->ld_res;
     p.aux = reinterpret_cast<__half*>(a->aux); p.ld_aux = a->ld_aux;
     p.out = a->out; p.ld_out = a->ld_out; p.out_dtype = a->out_dtype;
@@ -988,7 +1010,8 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     int rc;
     // 16 epilogue warps only where 12 would be unbalanced: BN = 256 is 8 chunks over 3 column groups (3 / 3 / 2)
     const bool heavy = (a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU) && BN == 256;
-    if (BN == 256) rc = heavy ? launch_gemm2<256, 16>(ta, tb, p, grid, st) : launch_gemm2<256, 12>(ta, tb, p, grid, st);
+    if (BN == 384) rc = launch_gemm2<384, 12>(ta, tb, p, grid, st);
+    else if (BN == 256) rc = heavy ? launch_gemm2<256, 16>(ta, tb, p, grid, st) : launch_gemm2<256, 12>(ta, tb, p, grid, st);
     else if (BN == 192) rc = heavy ? launch_gemm2<192, 16>(ta, tb, p, grid, st) : launch_gemm2<192, 12>(ta, tb, p, grid, st);
     else rc = heavy ? launch_gemm2<128, 16>(ta, tb, p, grid, st) : launch_gemm2<128, 12>(ta, tb, p, grid, st);
     if (rc) return rc;
@@ -1056,7 +1079,7 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     p.q_res = FloatFmt{a->q_res_exp, a->q_res_man};
     p.accumulate = a->accumulate;
     p.rows_per_img = a->rows_per_img;
-    p.variant = 0; p.colsum = nullptr;
+    p.variant = 0; p.colsum = nullptr; p.idesc2 = 0;
 
     // CTA pairs sharing B through TMA multicast: measured no faster on B200 (the bound is the per-SM
     // L2->SM ingest, which multicast does not reduce), so it is opt-in (cluster == 2)

@@ -90,6 +90,21 @@ def test_gemm_splitk_accumulate_and_epilogues():
     assert relmax(o2, A2.double() @ B.double().t() + bias.double() + pos.double().repeat(2, 1)) < 1e-5
 
 
+@pytest.mark.parametrize("T,No,Ki", [(8192, 1536, 384), (8200, 1152, 384), (4097, 384, 384), (8192, 384, 768),
+                                     (65792, 200, 384)])
+def test_gemm_wgrad_384_wide_tiles(T, No, Ki):
+    """Split-K wgrad into outputs 384 (or a multiple) wide: 256 x 384 cluster tiles, two MMAs (N = 256, N = 128)
+    per k step into one accumulator.  Against fp64 and against the 128-wide tiling, row tails included."""
+    import mv_native as mv
+    torch.manual_seed(T + No)
+    dY = torch.randn(T, No, device=dev).half(); X = torch.randn(T, Ki, device=dev).half()
+    ref = dY.double().t() @ X.double()
+    for tile_n in (0, 384, 128):
+        out = torch.full((No, Ki), 1.0, device=dev)
+        mv.gemm(dY, X, out, a_major=1, b_major=1, accumulate=True, tile_n=tile_n)
+        assert relmax(out - 1.0, ref) < 1e-5, tile_n
+
+
 def test_gemm_rejects_mixed_operand_types():
     import mv_native as mv
     A = torch.zeros(128, 64, device=dev).half(); B = torch.zeros(128, 64, device=dev).bfloat16()
