@@ -105,6 +105,7 @@ typedef struct {
     float* colsum;                /* NULL, or fp32 [N]: colsum[n] += sum over m of the value stored to out[m, n] (fp32, before
                                    * the container rounding) with red.add — the bias gradient of the Linear whose output
                                    * gradient this GEMM produces, without a second pass over it.  CTA-pair kernel only. */
+    int transpose_out;            /* accumulate only: out is [N, M] (pitch ld_out) and receives out[n, m] += acc[m, n] */
     int cluster;                  /* 0 = CTA-pair kernel (tcgen05 cta_group::2, 256 x tile_n cluster tiles; 16-bit operands);
                                    * 1 = single-CTA kernel (always used for tf32); 2 = single-CTA MMAs with the B tile
                                    * TMA-multicast across a CTA pair (kept for comparison) */

@@ -53,6 +53,7 @@ struct GemmDev {
     int a_major, b_major;
     uint32_t idesc;
     uint32_t idesc2;            // CTA-pair kernel, 384-wide tiles: the second (N = 128) MMA of every k step
+    int transpose_out;          // CTA-pair kernel, accumulate: out[n, m] += acc[m, n]
     const float* bias;
     const float* residual; int ld_res;
     __half* aux; int ld_aux;
@@ -649,6 +650,26 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
     __syncwarp();                                      // staging is rewritten by the next chunk
 }
 
+// Split-K accumulation into the TRANSPOSED output, out[n, m] += acc[m, n]: the staged 32 x 32 chunk is read
+// column-wise (lane = column, conflict-free with the 36-float pitch), so every lane adds 4 consecutive m of one
+// output row with one red.add.v4.  Lets a wgrad whose natural output is 384 tall and wide (fc2: [384, 1536]) run
+// as its transpose on 256 x 384 tiles without padding rows.
+__device__ __forceinline__ void epi_chunk_acc_t(const GemmDev& p, const EpiWarp& w, uint32_t taddr, uint32_t release,
+                                                int mrow0, int nc0) {
+    stage_chunk(w, taddr, release);
+    float* o = reinterpret_cast<float*>(p.out) + int64_t(nc0 + w.lane) * p.ld_out + mrow0;
+    const uint32_t sp = w.stg_s + w.lane * 4;
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j]) : "r"(sp + (4 * g + j) * kStgPitch * 4));
+        red_add_v4(o + 4 * g, v[0], v[1], v[2], v[3]);
+    }
+    __syncwarp();
+}
+
 // Generic path: tails in M / N, unaligned pitches, bf16 / second outputs.  Same arithmetic, rolled loops.
 __device__ __forceinline__ void epi_chunk_generic(const GemmDev& p, const EpiWarp& w, uint32_t taddr, uint32_t release,
                                                int mrow0, int nc0) {
@@ -665,8 +686,9 @@ __device__ __forceinline__ void epi_chunk_generic(const GemmDev& p, const EpiWar
             const float4 a4 = *reinterpret_cast<const float4*>(w.stg + row * kStgPitch + w.lc);
             float v[4] = {a4.x, a4.y, a4.z, a4.w};
             if (p.accumulate) {
-                float* o = reinterpret_cast<float*>(p.out) + int64_t(m) * p.ld_out + n;
-                for (int j = 0; j < 4; j++) if (j < nvalid) atomicAdd(o + j, v[j]);
+                float* o = reinterpret_cast<float*>(p.out) + (p.transpose_out ? int64_t(n) * p.ld_out + m : int64_t(m) * p.ld_out + n);
+                const int64_t step = p.transpose_out ? p.ld_out : 1;
+                for (int j = 0; j < 4; j++) if (j < nvalid) atomicAdd(o + j * step, v[j]);
                 continue;
             }
             if (p.bias != nullptr) for (int j = 0; j < 4; j++) if (j < nvalid) v[j] += __ldg(p.bias + n + j);
@@ -887,6 +909,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             MV_EPI_CASE(9, MV_F16, MV_EPI_GELU, 0, 1, 1, false)
             MV_EPI_CASE(10, MV_F32, MV_EPI_NONE, 2, 1, 1, false)
             MV_EPI_CASE(11, MV_F16, MV_EPI_DGELU, 0, 0, 0, false, true)
+            case 12:
+                walk([&](uint32_t taddr, uint32_t release, int mrow0, int nc0) { epi_chunk_acc_t(p, w, taddr, release, mrow0, nc0); });
+                break;
             default:       // variant 0: every chunk takes the generic path (`fast` is false)
                 walk([&](uint32_t, uint32_t, int, int) {});
                 break;
@@ -976,6 +1001,7 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     p.q_out = FloatFmt{a->q_out_exp, a->q_out_man};
     p.q_res = FloatFmt{a->q_res_exp, a->q_res_man};
     p.accumulate = a->accumulate;
+    p.transpose_out = a->transpose_out;
     p.rows_per_img = a->rows_per_img;
     p.colsum = a->accumulate ? nullptr : a->colsum;
     // epilogue variant (epi_chunk<> instantiations in gemm2_kernel); anything else runs the generic path
@@ -997,7 +1023,7 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
             {7, MV_F32, MV_EPI_NONE, 2, 0, 0, 0}, {9, MV_F16, MV_EPI_GELU, 0, 1, 1, 0}, {10, MV_F32, MV_EPI_NONE, 2, 1, 1, 0},
             {11, MV_F16, MV_EPI_DGELU, 0, 0, 0, 1}};
         int v = 0;
-        if (ok && a->accumulate) v = 8;
+        if (ok && a->accumulate) v = a->transpose_out ? 12 : 8;
         else if (ok)
             for (const Row& r : table)
                 if (r.out == a->out_dtype && r.epi == a->epilogue && r.res == res && r.qo == qo && r.qr == qr && r.cs == cs) v = r.id;
@@ -1026,6 +1052,8 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     const bool tf32 = a->a_dtype == MV_F32;
     MV_CHECK(a->a_dtype == a->b_dtype, "mv_gemm: A and B must share one element type (tcgen05 kind::f16 rejects f16 x bf16)");
     if (a->accumulate) MV_CHECK(a->out_dtype == MV_F32, "mv_gemm: accumulate needs an fp32 output");
+    MV_CHECK(!a->transpose_out || (a->accumulate && !tf32 && a->cluster == 0),
+             "mv_gemm: transpose_out needs accumulate on the CTA-pair kernel (16-bit operands, cluster == 0)");
     if (a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU) MV_CHECK(a->aux != nullptr, "mv_gemm: GELU epilogues need aux");
     if (!tf32 && a->cluster == 0) return gemm2_host(a, stream);      // CTA-pair kernel (default)
     MV_CHECK(a->colsum == nullptr, "mv_gemm: colsum is only fused into the CTA-pair kernel (16-bit operands, cluster == 0)");
@@ -1079,7 +1107,7 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     p.q_res = FloatFmt{a->q_res_exp, a->q_res_man};
     p.accumulate = a->accumulate;
     p.rows_per_img = a->rows_per_img;
-    p.variant = 0; p.colsum = nullptr; p.idesc2 = 0;
+    p.variant = 0; p.colsum = nullptr; p.idesc2 = 0; p.transpose_out = 0;
 
     // CTA pairs sharing B through TMA multicast: measured no faster on B200 (the bound is the per-SM
     // L2->SM ingest, which multicast does not reduce), so it is opt-in (cluster == 2)

@@ -218,7 +218,8 @@ class EncoderEngine:
             du = torch.empty(M, Mm, dtype=f16, device=dev)
             # fc1's bias gradient (column sums of du) rides in the epilogue
             mv.gemm(dx_h, wq[b0 + 10][1], du, aux=u, epilogue=mv.EPI_DGELU, colsum=g[b0 + 9].view(-1))
-            mv.gemm(dx_h, h, g[b0 + 10], a_major=1, b_major=1, accumulate=True)
+            # fc2's [D, 4D] gradient as its transpose h^T dx: 256 x 384 tiles over 4D rows instead of 1.5 padded 256-row tiles
+            mv.gemm(h, dx_h, g[b0 + 10], a_major=1, b_major=1, accumulate=True, transpose_out=True)
             dxn2 = torch.empty(M, D, dtype=f16, device=dev)
             mv.gemm(du, wq[b0 + 8][1], dxn2, tag="dgrad")
             mv.gemm(du, xn2, g[b0 + 8], a_major=1, b_major=1, accumulate=True)

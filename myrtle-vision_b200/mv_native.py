@@ -40,6 +40,7 @@ class GemmArgs(ctypes.Structure):
         ("rows_per_img", ctypes.c_int),
         ("tile_n", ctypes.c_int),
         ("colsum", ctypes.c_void_p),
+        ("transpose_out", ctypes.c_int),
         ("cluster", ctypes.c_int),
     ]
 
@@ -204,7 +205,7 @@ def quantize_weight(w, exp, man, out_dtype=torch.float16, transpose=True, out=No
 # ------------------------------------------------------------------------ GEMM
 def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out2=None,
          epilogue=EPI_NONE, q_out=None, q_res=None, accumulate=False, rows_per_img=0,
-         M=None, N=None, K=None, tag=None, tile_n=0, cluster=0, colsum=None):
+         M=None, N=None, K=None, tag=None, tile_n=0, cluster=0, colsum=None, transpose_out=False):
     """out[M,N] = A . B^T over K with the fused epilogue of mv_gemm (include/mv_b200.h).
     a_major/b_major = 0: operand is [M|N, K] (K contiguous); 1: operand is [K, M|N]."""
     _need_cuda(A, B, out)
@@ -238,6 +239,7 @@ def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None,
     a.rows_per_img = rows_per_img
     a.tile_n = tile_n
     a.cluster = cluster
+    a.transpose_out = int(bool(transpose_out))
     if colsum is not None:
         assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == N
         a.colsum = colsum.data_ptr()

@@ -103,6 +103,10 @@ def test_gemm_wgrad_384_wide_tiles(T, No, Ki):
         out = torch.full((No, Ki), 1.0, device=dev)
         mv.gemm(dY, X, out, a_major=1, b_major=1, accumulate=True, tile_n=tile_n)
         assert relmax(out - 1.0, ref) < 1e-5, tile_n
+    # the same product accumulated into the transposed output: out_t[n, m] += acc[m, n]
+    out_t = torch.full((Ki, No), 1.0, device=dev)
+    mv.gemm(dY, X, out_t, a_major=1, b_major=1, accumulate=True, transpose_out=True)
+    assert relmax(out_t - 1.0, ref.t()) < 1e-5
 
 
 def test_gemm_rejects_mixed_operand_types():

@@ -25,5 +25,8 @@ for name, no, ki in (("fc1 [1536,384]", 1536, 384), ("qkv [1152,384]", 1152, 384
             line.append("tile_n %3d: %.4f ms (%4.0f TFLOP/s)" % (tn, ms, 2.0 * T * no * ki / ms / 1e9))
         except mv.MvError:
             line.append("tile_n %3d: n/a" % tn)
+    out_t = torch.zeros(ki, no, device=dev)
+    ms = timeit(lambda i: mv.gemm(X[i % 3], dY[i % 3], out_t, a_major=1, b_major=1, accumulate=True, transpose_out=True))
+    line.append("as transpose: %.4f ms (%4.0f TFLOP/s)" % (ms, 2.0 * T * no * ki / ms / 1e9))
     print(name, " | ".join(line))
     del dY, X
