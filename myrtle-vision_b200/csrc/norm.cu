@@ -354,14 +354,15 @@ __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, OutT* __restrict__ out, int B, int C, int H, int W,
                 int P, FloatFmt q_in, int cls_slot) {
     // One CTA per (b, patch row gy).  Phase 1 reads the C x P image rows (W contiguous floats each,
-    // 16-byte loads), quantises and parks them in shared memory as [c][ph][w]; phase 2 walks the
-    // gw * pdim output elements of this patch row — one contiguous span of `out` — so the (ph, pw, c)
-    // interleave happens in shared memory and every global store is a full, consecutive sector.
-    extern __shared__ uint8_t patch_smem[];
+    // 16-byte loads), quantises and scatters them into shared memory at their OUTPUT position
+    // [gx][ph][pw][c] (the index arithmetic is per 16-byte load, not per element); phase 2 copies the
+    // gw * pdim elements of this patch row — one contiguous span of `out` — with 16-byte vectors.
+    extern __shared__ __align__(16) uint8_t patch_smem[];
     OutT* sm = reinterpret_cast<OutT*>(patch_smem);
     const int gw = W / P, gh = H / P;
     const int b = blockIdx.x / gh, gy = blockIdx.x % gh;
     const int pdim = P * P * C;
+    const int PC = P * C;
     const int64_t rows_per_img = int64_t(gh) * gw + cls_slot;
     OutT* obase = out + (int64_t(b) * rows_per_img + cls_slot + int64_t(gy) * gw) * pdim;
     if (cls_slot && gy == 0) {          // row b*N + 0 is the (zero) slot of the class token
@@ -376,29 +377,25 @@ patchify_kernel(const float* __restrict__ img, OutT* __restrict__ out, int B, in
         float4 v = __ldcs(reinterpret_cast<const float4*>(img + ((int64_t(b) * C + c) * H + gy * P + ph) * W) + wv);
         if (mode == 1) v = fq_half4_f32(v);
         else { v.x = fq_apply(v.x, mode, q_in); v.y = fq_apply(v.y, mode, q_in); v.z = fq_apply(v.z, mode, q_in); v.w = fq_apply(v.w, mode, q_in); }
-        OutT* d = sm + r * W + wv * 4;
-        d[0] = OutT(v.x); d[1] = OutT(v.y); d[2] = OutT(v.z); d[3] = OutT(v.w);
+        const int w = wv * 4;
+        if ((P & 3) == 0) {                                // the four pixels share a patch
+            OutT* d = sm + (w / P) * pdim + ph * PC + (w % P) * C + c;
+            d[0] = OutT(v.x); d[C] = OutT(v.y); d[2 * C] = OutT(v.z); d[3 * C] = OutT(v.w);
+        } else {
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) sm[((w + j) / P) * pdim + ph * PC + ((w + j) % P) * C + c] = OutT(e[j]);
+        }
     }
     __syncthreads();
     const int total = gw * pdim;
-    const int PC = P * C;
-    if (sizeof(OutT) == 2 && (pdim & 1) == 0) {
-        for (int o = threadIdx.x * 2; o < total; o += blockDim.x * 2) {
-            OutT pair[2];
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int gx = (o + e) / pdim, r = (o + e) % pdim;
-                const int ph = r / PC, pw = (r % PC) / C, c = r % C;
-                pair[e] = sm[(c * P + ph) * W + gx * P + pw];
-            }
-            *reinterpret_cast<uint32_t*>(obase + o) = *reinterpret_cast<const uint32_t*>(pair);
-        }
+    constexpr int kVec = 16 / int(sizeof(OutT));
+    const bool vec_ok = (total % kVec) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0;
+    if (vec_ok) {
+        for (int o = threadIdx.x; o < total / kVec; o += blockDim.x)
+            reinterpret_cast<uint4*>(obase)[o] = reinterpret_cast<const uint4*>(sm)[o];
     } else {
-        for (int o = threadIdx.x; o < total; o += blockDim.x) {
-            const int gx = o / pdim, r = o % pdim;
-            const int ph = r / PC, pw = (r % PC) / C, c = r % C;
-            obase[o] = sm[(c * P + ph) * W + gx * P + pw];
-        }
+        for (int o = threadIdx.x; o < total; o += blockDim.x) obase[o] = sm[o];
     }
 }
 

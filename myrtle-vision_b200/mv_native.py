@@ -318,8 +318,9 @@ def patchify_q(img, patch, q_in=None, out_dtype=torch.float16, cls_slot=False):
     rows = B * ((H // patch) * (W // patch) + (1 if cls_slot else 0))
     out = torch.empty(rows, patch * patch * C, dtype=out_dtype, device=img.device)
     q = _fmt(q_in)
-    _check(lib().mv_patchify_q(_ptr(img), _ptr(out), _DT[out_dtype], B, C, H, W, patch, q[0], q[1],
-                               int(bool(cls_slot)), _stream()), "mv_patchify_q")
+    with _timed("patchify"):
+        _check(lib().mv_patchify_q(_ptr(img), _ptr(out), _DT[out_dtype], B, C, H, W, patch, q[0], q[1],
+                                   int(bool(cls_slot)), _stream()), "mv_patchify_q")
     return out
 
 

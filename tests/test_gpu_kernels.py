@@ -185,6 +185,13 @@ def test_patchify_and_colsum():
     assert torch.equal(pt.float(), mv.float_quantize(ref, 5, 10))
     pc = mv.patchify_q(img, 16, q_in=(5, 10), cls_slot=True).reshape(4, 25, 768)
     assert torch.equal(pc[:, 1:].reshape(-1, 768), pt) and pc[:, 0].abs().max() == 0
+    for (C, Hh, Ww, P, fmt, dt) in [(3, 32, 48, 8, (5, 10), torch.float16), (1, 12, 24, 6, (8, 10), torch.float32),
+                                    (4, 256, 256, 16, None, torch.float32)]:
+        im = torch.randn(2, C, Hh, Ww, device=dev)
+        got = mv.patchify_q(im, P, q_in=fmt, out_dtype=dt)
+        want = im.reshape(2, C, Hh // P, P, Ww // P, P).permute(0, 2, 4, 3, 5, 1).reshape(-1, P * P * C)
+        want = mv.float_quantize(want.contiguous(), *fmt) if fmt else want
+        assert torch.equal(got.float(), want)
     a = torch.randn(8000, 1152, device=dev).half(); o = torch.zeros(1152, device=dev)
     mv.colsum(a, o)
     assert relmax(o, a.double().sum(0)) < 1e-5

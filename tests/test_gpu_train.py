@@ -53,6 +53,32 @@ def test_entry_point_trains(task, fmt, size, classes, tmp_path):
     assert len(more) == 2 and more[-1] < history[0]
 
 
+@pytest.mark.parametrize("task,size,classes", [("classification", 80, 5), ("segmentation", 96, 4), ("detection", 176, 3)])
+def test_eval_cli_on_a_trained_checkpoint(task, size, classes, tmp_path, capsys):
+    """{classification,segmentation,detection}/test.py: checkpoint -> eval forward -> the task's report."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = config(task, tmp_path, "FP16_32", size, classes)
+    from myrtle_vision.utils.trainer import train_deit
+    train_deit(0, 1, copy.deepcopy(cfg), max_iterations=6)
+    spec = importlib.util.spec_from_file_location("test_cli_%s" % task,
+                                                  os.path.join(root, "myrtle-vision_b200", task, "test.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg2 = copy.deepcopy(cfg)
+    with pytest.raises(AssertionError, match="checkpoint path"):
+        mod.test_deit(copy.deepcopy(cfg2))
+    cfg2["train_config"]["checkpoint_path"] = os.path.join(cfg["train_config"]["output_directory"], "vit_000005")
+    res = mod.test_deit(cfg2)
+    out = capsys.readouterr().out
+    if task == "classification":
+        assert 0.0 <= res["accuracy"] <= 1.0 and "precision" in out
+    elif task == "segmentation":
+        assert 0.0 <= res["miou"] <= 1.0 and "mIoU is:" in out and res["per_class_iou"].numel() == classes
+    else:
+        assert "IoU=0.50:0.95" in out and (res["AP"] != res["AP"] or 0.0 <= res["AP"] <= 1.0)
+
+
 def test_ptq_eval_flow_from_an_fp32_checkpoint(tmp_path):
     """classification/test_quantize.py — FP32 checkpoint -> prepare_qat -> convert -> eval."""
     import importlib.util

@@ -207,3 +207,26 @@ def test_miou_matches_the_histogram_definition():
         tu += ap + al - inter
     assert torch.allclose(m.get_per_class_iou(), ti / tu)
     assert abs(m.get_miou() - float((ti / tu).mean())) < 1e-12
+
+
+def test_box_average_precision():
+    """COCO-style AP of detection/test.py (myrtle_vision/utils/evaluate.py) on hand-checked cases."""
+    import torch
+    from myrtle_vision.utils.evaluate import box_average_precision, pairwise_iou
+    gt = [{"labels": torch.tensor([0, 1, 1]),
+           "boxes": torch.tensor([[0., 0, 10, 10], [20, 20, 40, 40], [50, 50, 60, 70]])}]
+    perfect = [{"scores": torch.tensor([0.9, 0.8, 0.7, 0.1]), "labels": torch.tensor([0, 1, 1, 1]),
+                "boxes": torch.tensor([[0., 0, 10, 10], [20, 20, 40, 40], [50, 50, 60, 70], [0, 0, 5, 5]])}]
+    res = box_average_precision(perfect, gt, 3)
+    assert res["AP"] == 1.0 and res["AP50"] == 1.0          # the low-score false positive comes after full recall
+    # class 0 localised at IoU 0.8 (a hit for 7 of the 10 thresholds), class 1 missed entirely
+    loose = [{"scores": torch.tensor([0.9, 0.8]), "labels": torch.tensor([0, 1]),
+              "boxes": torch.tensor([[0., 0, 10, 8], [100, 100, 110, 110]])}]
+    res = box_average_precision(loose, gt, 3)
+    assert abs(res["per_class"][0] - 0.7) < 1e-9 and res["per_class"][1] == 0.0
+    assert abs(res["AP"] - 0.35) < 1e-9 and abs(res["AP50"] - 0.5) < 1e-9
+    # a confident false positive ahead of the true positive halves the precision at every recall level
+    fp_first = [{"scores": torch.tensor([0.9, 0.5]), "labels": torch.tensor([0, 0]),
+                 "boxes": torch.tensor([[30., 30, 35, 35], [0, 0, 10, 10]])}]
+    assert abs(box_average_precision(fp_first, gt, 3)["per_class"][0] - 0.5) < 1e-9
+    assert abs(float(pairwise_iou(torch.tensor([[0., 0, 10, 10]]), torch.tensor([[0., 0, 10, 8]]))) - 0.8) < 1e-6
