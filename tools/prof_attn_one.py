@@ -9,9 +9,10 @@ D = H * 64
 torch.manual_seed(0)
 qkv = torch.randn(B * N, 3 * D, device="cuda").half()
 do = torch.randn(B * N, D, device="cuda").half()
+dbias = torch.zeros(3 * D, device="cuda")
 for _ in range(3):
     out, lse = mv.attention_fwd(qkv, B, H, N, q_out=(5, 10))
     if "bwd" in sys.argv:
-        mv.attention_bwd(qkv, out, do, lse, B, H, N)
+        mv.attention_bwd(qkv, out, do, lse, B, H, N, dbias=dbias)     # with the fused to_qkv bias gradient, as in the step
 torch.cuda.synchronize()
 print("ok")
