@@ -141,6 +141,11 @@ int mv_cls_rows(const float* cls, const float* pos_q, float* x, int B, int n_tok
                 int q_man, void* stream);
 /* fp32 -> fp16 (saturating) / bf16 copy of n elements (n % 4 == 0) */
 int mv_convert_f32(const float* in, void* out, int out_dtype, int64_t n, void* stream);
+/* out_f32[i] = in[i] * s and / or out_f16[i] = fp16_sat(in[i] * s) for n elements (n % 4 == 0; either output may
+ * be NULL, out_f32 may alias in), s = *scale_dev or, with invert != 0, its reciprocal.  The backward's power-of-two
+ * gradient scale is chosen on the device (no host sync); this applies / removes it in one pass. */
+int mv_scale_f32(const float* in, const float* scale_dev, int invert, float* out_f32, void* out_f16, int64_t n,
+                 void* stream);
 /* fp16 / fp32 in[rows, cols] (row pitch ld elements) times `mul` -> fp32 copy out[rows, cols] and / or
  * fp32 transpose out_t[cols, rows] with row pitch ld_t >= rows (either may be NULL).  The 32-bit formats (q_format TF32 / FP32) run
  * their contractions as kind::tf32 on K-major fp32 operands; this prepares dY^T / X^T for wgrad and

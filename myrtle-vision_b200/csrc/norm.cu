@@ -431,6 +431,24 @@ convert_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t n4)
     }
 }
 
+// out32 = in * s and / or out16 = fp16(in * s), s = *scale_dev or its reciprocal (a power of two: exact).
+// The loss-scale style gradient scale lives in device memory, so no host synchronisation.
+__global__ void __launch_bounds__(256)
+scale_kernel(const float* __restrict__ in, const float* __restrict__ scale_dev, int invert, float* __restrict__ out32,
+             __half* __restrict__ out16, int64_t n4) {
+    const float s = invert ? 1.0f / __ldg(scale_dev) : __ldg(scale_dev);
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = __ldcs(reinterpret_cast<const float4*>(in) + i);
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        if (out32 != nullptr) reinterpret_cast<float4*>(out32)[i] = v;
+        if (out16 != nullptr) {
+            __half2 lo = __floats2half2_rn(sat16(v.x), sat16(v.y)), hi = __floats2half2_rn(sat16(v.z), sat16(v.w));
+            reinterpret_cast<uint2*>(out16)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+    }
+}
+
 template <int NV>
 static int launch_ln_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, void* y,
                          int64_t ld_y, int y_dtype, float* mean, float* rstd, int rows, int D,
@@ -623,6 +641,20 @@ extern "C" int mv_convert_f32(const float* in, void* out, int out_dtype, int64_t
     else MV_CHECK(false, "mv_convert_f32: bad dtype");
     g_launches++;
     return check_cuda(cudaGetLastError(), "convert launch");
+}
+
+extern "C" int mv_scale_f32(const float* in, const float* scale_dev, int invert, float* out_f32, void* out_f16, int64_t n,
+                            void* stream) {
+    MV_CHECK(in && scale_dev && (out_f32 || out_f16), "mv_scale_f32: null pointer");
+    MV_CHECK(n % 4 == 0, "mv_scale_f32: n must be a multiple of 4");
+    if (n == 0) return 0;
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    scale_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, scale_dev, invert, out_f32,
+                                                                           reinterpret_cast<__half*>(out_f16), n4);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "scale launch");
 }
 
 extern "C" int mv_widen_transpose(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out,

@@ -203,10 +203,9 @@ class EncoderEngine:
 
         # power-of-two gradient scale chosen on the device (no host sync)
         gx = gx.reshape(M, D)
-        amax = gx.abs().amax().clamp_min(1e-30)
+        amax = torch.linalg.vector_norm(gx, float("inf")).clamp_min(1e-30)          # one reduction, no |gx| temporary
         S = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).clamp(2.0 ** -60, 2.0 ** 60)
-        dx = gx * S
-        dx_h = mv.convert_f32(dx, f16)
+        dx, dx_h = mv.scale_f32(gx, S, want_f16=True)                             # fp32 master and fp16 operand in one pass
         self.gflat.zero_()
         last = cfg.depth - 1
         mv.colsum(dx, g[2 + PER_LAYER * last + 11].view(-1))               # fc2 bias of the last block
@@ -256,12 +255,13 @@ class EncoderEngine:
         if self.reducer is not None:
             self.reducer.reduce_slice(self.gflat[:self.offsets[2]], inv)
             self.reducer.wait()
-        else:
-            self.gflat.mul_(inv)
         dpos = dpos * inv
         dcls = dpos[:, 0:1, :].clone()
         # hand autograd its own copy: self.gflat is reused (zeroed) by the next backward
-        out = self.gflat.clone()
+        if self.reducer is not None:
+            out = self.gflat.clone()
+        else:
+            out, _ = mv.scale_f32(self.gflat, S, invert=True)                     # un-scale and copy in one pass
         grads = [out[self.offsets[i]:self.offsets[i] + p.numel()].view_as(p)
                  for i, p in enumerate(self.params)]
         return dpos, dcls, grads

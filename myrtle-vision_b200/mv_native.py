@@ -340,6 +340,20 @@ def convert_f32(x, out_dtype=torch.float16, out=None):
     return out
 
 
+def scale_f32(x, scale, *, invert=False, out=None, out_h=None, want_f32=True, want_f16=False):
+    """(x * scale [or / scale]) as fp32 and / or saturating fp16, `scale` a 0-dim / 1-element device tensor."""
+    _need_cuda(x, scale)
+    assert x.dtype == torch.float32 and scale.dtype == torch.float32 and scale.numel() == 1
+    x = x.contiguous()
+    if out is None and want_f32:
+        out = torch.empty_like(x)
+    if out_h is None and want_f16:
+        out_h = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _check(lib().mv_scale_f32(_ptr(x), _ptr(scale), int(bool(invert)), _ptr(out), _ptr(out_h),
+                              ctypes.c_int64(x.numel()), _stream()), "mv_scale_f32")
+    return out, out_h
+
+
 def widen_transpose(x2d, *, want_copy=False, want_t=True, mul=1.0, padded=False):
     """fp16/fp32 [rows, cols] -> (fp32 copy or None, fp32 transpose [cols, rows] or None).  The
     transpose is a view of a buffer whose row pitch is padded to 16 bytes (TMA global stride rule)."""

@@ -177,6 +177,18 @@ def test_attention_fwd_bwd(B, H, N, sn, request):
     assert relmax(outq, o) < 2e-3
 
 
+def test_scale_f32():
+    import mv_native as mv
+    x = torch.randn(1000, 384, device=dev) * 300
+    S = torch.tensor(2.0 ** 9, device=dev)
+    y, yh = mv.scale_f32(x, S, want_f16=True)
+    assert torch.equal(y, x * 512) and torch.equal(yh, (x * 512).clamp(-65504, 65504).half())
+    z, none = mv.scale_f32(y, S, invert=True)
+    assert torch.equal(z, x) and none is None
+    mv.scale_f32(y, S.reshape(1), invert=True, out=y)                  # in place
+    assert torch.equal(y, x)
+
+
 def test_patchify_and_colsum():
     import mv_native as mv
     img = torch.randn(4, 3, 64, 96, device=dev)
