@@ -23,6 +23,8 @@ Gradients travel as fp16 tensor-core operands scaled by a power of two S chosen 
 the incoming gradient (the reference itself trains under GradScaler(65536), classification/
 train.py:167); parameter gradients are un-scaled in fp32 before they are returned.
 """
+import os
+
 import torch
 
 import mv_native as mv
@@ -69,6 +71,7 @@ class EncoderEngine:
         self.gviews = [self.gflat[self.offsets[i]:self.offsets[i] + sizes[i]].view_as(p)
                        for i, p in enumerate(self.params)]
         self.reducer = None      # set by parallel.DataParallel: called with flat gradient slices
+        self.bucket_blocks = max(1, int(os.environ.get("MV_DP_BUCKET_BLOCKS", "3")))   # encoder blocks per all-reduce
         # True once an optimizer (utils/fused_adamw.FusedAdamW) emits q(W) / q(W)^T itself after every
         # update: a CUDA-graph capture then leaves the re-quantisation out of the graph
         self.external_requant = False
@@ -238,8 +241,11 @@ class EncoderEngine:
             dx, dx_h = mv.layernorm_q_bwd(dxn1, x, prm[b0], mean1, rstd1, dres=dx1, q_in=fmt,
                                           dgamma=g[b0], dbeta=g[b0 + 1], dbias_prev=prev_bias,
                                           dx=dx, dx_f16=dx_h)
-            if self.reducer is not None:
-                lo, hi = self.offsets[b0], self.offsets[b0 + PER_LAYER]
+            if self.reducer is not None and l % self.bucket_blocks == 0:
+                # one all-reduce per bucket of `bucket_blocks` encoder blocks (their gradient slices are contiguous),
+                # issued as soon as the bucket's last wgrad is enqueued
+                top = min(cfg.depth, l + self.bucket_blocks)
+                lo, hi = self.offsets[b0], self.offsets[2 + PER_LAYER * top]
                 self.reducer.reduce_slice(self.gflat[lo:hi], 1.0 / S)
         # ---- patch embedding: dW = dx^T patches (cls rows of `patches` are zero)
         mv.gemm(dx_h, saved["patches"], g[0], a_major=1, b_major=1, accumulate=True)
@@ -414,8 +420,11 @@ class EncoderEngine:
             dx, _ = mv.layernorm_q_bwd(dxn1, x, prm[b0], mean1, rstd1, dres=dx1, q_in=fmt,
                                        dgamma=g[b0], dbeta=g[b0 + 1], dbias_prev=prev_bias,
                                        want_f16=False, dx=dx)
-            if self.reducer is not None:
-                lo, hi = self.offsets[b0], self.offsets[b0 + PER_LAYER]
+            if self.reducer is not None and l % self.bucket_blocks == 0:
+                # one all-reduce per bucket of `bucket_blocks` encoder blocks (their gradient slices are contiguous),
+                # issued as soon as the bucket's last wgrad is enqueued
+                top = min(cfg.depth, l + self.bucket_blocks)
+                lo, hi = self.offsets[b0], self.offsets[2 + PER_LAYER * top]
                 self.reducer.reduce_slice(self.gflat[lo:hi], 1.0 / S)
         wgrad(dx, saved["patches"], g[0])
         return self._finish_backward(dx, S, B, N, D)
