@@ -15,7 +15,8 @@ Prints ONE JSON line (rank 0).  `value` has inputs resident in HBM; `e2e` copies
 batch from pinned host memory and reads the loss back.  `roofline` describes the dominant kernel
 class of the step, timed with CUDA events inside the timed region; `cpu_baseline` times the
 oracle port of the reference (stock PyTorch CPU ops + the C restatement of QPyTorch quant_cpu)
-on a bounded sample on this box's host cores.
+on a bounded sample on this box's host cores.  `quant_kernels` (N=1) is the second half of the
+metric: HBM GB/s of the standalone fake-quant kernel on 2^28 fp32 values, nearest and stochastic.
 """
 import argparse
 import json
@@ -326,6 +327,33 @@ def run_b200(args):
                                 "avg_launch_ms": avg_ms, "algorithmic_per_launch": work}
             breakdown[name] = entry
 
+    # second half of BASELINE.json's metric: HBM GB/s of the standalone fake-quant kernels (SURVEY.md §8d input:
+    # 2^28 fp32 = 1 GiB, randn * exp(U(-12, 8)) so that normal, subnormal and saturating branches all run;
+    # 8 algorithmic bytes per element, timed with CUDA events, 2 GiB per launch >> 126 MB L2)
+    quant = None
+    if world == 1 and not args.no_quant_bench:
+        gq = torch.Generator(device=dev).manual_seed(1234)
+        nq = 1 << 28
+        xq = torch.randn(nq, device=dev, generator=gq)
+        xq.mul_(torch.exp(torch.empty(nq, device=dev).uniform_(-12, 8, generator=gq)))
+        oq = torch.empty_like(xq)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        quant = {"unit": "GB/s", "elements": nq, "bytes_per_element": 8, "peak": hbm_peak,
+                 "peak_source": "MEASURED_PEAKS.json (hbm_gbs)" if peaks else "fallback"}
+        for label, kw in (("float(5,10) nearest", dict(rounding="nearest")),
+                          ("float(5,10) stochastic", dict(rounding="stochastic", seed=1234, offset=0))):
+            for _ in range(3):
+                mv_native.float_quantize(xq, 5, 10, out=oq, **kw)
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(10):
+                mv_native.float_quantize(xq, 5, 10, out=oq, **kw)
+            q1.record()
+            torch.cuda.synchronize()
+            gbs = 8.0 * nq * 10 / q0.elapsed_time(q1) / 1e6
+            quant[label] = {"value": gbs, "frac": gbs / hbm_peak}
+        del xq, oq
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         ips, ms_cpu, threads = cpu_port_throughput(8, 2, 1, args.q_format)
@@ -355,6 +383,7 @@ def run_b200(args):
         "model_tflops": value * fl / 1e12,
         "roofline": roofline,
         "kernels": breakdown,
+        "quant_kernels": quant,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -373,6 +402,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--no-quant-bench", action="store_true", help="skip the fake-quant kernel GB/s microbench")
     ap.add_argument("--no-graph", action="store_true", help="time the eagerly launched step instead of the CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
