@@ -153,7 +153,9 @@ def train_deit(rank, num_gpus, config, task=None, max_iterations=None):
     # "device_matching": false restores the host (SciPy) matcher between two captured graphs
     device_matching = task == "detection" and train_config.get("device_matching", True)
     det_capacity = 0
-    use_graph = train_config.get("cuda_graph", task != "detection" or device_matching) and n_batch_accum == 1 \
+    # (the one-graph detection step is measured on one GPU; under data parallelism it is opt-in via "cuda_graph": true)
+    use_graph = train_config.get("cuda_graph", task != "detection" or (device_matching and num_gpus <= 1)) \
+        and n_batch_accum == 1 \
         and train_config["drop_last_batch"]
     split_graph = (task == "detection" and not device_matching and train_config.get("cuda_graph", True)
                    and n_batch_accum == 1 and train_config["drop_last_batch"] and num_gpus <= 1)
