@@ -77,3 +77,21 @@ def test_infeasible_block_sets_the_flag(host):
     cost = np.full((4, 3), np.inf, dtype=np.float32)
     _, flag = run(host, cost, 3)
     assert flag == 1
+
+
+def test_random_shapes_property(host):
+    """Any shape, any number of valid columns, costs with many exact ties (small integers): the matching's total
+    cost equals SciPy's optimum and it is a valid matching of min(nq, nt) pairs."""
+    rng = np.random.default_rng(99)
+    for trial in range(300):
+        nq, ld = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        nt = int(rng.integers(0, ld + 1))
+        cost = rng.integers(-3, 4, size=(nq, ld)).astype(np.float32)
+        match, flag = run(host, cost, nt)
+        assert flag == 0 and (match[nt:] == -1).all()
+        used = match[:nt][match[:nt] >= 0]
+        assert len(used) == min(nq, nt) and len(set(used.tolist())) == len(used) and (used < nq).all()
+        if nt:
+            ri, ci = linear_sum_assignment(cost[:, :nt].astype(np.float64))
+            got = sum(float(cost[match[t], t]) for t in range(nt) if match[t] >= 0)
+            assert got == float(cost[ri, ci].astype(np.float64).sum())
