@@ -63,6 +63,8 @@ class EncoderEngine:
         self.dev = self.params[0].device
         self._wq = None
         self._wq_versions = None
+        self._wq_capture_done = None
+        self.capture_generation = 0
         sizes = [p.numel() for p in self.params]
         self.offsets = [0]
         for s in sizes:
@@ -94,7 +96,7 @@ class EncoderEngine:
         if self._wq is not None and versions == self._wq_versions and (
                 not capturing or self.external_requant):
             return self._wq
-        if capturing and getattr(self, "_wq_capture_done", None) == id(torch.cuda.current_stream()):
+        if capturing and self._wq is not None and self._wq_capture_done == self._capture_key():
             return self._wq          # already re-quantised once inside this capture (forward)
         if self.exact:
             wq = {i: (mv.split_tf32(self.params[i].detach(), 1),
@@ -104,8 +106,14 @@ class EncoderEngine:
         self._wq, self._wq_versions = wq, versions
         # inside a CUDA-graph capture the re-quantisation must be part of the graph (weights change
         # between replays) but only once per step: backward reuses the forward's operands
-        self._wq_capture_done = id(torch.cuda.current_stream()) if capturing else None
+        self._wq_capture_done = self._capture_key() if capturing else None
         return wq
+
+    def _capture_key(self):
+        """Identifies the running capture: the capturing stream's handle and the capture generation
+        (utils.graph.GraphedTrainStep bumps it around every capture, so a flag left by an earlier capture on the
+        same stream never matches a later one)."""
+        return (torch.cuda.current_stream().cuda_stream, self.capture_generation)
 
     def _requantise_all(self, idx):
         """q(W) and q(W)^T of every Linear in ONE launch: the multi-tensor optimizer kernel (mv_adamw_step)
@@ -140,6 +148,10 @@ class EncoderEngine:
         mv._check(mv.lib().mv_adamw_step(ctypes.c_void_p(table.data_ptr()), n, chunks, mv._ptr(hyper),
                                          mv._stream()), "mv_adamw_step (re-quantise)")
         return wq
+
+    def invalidate_weights(self):
+        """The parameters changed behind the version counters: rebuild the operands on the next use."""
+        self._wq, self._wq_versions = None, None
 
     def mark_weights_fresh(self):
         """The operand buffers were just rewritten from the current parameter values (fused optimizer)."""

@@ -50,6 +50,10 @@ class FusedAdamW(torch.optim.Optimizer):
         engine = self.model.engine()
         if engine is not self._engine:
             self._engine, self._table = engine, None
+        if engine.exact:
+            # FP32: the engine's operands are 3xTF32 split buffers ([r, 3c] / [c, 3r]), not plain q(W) / q(W)^T
+            # tiles — the kernel must not write into them; the engine re-splits after every update instead
+            return {}
         engine.external_requant = True
         wq = engine.quantised_weights()
         return {id(engine.params[i]): (q, qt, engine.fmt) for i, (q, qt) in wq.items()}
@@ -65,6 +69,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def _build_table(self):
         ops = self._operands()
         rows, key, chunk = [], [], 0
+        self._updated = []
         for group in self.param_groups:
             for p in group["params"]:
                 if p.grad is None:
@@ -88,6 +93,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 else:
                     chunk += (p.numel() + 1023) // 1024
                 rows.append((t, g))
+                self._updated.append((t, p))
                 key.append((t.param, t.grad, t.wq, float(t.lr), float(t.weight_decay)))
         return rows, tuple(key), chunk
 
@@ -127,8 +133,13 @@ class FusedAdamW(torch.optim.Optimizer):
         mv._check(mv.lib().mv_adamw_step(ctypes.c_void_p(self._table[1].data_ptr()), len(rows), chunks,
                                          mv._ptr(hy), mv._stream()), "mv_adamw_step")
         del keep
+        # the kernel wrote the parameters through raw pointers: let every version-keyed cache see the update
+        torch.autograd.graph.increment_version([p for _, p in self._updated])
         if self._engine is not None:
-            self._engine.mark_weights_fresh()
+            if self._engine.exact:
+                self._engine.invalidate_weights()
+            else:
+                self._engine.mark_weights_fresh()
         return loss
 
     def load_state_dict(self, state_dict):

@@ -28,10 +28,15 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         self.model.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
+        engine = self.model.engine() if hasattr(self.model, "engine") else None
+        if engine is not None:
+            engine.capture_generation += 1       # operands re-quantised by an earlier capture do not count for this one
         with torch.cuda.graph(self.graph):
             self.output = self.net(self.static_img)
             self.loss = self.loss_fn(self.output, self.static_target)
             self.loss.backward()
+        if engine is not None:
+            engine.capture_generation += 1
         self.params = [p for p in self.model.parameters() if p.grad is not None]
         self.grads = [p.grad for p in self.params]
 

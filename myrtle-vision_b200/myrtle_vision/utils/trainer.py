@@ -65,8 +65,10 @@ def build_criterion(task, train_config, num_classes, device):
     from myrtle_vision.models.matcher import HungarianMatcher
     weights = {k: train_config[k] for k in ("loss_ce", "class_error", "loss_bbox", "loss_giou",
                                             "cardinality_error") if k in train_config}
-    matcher = HungarianMatcher(cost_class=weights.get("loss_ce", 1), cost_bbox=weights.get("loss_bbox", 5),
-                               cost_giou=weights.get("loss_giou", 2))
+    # the reference matches with HungarianMatcher()'s default costs (1 / 1 / 1, detection/train.py:199) and applies
+    # the weight_dict to the loss terms only; "matcher_costs": [class, bbox, giou] is an explicit opt-in
+    mc = train_config.get("matcher_costs")
+    matcher = HungarianMatcher(*mc) if mc else HungarianMatcher()
     crit = SetCriterion(num_classes, matcher, weights, train_config.get("eos_coef", 0.1),
                         ["labels", "boxes", "cardinality"]).to(device)
 
@@ -170,7 +172,6 @@ def train_deit(rank, num_gpus, config, task=None, max_iterations=None):
     for epoch in range(epoch_offset, train_config["epochs"]):
         if sampler is not None:
             sampler.set_epoch(epoch)
-        lr_scheduler.step(epoch)
         for imgs, targets in train_loader:
             if rank == 0 and n_accum == 0 and iters_per_checkpoint and iteration % iters_per_checkpoint == 0:
                 save_checkpoint(model=vit, optimizer=optimizer, lr_scheduler=lr_scheduler,
@@ -212,6 +213,8 @@ def train_deit(rank, num_gpus, config, task=None, max_iterations=None):
                     print(f"Iteration {iteration}:\tloss={history[-1]:.4f}")
                 if max_iterations is not None and iteration >= max_iterations:
                     break
+        # after the epoch's batches, as the reference (classification/train.py:287): epoch e trains at lr(e - 1)
+        lr_scheduler.step(epoch)
         if rank == 0:
             print(f"Epoch : {epoch + 1} - val_loss : {last_val[0]:.4f} - val_metric: {last_val[1]:.4f}\n")
         if max_iterations is not None and iteration >= max_iterations:

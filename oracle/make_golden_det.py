@@ -43,17 +43,20 @@ def make_case(seed, B=4, Q=100, C=20):
 
 def main():
     out = {}
-    for seed in (1, 2):
+    # seeds 1, 2: HungarianMatcher() with its default costs 1 / 1 / 1, exactly as detection/train.py:199 builds it
+    # (the weight_dict only weighs the loss terms); seed 3: explicit non-default costs
+    for seed, costs in ((1, None), (2, None), (3, (1, 5, 2))):
         logits, boxes, targets = make_case(seed)
         logits.requires_grad_(True)
         boxes.requires_grad_(True)
-        crit = SetCriterion(20, HungarianMatcher(cost_class=1, cost_bbox=5, cost_giou=2), WEIGHTS, 0.1,
-                            ["labels", "boxes", "cardinality"])
+        matcher = HungarianMatcher() if costs is None else HungarianMatcher(*costs)
+        crit = SetCriterion(20, matcher, WEIGHTS, 0.1, ["labels", "boxes", "cardinality"])
         losses = crit({"pred_logits": logits, "pred_boxes": boxes}, targets)
         total = sum(losses[k] * WEIGHTS[k] for k in WEIGHTS)
         total.backward()
         indices = crit.matcher({"pred_logits": logits.detach(), "pred_boxes": boxes.detach()}, targets)
         p = "s%d_" % seed
+        out[p + "costs"] = np.array([matcher.cost_class, matcher.cost_bbox, matcher.cost_giou], dtype=np.float64)
         out[p + "logits"] = logits.detach().numpy()
         out[p + "boxes"] = boxes.detach().numpy()
         out[p + "n_tgt"] = np.array([len(t["labels"]) for t in targets])

@@ -21,12 +21,12 @@ def load_case(seed):
     return z, p, torch.from_numpy(z[p + "logits"]), torch.from_numpy(z[p + "boxes"]), targets
 
 
-@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("seed", [1, 2, 3])
 def test_matcher_and_losses_equal_the_reference(seed):
     from myrtle_vision.models.detector import SetCriterion
     from myrtle_vision.models.matcher import HungarianMatcher
     z, p, logits, boxes, targets = load_case(seed)
-    matcher = HungarianMatcher(cost_class=1, cost_bbox=5, cost_giou=2)
+    matcher = HungarianMatcher(*z[p + "costs"].tolist())   # seeds 1, 2: the defaults, as detection/train.py:199
     indices = matcher({"pred_logits": logits, "pred_boxes": boxes}, targets)
     assert [len(i) for i, _ in indices] == [min(100, len(t["labels"])) for t in targets]
     assert torch.cat([i for i, _ in indices]).numpy().tolist() == z[p + "match_src"].tolist()
@@ -84,12 +84,12 @@ def scipy_match_padded(matcher):
     return match_padded
 
 
-@pytest.mark.parametrize("seed,capacity", [(1, None), (2, 64)])
+@pytest.mark.parametrize("seed,capacity", [(1, None), (2, 64), (3, 32)])
 def test_padded_criterion_equals_the_reference(seed, capacity, monkeypatch):
     from myrtle_vision.models.detector import SetCriterion
     from myrtle_vision.models.matcher import HungarianMatcher, pad_targets
     z, p, logits, boxes, targets = load_case(seed)
-    matcher = HungarianMatcher(cost_class=1, cost_bbox=5, cost_giou=2)
+    matcher = HungarianMatcher(*z[p + "costs"].tolist())   # seeds 1, 2: the defaults, as detection/train.py:199
     monkeypatch.setattr(matcher, "match_padded", scipy_match_padded(matcher))
     padded = pad_targets(targets, capacity=capacity)
     assert padded["labels"].shape[1] % 8 == 0 and padded["sizes"].tolist() == [len(t["labels"]) for t in targets]

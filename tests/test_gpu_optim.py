@@ -88,3 +88,40 @@ def test_model_step_emits_the_next_steps_operands(fmt):
         assert torch.equal(qw, want) and torch.equal(qwt, want_t)    # bit-exact operands
     with torch.no_grad():
         assert torch.allclose(m(img), twin(img), rtol=1e-3, atol=1e-3)
+
+
+def test_fp32_eager_steps_track_torch_adamw():
+    """q_format=FP32 (3xTF32 split operands): the fused optimizer must not write q(W) tiles into the split buffers,
+    and the engine must re-split the weights it updated through raw pointers — eager mode, several steps."""
+    from myrtle_vision.models.vit import ViT
+    from myrtle_vision.utils.fused_adamw import FusedAdamW
+    from myrtle_vision.utils.optim import add_weight_decay
+    case = CASES["classification"]
+    torch.manual_seed(5)
+    m = ViT(decoder="classification", image_size=case["image_size"], patch_size=16, num_classes=5,
+            dim=128, depth=2, heads=2, mlp_dim=256, q_format="FP32").to(dev).train()
+    twin = copy.deepcopy(m)
+    img, tgt = make_inputs("classification", case, 11)
+    img, tgt = img.to(dev), tgt.to(dev)
+    ours = FusedAdamW(add_weight_decay(m, 0.05), lr=2e-3, model=m)
+    ref = torch.optim.AdamW(add_weight_decay(twin, 0.05), lr=2e-3)
+    losses, losses_ref = [], []
+    for it in range(4):
+        m.zero_grad(set_to_none=True)
+        twin.zero_grad(set_to_none=True)
+        la, lb = F.cross_entropy(m(img), tgt), F.cross_entropy(twin(img), tgt)
+        la.backward()
+        lb.backward()
+        losses.append(float(la)); losses_ref.append(float(lb))
+        ours.step()
+        ref.step()
+    # both models run the same kernels; the only difference is the optimizer: the trajectories must coincide
+    for a, b in zip(losses, losses_ref):
+        assert abs(a - b) <= 2e-4 * abs(b), (losses, losses_ref)
+    assert losses[-1] < losses[0]
+    # parameters: Adam's first steps move every weight by ~lr whatever the gradient's size, so two runs whose
+    # gradients differ in the last bits agree to a fraction of lr, not to fp32 rounding
+    for (n, p), q in zip(m.named_parameters(), twin.parameters()):
+        assert (p - q).abs().max() <= 2e-3 * 4 * 0.25 + 1e-6, n
+    with torch.no_grad():
+        assert torch.allclose(m(img), twin(img), rtol=2e-3, atol=2e-3)
