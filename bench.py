@@ -129,13 +129,54 @@ def cpu_port_throughput(batch, steps, warmup, q_format):
     return batch / mean, mean * 1e3, torch.get_num_threads()
 
 
+def cpu_reference_throughput(batch, steps, warmup, q_format):
+    """The UNMODIFIED reference (`oracle/_ref/myrtle_vision`, staged by oracle/make_ref.py) through the qtorch
+    shim: img/s of the span classification/train.py:239-264 times (zero_grad -> forward -> CE -> backward) on
+    `batch` images per step, all host threads.  Raises ImportError when oracle/_ref is not staged."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import make_ref
+    ref_vit = make_ref.import_reference()
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
+    torch.manual_seed(1234)
+    model = ref_vit.ViT(decoder="classification", image_size=IMAGE, patch_size=PATCH, num_classes=CLASSES,
+                        dim=ARCH["dim"], depth=ARCH["depth"], heads=ARCH["heads"], mlp_dim=ARCH["mlp_dim"],
+                        q_format=q_format).train()
+    g = torch.Generator().manual_seed(1234)
+    img = torch.randn(batch, 3, IMAGE, IMAGE, generator=g).clamp(-1, 1)
+    tgt = torch.randint(0, CLASSES, (batch,), generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.zero_grad()
+        F.cross_entropy(model(img), tgt).backward()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return batch / mean, mean * 1e3, torch.get_num_threads()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 8
+    batch = args.ref_batch
     steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 1))
-    ips, ms, threads = cpu_port_throughput(batch, steps, warmup, args.q_format)
+    try:
+        ips, ms, threads = cpu_reference_throughput(batch, steps, warmup, args.q_format)
+        kind, what = "reference", "unmodified reference package (oracle/_ref) + qtorch shim over oracle/quant_oracle.c"
+    except ImportError as e:
+        sys.stderr.write("reference arm: %s — timing the oracle port instead\n" % e)
+        ips, ms, threads = cpu_port_throughput(batch, steps, warmup, args.q_format)
+        kind, what = "port", "oracle/vit_oracle.py (restatement of the reference) + oracle/quant_oracle.c"
+    extra = {}
+    if args.ref_batch2 and kind == "reference":
+        # second, larger sample (SURVEY.md section 8d: "batch 8 and, if time allows, 32")
+        ips2, ms2, _ = cpu_reference_throughput(args.ref_batch2, max(1, min(steps, 2)), 1, args.q_format)
+        extra = {"batch_%d" % args.ref_batch2: {"value": ips2, "ms_per_step": ms2}}
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -144,11 +185,31 @@ def run_reference(args):
                                % (args.q_format, args.batch),
                    "sample": "each step is batch %d of that workload on the host cores (bounded CPU sample)" % batch,
                    "parallelism": "cpu, %d threads" % threads},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": "%d steps of batch %d (same model/input shape), host cores=%d" % (steps, batch, os.cpu_count())},
+        "cpu_baseline": dict({"value": ips, "unit": "images/s", "cores": threads, "kind": kind, "what": what,
+                              "sample": "%d steps of batch %d (same model/input shape), host cores=%d"
+                                        % (steps, batch, os.cpu_count())}, **extra),
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(q_format):
+    """`cpu_baseline` of the B200 arm: the reference arm in a child process (this process has this repo's own
+    `myrtle_vision` package imported, the reference's has the same name)."""
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
+                              "--warmup", "1", "--q-format", q_format, "--ref-batch2", "0"],
+                             capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        sys.stderr.write("cpu_baseline child printed no JSON: %s\n" % out.stderr[-500:])
+    except (subprocess.SubprocessError, OSError, ValueError, KeyError) as e:
+        sys.stderr.write("cpu_baseline child failed: %r\n" % (e,))
+    return None
 
 
 # ------------------------------------------------------------------------------------------
@@ -356,10 +417,12 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, ms_cpu, threads = cpu_port_throughput(8, 2, 1, args.q_format)
-        cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": "2 timed steps of batch 8, same model and image shape (%.0f ms/step), host cpu_count=%d"
-                         % (ms_cpu, os.cpu_count())}
+        cpu = cpu_baseline_subprocess(args.q_format)
+        if cpu is None:
+            ips, ms_cpu, threads = cpu_port_throughput(8, 2, 1, args.q_format)
+            cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": "2 timed steps of batch 8, same model and image shape (%.0f ms/step), host cpu_count=%d"
+                             % (ms_cpu, os.cpu_count())}
 
     value = world * B / ms_step * 1e3
     fl = flops_per_image(n_tok, D, L, Mm, CLASSES)
@@ -400,6 +463,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--q-format", default="FP16_32", choices=["FP16_32", "FP16_16", "TF32", "FP32"])
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--ref-batch", type=int, default=8, help="reference arm: images per CPU step")
+    ap.add_argument("--ref-batch2", type=int, default=32, help="reference arm: second, larger sample (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-quant-bench", action="store_true", help="skip the fake-quant kernel GB/s microbench")

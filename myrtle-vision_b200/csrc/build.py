@@ -26,8 +26,12 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, report=None):
+    """-> path of the .so.  `report` (a list) receives one line saying what was done."""
     if not force and not needs_build():
+        if report is not None:
+            report.append("csrc: %s is newer than every source (%d .cu files) — nothing to compile "
+                          "(MV_FORCE_BUILD=1 or build.py --force recompiles)" % (os.path.basename(SO), len(sources())))
         return SO
     objs = []
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -46,6 +50,9 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on " + src)
     subprocess.check_call([NVCC, "-shared", "-o", SO] + objs +
                           ["-gencode", "arch=compute_100a,code=sm_100a"])
+    if report is not None:
+        report.append("csrc: compiled %d .cu files with nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 "
+                      "and linked %s" % (len(objs), os.path.basename(SO)))
     return SO
 
 

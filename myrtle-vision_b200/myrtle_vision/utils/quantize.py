@@ -188,8 +188,17 @@ class ModelQuantizer:
             setattr(parent, parts[-1], nn.Sequential(QuantStubSlot(fmt), module))
 
     def convert(self):
-        """Bake weight_fake_quant into the weights for inference (reference :329-348): Linear
-        weights and LayerNorm gammas become their quantised values, in place."""
+        """PTQ conversion for inference (reference :329-348, flow of classification/test_quantize.py:37-134).
+        `torch.quantization.convert(mapping={qat.Linear: QLinear, LayerNorm: QLayerNorm})` does two things in the
+        reference, both pinned by tests/golden/convert_*.npz (oracle/make_golden_convert.py runs it unmodified):
+          * Linear weights and LayerNorm gammas are replaced by their fake-quantised values
+            (QLinear.from_float / QLayerNorm.from_float, :134-166);
+          * every hook-based quantiser disappears with its observer hook — the QuantStub in front of each
+            Linear / LayerNorm / GELU and the Linear / LayerNorm output observers — while the FloatFunctional
+            quantisers (FP16_16's residual adds and cat / pos adds), which are called inside FloatFunctional's
+            own forward, stay.
+        So the converted model computes in fp32 on quantised weights; the plan below says exactly that and the
+        engine runs it on its fp32-grade (3xTF32) path."""
         if self.q_format == QFormat.FP32 or getattr(self, "converted", False):
             return
         fmt = self.plan.inp
@@ -200,6 +209,7 @@ class ModelQuantizer:
                     module.weight.copy_(mv_native.float_quantize(module.weight.data, fmt[0], fmt[1]))
                 elif isinstance(module, (nn.Linear, nn.LayerNorm)):
                     raise RuntimeError("convert() needs the model on a CUDA device")
+        self.plan = QuantPlan(None, None, self.plan.ff, None)
         self.converted = True
         if hasattr(self.model, "_invalidate_engine"):
             self.model._invalidate_engine()

@@ -43,6 +43,22 @@ PLACEMENT = {
 }
 
 
+# After ModelQuantizer.convert() (utils/quantize.py:329-348): torch.quantization.convert drops every hook-based
+# quantiser together with its observer hook (QuantStubs, Linear / LayerNorm output observers); only the
+# FloatFunctional ones survive.  Pinned by tests/golden/convert_*.npz (oracle/make_golden_convert.py).
+CONVERTED = {fmt: (None, None, pl[2], None) for fmt, pl in PLACEMENT.items()}
+
+
+def convert_params(P, q_format):
+    """QLinear.from_float / QLayerNorm.from_float (utils/quantize.py:134-166): Linear weights and LayerNorm gammas
+    become their fake-quantised values; biases, tokens and positional embeddings are untouched."""
+    fmt = PLACEMENT[str(q_format)][0]
+    if fmt is None:
+        return dict(P)
+    with torch.no_grad():
+        return {k: (fq(v, fmt) if k.endswith(".weight") else v) for k, v in P.items()}
+
+
 class _STEQuant(torch.autograd.Function):
     """forward: float_quantize nearest on x.data; backward: identity."""
 
@@ -94,9 +110,10 @@ def _layernorm(x, P, name, fin, fout):
 
 
 def vit_forward(P, img, *, decoder, patch_size=16, heads, q_format="FP32", num_det_tokens=100,
-                image_size=None, dim_head=64):
-    """P: canonical parameter dict.  Returns what ViT.forward returns."""
-    fin, fout, ffn, fgelu = PLACEMENT[str(q_format)]
+                image_size=None, dim_head=64, converted=False):
+    """P: canonical parameter dict.  Returns what ViT.forward returns.  converted=True: the quantiser set that is
+    left after ModelQuantizer.convert() (pass convert_params(P, q_format) as P)."""
+    fin, fout, ffn, fgelu = (CONVERTED if converted else PLACEMENT)[str(q_format)]
     b, c, h, w = img.shape
     p = patch_size
     gh, gw = h // p, w // p

@@ -65,3 +65,36 @@ def test_canonical_key():
     assert (vit_oracle.canonical_key("transformer.layers.3.1.fn.fn.net.0.weight")
             == "transformer.layers.3.1.fn.fn.net.0.weight")
     assert vit_oracle.canonical_key("pos_embedding") == "pos_embedding"
+
+
+def _convert_case(seed=4321):
+    case = CASES["classification"]
+    P = vit_oracle.init_params(decoder="classification", num_classes=case["num_classes"], dim=ARCH["dim"],
+                               depth=ARCH["depth"], heads=ARCH["heads"], mlp_dim=ARCH["mlp_dim"], seed=seed)
+    g = torch.Generator().manual_seed(99)          # gammas away from 1: their quantisation happens in convert() only
+    for k in P:
+        if k.endswith("norm.weight"):
+            P[k] = P[k] + 0.3 * torch.randn(P[k].shape, generator=g)
+    img, _ = make_inputs("classification", case, 77)
+    return case, P, img
+
+
+@pytest.mark.parametrize("fmt", ["FP16_32", "FP16_16", "TF32"])
+def test_oracle_convert_matches_the_reference_convert(fmt):
+    """PTQ path: fixtures from the unmodified reference's vit.convert() + eval forward
+    (oracle/make_golden_convert.py).  Pins WHICH quantisers survive convert(): none of the hook-based ones."""
+    z = np.load(os.path.join(GOLD, "convert_%s.npz" % fmt))
+    case, P, img = _convert_case()
+    with torch.no_grad():
+        before = vit_oracle.vit_forward(P, img, decoder="classification", heads=ARCH["heads"], q_format=fmt)
+        Q = vit_oracle.convert_params(P, fmt)
+        after = vit_oracle.vit_forward(Q, img, decoder="classification", heads=ARCH["heads"], q_format=fmt,
+                                       converted=True)
+        kept = vit_oracle.vit_forward(Q, img, decoder="classification", heads=ARCH["heads"], q_format=fmt)
+    np.testing.assert_allclose(before.numpy(), z["before"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(after.numpy(), z["after"], rtol=1e-5, atol=2e-5)
+    # the alternative reading (activation quantisers kept) is measurably not what the reference does
+    assert np.abs(kept.numpy() - z["after"]).max() > 10 * np.abs(after.numpy() - z["after"]).max()
+    for k in z.files:
+        if k.startswith("sd/"):
+            assert np.array_equal(Q[vit_oracle.canonical_key(k[3:])].numpy(), z[k]), k
