@@ -113,6 +113,27 @@ typedef struct {
 
 int mv_gemm(const mv_gemm_args* args, void* stream);
 
+/* ---------------------------------------------------------------- overflow sink
+ * Replaces the inf / NaN test of torch.cuda.amp.GradScaler (classification/train.py:167, 259-277; the reference
+ * trains under GradScaler(65536) and skips a step whose gradients are not finite).  flag_dev: one device int (or
+ * NULL to switch reporting off, the default).  It is raised (set to 1, never cleared by the library) when
+ *   - a value that a backward kernel rounds into an fp16 operand container does not fit it (|v| >= 65520: the
+ *     container saturates at 65504): mv_scale_f32's fp16 copy, mv_layernorm_q_bwd's dx_f16, 16-bit outputs of
+ *     mv_gemm that carry no quantiser (dgrad / gelu' outputs; the unquantised qkv of FP16_32), dqkv of
+ *     mv_attention_bwd;
+ *   - mv_scale_f32 meets a non-finite result (the un-scale pass over the parameter gradients sees every NaN / inf
+ *     the backward produced).
+ * The caller clears it at the start of a step and hands it to mv_adamw_step's found_inf (no host sync). */
+int mv_set_overflow_flag(int* flag_dev);
+/* End-of-step bookkeeping, GradScaler.update() on the device: state_dev = {found_inf, scale_target, good_steps}
+ * (3 floats).  found_inf <- found_inf (sticky until the caller clears it) or flag != 0 or *shared_slot != 0 (shared_slot, nullable: a float that went through the
+ * gradient all-reduce, so that every rank of a data-parallel job sees every rank's flag); on found_inf
+ * scale_target <- max(scale_target * backoff, min_target), else after growth_interval clean steps
+ * scale_target <- min(scale_target * growth, max_target).  scale_target is the magnitude the backward scales the
+ * largest incoming gradient to before it enters fp16 operand containers. */
+int mv_overflow_update(const int* flag_dev, const float* shared_slot_dev, float* state_dev, float backoff, float growth,
+                       int growth_interval, float min_target, float max_target, void* stream);
+
 
 /* ---------------------------------------------------------------- LayerNorm + quant (warp-shuffle)
  * y = q_post(LN(q_in(x); gamma, beta)) : Sequential(QuantStub, nn.LayerNorm) followed by the next

@@ -10,6 +10,7 @@ namespace mv {
 static thread_local char g_err[512] = "";
 int64_t g_launches = 0;
 int g_opt_attn_sn = 1;          // short-sequence attention kernels (attention_sn.cu) when N fits
+int* g_overflow = nullptr;      // device int registered with mv_set_overflow_flag (NULL: no overflow reporting)
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -98,7 +99,8 @@ int make_tmap_3d(CUtensorMap* map, const void* ptr, int dtype, uint64_t d0, uint
 }  // namespace mv
 
 extern "C" const char* mv_last_error(void) { return mv::g_err; }
-extern "C" int mv_version(void) { return 100; }
+extern "C" int mv_version(void) { return 101; }
+extern "C" int mv_set_overflow_flag(int* flag_dev) { mv::g_overflow = flag_dev; return 0; }
 extern "C" int64_t mv_launch_count(void) { return mv::g_launches; }
 
 extern "C" int mv_set_option(const char* name, int value) {

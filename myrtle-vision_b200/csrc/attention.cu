@@ -295,6 +295,7 @@ struct AttnBwdDev {
     const float* delta;
     __half* dqkv; int ld_dqkv;
     float* dq_accum;          // KV pass only: fp32 [B*N, D]; non-null => dQ += dS K by red.add (no Q pass)
+    int* ovf;                 // overflow sink (mv_set_overflow_flag) or NULL
 };
 
 // kModeKV = true : CTA owns key block blockIdx.x; loops over query blocks; emits dK, dV.
@@ -499,6 +500,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 tmem_ld_32x32((a == 0 ? tAcc0 : tAcc1) + lane_off + c * 32, v);
                 tmem_ld_wait();
                 if (orow < p.N) {
+                    float amax = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(__uint_as_float(v[i])));
+                    raise_overflow(p.ovf, amax);
 #pragma unroll
                     for (int i = 0; i < 4; i++)
                         reinterpret_cast<uint4*>(dst + c * 32)[i] =
@@ -707,6 +712,10 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_co
                     tmem_ld_32x32((a == 0 ? tdV : tdK) + lane_off + c * 32, v);
                     tmem_ld_wait();
                     if (key < p.N) {
+                        float amax = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(__uint_as_float(v[i])));
+                        raise_overflow(p.ovf, amax);
 #pragma unroll
                         for (int i = 0; i < 4; i++)
                             reinterpret_cast<uint4*>(dst + c * 32)[i] =
@@ -728,7 +737,7 @@ constexpr int kAttnBwd64Smem = 5 * kTile + 1024 + 256 + 4 * 32 * kStgPitchF * 4;
 
 // dq fp32 [rows, D] -> fp16 into the q columns of dqkv [rows, ld]
 __global__ void __launch_bounds__(256)
-dq_convert_kernel(const float* __restrict__ dq, __half* __restrict__ dqkv, int64_t rows, int D, int ld) {
+dq_convert_kernel(const float* __restrict__ dq, __half* __restrict__ dqkv, int64_t rows, int D, int ld, int* __restrict__ ovf) {
     const int vec_per_row = D >> 2;
     const int64_t total = rows * vec_per_row;
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -736,6 +745,7 @@ dq_convert_kernel(const float* __restrict__ dq, __half* __restrict__ dqkv, int64
         const int64_t row = i / vec_per_row;
         const int c = int(i % vec_per_row);
         const float4 v = __ldcs(reinterpret_cast<const float4*>(dq) + i);
+        raise_overflow(ovf, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         reinterpret_cast<uint2*>(dqkv + row * ld)[c] =
             make_uint2(pack_h2(sat16f(v.x), sat16f(v.y)), pack_h2(sat16f(v.z), sat16f(v.w)));
     }
@@ -810,6 +820,7 @@ extern "C" int mv_attention_bwd(const void* qkv, const void* o, const void* d_o,
     p.lse = lse; p.delta = delta;
     p.dqkv = reinterpret_cast<__half*>(dqkv); p.ld_dqkv = 3 * D;
     p.dq_accum = dq_accum;
+    p.ovf = g_overflow;
     dim3 grid((N + 127) / 128, H, B);
     if (dq_accum != nullptr) {
         // one pass: dK, dV per key block and dQ accumulated across key blocks with fp32 red.add
@@ -822,7 +833,7 @@ extern "C" int mv_attention_bwd(const void* qkv, const void* o, const void* d_o,
         g_launches++;
         int64_t blocks = (n / 4 + 255) / 256;
         if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-        dq_convert_kernel<<<int(blocks), 256, 0, st>>>(dq_accum, reinterpret_cast<__half*>(dqkv), int64_t(B) * N, D, 3 * D);
+        dq_convert_kernel<<<int(blocks), 256, 0, st>>>(dq_accum, reinterpret_cast<__half*>(dqkv), int64_t(B) * N, D, 3 * D, g_overflow);
         g_launches++;
     } else {
         // deterministic two-pass variant (no atomics): the Q pass recomputes S and dP

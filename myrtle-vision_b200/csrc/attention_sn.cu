@@ -84,10 +84,14 @@ __device__ __forceinline__ void sn_red_add_v4(float* p, float a, float b, float 
 }
 template <bool kCS>
 __device__ __forceinline__ void sn_store_rows(uint8_t* stg, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
-                                              __half* dst0, int64_t ld, int nvalid, int lane, float (&acc)[2][8]) {
+                                              __half* dst0, int64_t ld, int nvalid, int lane, float (&acc)[2][8],
+                                              float& amax) {
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         const uint32_t (&v)[32] = half == 0 ? v0 : v1;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+            amax = fmaxf(amax, fmaxf(fabsf(__uint_as_float(v[i])), fabsf(__uint_as_float(v[i + 1]))));
 #pragma unroll
         for (int i = 0; i < 4; i++)
             *reinterpret_cast<uint4*>(stg + lane * kSnStgPitch + i * 16) = make_uint4(
@@ -683,6 +687,7 @@ struct SnBwdDev {
     const __half* d_o;
     __half* dqkv; int ld_dqkv;
     float* dbias;               // NULL or fp32 [3 * D]: += column sums of dqkv (the to_qkv Linear's bias gradient)
+    int* ovf;                   // overflow sink (mv_set_overflow_flag) or NULL: a dqkv value saturated its fp16 container
 };
 
 __global__ void __launch_bounds__(kSnBwdThreads, 1)
@@ -894,6 +899,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         //   v: sum_k dV[k, :] = sum_q (sum_k P[q, k]) dO[q, :] = the column sums of dO, which stats_rows has in
         //      registers anyway (cs_v: this thread's 16-byte chunk of the head, every row it visits).
         float cs_q[2][8], cs_v[8], cs_t0 = 0.f, cs_t1 = 0.f;
+        float amax = 0.f;                                   // largest |dqkv| value stored (overflow sink)
 #pragma unroll
         for (int k = 0; k < 8; k++) { cs_q[0][k] = cs_q[1][k] = cs_v[k] = 0.f; }
         const bool do_cs = p.dbias != nullptr;
@@ -1079,7 +1085,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     {
                         const int key0 = j * 128 + quad * 32;            // first key row of this warp
                         __half* dst0 = p.dqkv + (int64_t(b) * p.N + key0) * p.ld_dqkv + (g == 0 ? 2 : 1) * p.D + h * 64;
-                        sn_store_rows<false>(sStg + (warp - 2) * 32 * kSnStgPitch, v0, v1, dst0, p.ld_dqkv, p.N - key0, lane, cs_q);
+                        sn_store_rows<false>(sStg + (warp - 2) * 32 * kSnStgPitch, v0, v1, dst0, p.ld_dqkv, p.N - key0, lane, cs_q, amax);
                     }
                 }
             }
@@ -1102,8 +1108,8 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     const int row0 = g * 128 + quad * 32;
                     __half* dst0 = p.dqkv + (int64_t(b) * p.N + row0) * p.ld_dqkv + h * 64;
                     uint8_t* stg = sStg + (warp - 2) * 32 * kSnStgPitch;
-                    if (do_cs) sn_store_rows<true>(stg, v0, v1, dst0, p.ld_dqkv, p.N - row0, lane, cs_q);
-                    else sn_store_rows<false>(stg, v0, v1, dst0, p.ld_dqkv, p.N - row0, lane, cs_q);
+                    if (do_cs) sn_store_rows<true>(stg, v0, v1, dst0, p.ld_dqkv, p.N - row0, lane, cs_q, amax);
+                    else sn_store_rows<false>(stg, v0, v1, dst0, p.ld_dqkv, p.N - row0, lane, cs_q, amax);
                 }
             }
             // rows >= 256: dQ from the shared-memory accumulators
@@ -1112,6 +1118,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             SN_TRACE(quad == 0 && lane == 0, 1 + g, 17, n);
             for (int i = mt; i < (p.N - 256) * 32; i += 256) {
                 const int r = i >> 5, l2 = i & 31;
+                amax = fmaxf(amax, fmaxf(fabsf(sdQt[r * 64 + 2 * l2]), fabsf(sdQt[r * 64 + 2 * l2 + 1])));
                 const uint32_t pk = pack_h2_satf(sdQt[r * 64 + 2 * l2], sdQt[r * 64 + 2 * l2 + 1]);
                 *reinterpret_cast<uint32_t*>(p.dqkv + (int64_t(b) * p.N + 256 + r) * p.ld_dqkv + h * 64 + 2 * l2) = pk;
                 const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk));
@@ -1120,6 +1127,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             named_bar_sync(1, 256);
             SN_TRACE(quad == 0 && lane == 0, 1 + g, 18, n);                 // pair finished
         }
+        raise_overflow(p.ovf, amax);
         if (do_cs && n_local > 0) {
             const int h = blockIdx.x % p.H;
             sn_flush_colsum(cs_q, p.dbias + h * 64, lane);
@@ -1225,6 +1233,7 @@ int mv_attention_bwd_sn(const void* qkv, const void* o, const void* d_o, const f
     const bool fuse = dbias != nullptr && H <= kNumSMs;
     const int grid = n_bh <= kNumSMs ? n_bh : (fuse ? (kNumSMs / H) * H : kNumSMs);
     p.dbias = fuse ? dbias : nullptr;
+    p.ovf = g_overflow;
     attn_bwd_sn_kernel<<<grid, kSnBwdThreads, kSnBwdSmem, st>>>(q128, q16, d128, d16, p);
     g_launches++;
     if (check_cuda(cudaGetLastError(), "attention bwd (short-sequence) launch")) return 1;

@@ -28,6 +28,15 @@ int check_cuda(cudaError_t e, const char* what);
 
 constexpr int kNumSMs = 148;
 
+// Overflow sink (mv_set_overflow_flag): kernels that round gradient values into fp16 containers keep the largest
+// |value| they convert and raise the flag when it would not fit (>= 65520 rounds past 65504: the container
+// saturates; +-inf included.  NaNs are caught by the final un-scale pass, which tests every parameter gradient).
+extern int* g_overflow;
+constexpr float kHalfOverflow = 65520.0f;
+__device__ __forceinline__ void raise_overflow(int* flag, float amax) {
+    if (flag != nullptr && amax >= kHalfOverflow) *flag = 1;
+}
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -65,6 +65,7 @@ struct GemmDev {
     int rows_per_img;
     int variant;                // CTA-pair kernel: compile-time epilogue variant (0 = generic), see gemm2_host
     float* colsum;              // CTA-pair kernel: fp32 [N] += column sums of the stored values (fused bias gradient)
+    int* ovf;                   // overflow sink (mv_set_overflow_flag) or NULL
 };
 
 __device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
@@ -440,6 +441,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 16; j++) v[j] = fq_apply(v[j], mode_res, p.q_res);
                 }
+                if (p.out_dtype == MV_F16 && !mode_out && !mode_res && p.epilogue != MV_EPI_GELU) {
+                    float amax = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) if (j < nvalid) amax = fmaxf(amax, fabsf(v[j]));
+                    raise_overflow(p.ovf, amax);
+                }
                 const int esz_o = p.out_dtype == MV_F32 ? 4 : 2;
                 const bool vec_o = full && ((p.ld_out * esz_o) % 16 == 0);
                 store_out16(p.out, p.out_dtype, m, p.ld_out, n, v, vec_o, nvalid);
@@ -605,6 +612,9 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
 #endif
     const uint32_t sp = w.stg_s + (w.lr * kStgPitch + w.lc) * 4;
     float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    // unquantised values rounded into an fp16 container (gradient operands; qkv of FP16_32): report saturation
+    constexpr bool kOvf = kOut == MV_F16 && kQO == 0 && kQR == 0 && kEpi != MV_EPI_GELU && !kAcc;
+    float amax = 0.f;
 #pragma unroll
     for (int it = 0; it < 8; it++) {
         const int m = m_first + it * 4;
@@ -629,6 +639,7 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
         if (kRes != 0) { v[0] += res4[it].x; v[1] += res4[it].y; v[2] += res4[it].z; v[3] += res4[it].w; }
         if (kQR == 1) fq_half4<kOut == MV_F16>(v);
         if (kCS) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
+        if (kOvf) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))));
         if (kOut == MV_F32)
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + int64_t(m) * p.ld_out + n) =
                 make_float4(v[0], v[1], v[2], v[3]);
@@ -644,6 +655,7 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
         }
         if (w.lr == 0) red_add_v4(p.colsum + n, cs[0], cs[1], cs[2], cs[3]);
     }
+    if (kOvf) raise_overflow(p.ovf, amax);
 #ifdef MV_GEMM_TRACE
     if (w.tr != nullptr && w.lane == 0) { w.tr[6] = 22; w.tr[7] = nc0; w.tr[8] = clock64(); }
 #endif
@@ -711,6 +723,8 @@ __device__ __forceinline__ void epi_chunk_generic(const GemmDev& p, const EpiWar
             }
             if (w.mode_res) for (int j = 0; j < 4; j++) v[j] = fq_apply(v[j], w.mode_res, p.q_res);
             for (int j = 0; j < 4; j++) cs[j] += v[j];
+            if (p.out_dtype == MV_F16 && !w.mode_out && !w.mode_res && p.epilogue != MV_EPI_GELU)
+                for (int j = 0; j < 4; j++) if (j < nvalid) raise_overflow(p.ovf, fabsf(v[j]));
             store_out4(p.out, p.out_dtype, m, p.ld_out, n, v, false, nvalid);
             if (p.out2 != nullptr) store_out4(p.out2, p.out2_dtype, m, p.ld_out2, n, v, false, nvalid);
         }
@@ -1004,6 +1018,7 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     p.transpose_out = a->transpose_out;
     p.rows_per_img = a->rows_per_img;
     p.colsum = a->accumulate ? nullptr : a->colsum;
+    p.ovf = g_overflow;
     // epilogue variant (epi_chunk<> instantiations in gemm2_kernel); anything else runs the generic path
     {
         auto al = [](const void* q, int bytes) { return (reinterpret_cast<uintptr_t>(q) & (bytes - 1)) == 0; };
@@ -1107,7 +1122,7 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
     p.q_res = FloatFmt{a->q_res_exp, a->q_res_man};
     p.accumulate = a->accumulate;
     p.rows_per_img = a->rows_per_img;
-    p.variant = 0; p.colsum = nullptr; p.idesc2 = 0; p.transpose_out = 0;
+    p.variant = 0; p.colsum = nullptr; p.idesc2 = 0; p.transpose_out = 0; p.ovf = g_overflow;
 
     // CTA pairs sharing B through TMA multicast: measured no faster on B200 (the bound is the per-SM
     // L2->SM ingest, which multicast does not reduce), so it is opt-in (cluster == 2)

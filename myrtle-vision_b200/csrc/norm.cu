@@ -169,7 +169,7 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               float* __restrict__ dx, int64_t ld_dx, __half* __restrict__ dx_lp, int64_t ld_lp,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias_prev,
-              int rows, int D, FloatFmt q_in) {
+              int rows, int D, FloatFmt q_in, int* __restrict__ ovf) {
     // Column sums (dgamma, dbeta, previous bias grad) are kept per warp in shared memory — each
     // lane owns its columns, so plain read-modify-write — which frees ~36 registers per thread for
     // occupancy; the next row's loads are issued before the current row is reduced.
@@ -204,6 +204,7 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
     };
     int row = blockIdx.x * kLnWarps + warp;
     LnBwdRow<NV, DyT> cur;
+    float amax = 0.f;                   // largest |dx| rounded into the fp16 operand copy (overflow sink)
     if (row < rows) load_row(row, cur);
     for (; row < rows; row += rstride) {
         LnBwdRow<NV, DyT> nxt;
@@ -264,6 +265,7 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
                 acc[2 * nvec + c] = ps;
                 __stcs(reinterpret_cast<float4*>(dxr) + c, o);
                 if (dx_lp != nullptr) {
+                    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
                     __stcs(reinterpret_cast<uint2*>(dx_lp + int64_t(row) * ld_lp) + c,
                            make_uint2(pack_h2_sat(o.x, o.y), pack_h2_sat(o.z, o.w)));
                 }
@@ -271,6 +273,7 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
         }
         cur = nxt;
     }
+    raise_overflow(ovf, amax);
     __syncthreads();
     // CTA-level column reduction over the warps, then one atomic per column per CTA
     for (int which = 0; which < 3; which++) {
@@ -435,18 +438,40 @@ convert_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t n4)
 // The loss-scale style gradient scale lives in device memory, so no host synchronisation.
 __global__ void __launch_bounds__(256)
 scale_kernel(const float* __restrict__ in, const float* __restrict__ scale_dev, int invert, float* __restrict__ out32,
-             __half* __restrict__ out16, int64_t n4) {
+             __half* __restrict__ out16, int64_t n4, int* __restrict__ ovf) {
     const float s = invert ? 1.0f / __ldg(scale_dev) : __ldg(scale_dev);
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    // overflow sink: a non-finite result anywhere (the final un-scale of the parameter gradients: GradScaler's
+    // inf / NaN test), or a value that does not fit the fp16 copy
+    const float limit = out16 != nullptr ? kHalfOverflow : 3.4028234664e38f;
+    bool bad = false;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 v = __ldcs(reinterpret_cast<const float4*>(in) + i);
         v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+        bad |= !(m < limit) | !((v.x + v.y) + (v.z + v.w) == (v.x + v.y) + (v.z + v.w));     // too large, inf, or NaN
         if (out32 != nullptr) reinterpret_cast<float4*>(out32)[i] = v;
         if (out16 != nullptr) {
             __half2 lo = __floats2half2_rn(sat16(v.x), sat16(v.y)), hi = __floats2half2_rn(sat16(v.z), sat16(v.w));
             reinterpret_cast<uint2*>(out16)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
         }
     }
+    if (bad && ovf != nullptr) *ovf = 1;
+}
+
+// GradScaler bookkeeping on the device (torch.cuda.amp.GradScaler.update: backoff on inf, growth after a run of good
+// steps), for the power-of-two gradient operand scale.  state = {found_inf, scale_target, good_steps}.
+__global__ void overflow_update_kernel(const int* __restrict__ flag, const float* __restrict__ shared_slot,
+                                       float* __restrict__ state, float backoff, float growth, float interval,
+                                       float min_target, float max_target) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    bool found = *flag != 0;
+    if (shared_slot != nullptr) found |= !(*shared_slot == 0.0f);          // NaN counts
+    float target = state[1], good = state[2];
+    if (found) { target = fmaxf(target * backoff, min_target); good = 0.f; }
+    else if (++good >= interval) { target = fminf(target * growth, max_target); good = 0.f; }
+    // found_inf is sticky (gradient accumulation runs several backwards per optimizer step): whoever consumes it clears it
+    state[0] = (found || state[0] != 0.0f) ? 1.0f : 0.0f; state[1] = target; state[2] = good;
 }
 
 template <int NV>
@@ -481,10 +506,10 @@ static int launch_ln_bwd(const void* dy, int dy_dtype, int64_t ld_dy, const floa
     }
     if (dy_dtype == MV_F16)
         ln_bwd_kernel<NV, __half><<<grid, kLnWarps * 32, smem, st>>>((const __half*)dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx,
-                                                                    (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in);
+                                                                    (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in, g_overflow);
     else
         ln_bwd_kernel<NV, float><<<grid, kLnWarps * 32, smem, st>>>((const float*)dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx,
-                                                                   (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in);
+                                                                   (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in, g_overflow);
     g_launches++;
     return check_cuda(cudaGetLastError(), "ln bwd launch");
 }
@@ -652,9 +677,18 @@ extern "C" int mv_scale_f32(const float* in, const float* scale_dev, int invert,
     int64_t blocks = (n4 + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     scale_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, scale_dev, invert, out_f32,
-                                                                           reinterpret_cast<__half*>(out_f16), n4);
+                                                                           reinterpret_cast<__half*>(out_f16), n4, g_overflow);
     g_launches++;
     return check_cuda(cudaGetLastError(), "scale launch");
+}
+
+extern "C" int mv_overflow_update(const int* flag_dev, const float* shared_slot_dev, float* state_dev, float backoff,
+                                  float growth, int growth_interval, float min_target, float max_target, void* stream) {
+    MV_CHECK(flag_dev && state_dev, "mv_overflow_update: null pointer");
+    overflow_update_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flag_dev, shared_slot_dev, state_dev, backoff, growth,
+                                                                          float(growth_interval), min_target, max_target);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "overflow update launch");
 }
 
 extern "C" int mv_widen_transpose(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out,

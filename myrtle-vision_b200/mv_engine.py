@@ -66,12 +66,20 @@ class EncoderEngine:
         self._wq_capture_done = None
         self.capture_generation = 0
         sizes = [p.numel() for p in self.params]
-        self.offsets = [0]
+        # gflat[0:4] is a slot that travels through the last gradient all-reduce: under data parallelism it carries
+        # this rank's overflow flag to every rank (no extra collective)
+        self.offsets = [4]
         for s in sizes:
             self.offsets.append(self.offsets[-1] + ((s + 3) // 4) * 4)
         self.gflat = torch.zeros(self.offsets[-1], dtype=torch.float32, device=self.dev)
         self.gviews = [self.gflat[self.offsets[i]:self.offsets[i] + sizes[i]].view_as(p)
                        for i, p in enumerate(self.params)]
+        # Overflow handling in place of the reference's GradScaler (classification/train.py:167, 259-277), all on the
+        # device: `overflow` is raised by the backward kernels (mv_set_overflow_flag), `scaler_state` =
+        # {found_inf of the last backward, scale_target, good_steps}; an optimizer that understands found_inf
+        # (utils.fused_adamw.FusedAdamW.step(found_inf=engine.found_inf)) skips the update, as GradScaler.step does
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.scaler_state = torch.tensor([0.0, 1024.0, 0.0], dtype=torch.float32, device=self.dev)
         self.reducer = None      # set by parallel.DataParallel: called with flat gradient slices
         self.bucket_blocks = max(1, int(os.environ.get("MV_DP_BUCKET_BLOCKS", "3")))   # encoder blocks per all-reduce
         # True once an optimizer (utils/fused_adamw.FusedAdamW) emits q(W) / q(W)^T itself after every
@@ -159,8 +167,24 @@ class EncoderEngine:
         self._wq_versions = tuple(self.params[i]._version for i in idx) + tuple(
             self.params[i].data_ptr() for i in idx)
 
+    @property
+    def found_inf(self):
+        """fp32 [1] on the device: 1.0 when the last backward overflowed (identical on every data-parallel rank)."""
+        return self.scaler_state[0:1]
+
+    def _gradient_scale(self, gx):
+        """Power-of-two operand scale S chosen on the device: max |gx| * S lands in [target / 2, target]."""
+        mv.set_overflow_flag(self.overflow)        # (cleared by the training forward this backward belongs to)
+        amax = torch.linalg.vector_norm(gx, float("inf")).clamp_min(1e-30)          # one reduction, no |gx| temporary
+        return torch.exp2(torch.floor(torch.log2(self.scaler_state[1] / amax))).clamp(2.0 ** -60, 2.0 ** 60)
+
     # ------------------------------------------------------------------ forward
     def forward(self, img, pos_full, cls_token, save):
+        # a training forward opens an overflow window that its backward closes (mv_overflow_update); inference
+        # forwards report nothing
+        mv.set_overflow_flag(self.overflow if save else None)
+        if save:
+            self.overflow.zero_()
         if self.wide:
             return self._forward_wide(img, pos_full, cls_token, save)
         cfg, plan, fmt = self.cfg, self.cfg.plan, self.fmt
@@ -218,8 +242,7 @@ class EncoderEngine:
 
         # power-of-two gradient scale chosen on the device (no host sync)
         gx = gx.reshape(M, D)
-        amax = torch.linalg.vector_norm(gx, float("inf")).clamp_min(1e-30)          # one reduction, no |gx| temporary
-        S = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).clamp(2.0 ** -60, 2.0 ** 60)
+        S = self._gradient_scale(gx)
         dx, dx_h = mv.scale_f32(gx, S, want_f16=True)                             # fp32 master and fp16 operand in one pass
         self.gflat.zero_()
         last = cfg.depth - 1
@@ -270,19 +293,31 @@ class EncoderEngine:
         dpos = dpos.view(1, N, D)
         g[1].copy_(dpos[0, 1:].sum(0))                                     # bias: patch rows only
         inv = 1.0 / S
+        slot = None
         if self.reducer is not None:
+            # this rank's overflow flag rides in the slot in front of the last bucket (any positive value survives
+            # the 1 / (S * world) factor: S is clamped to 2^+-60)
+            self.gflat[0:1].copy_(self.overflow)
             self.reducer.reduce_slice(self.gflat[:self.offsets[2]], inv)
             self.reducer.wait()
+            slot = self.gflat[0:1]
         dpos = dpos * inv
         dcls = dpos[:, 0:1, :].clone()
-        # hand autograd its own copy: self.gflat is reused (zeroed) by the next backward
+        # hand autograd its own copy: self.gflat is reused (zeroed) by the next backward.  The same pass un-scales
+        # (single GPU) and tests every parameter gradient for inf / NaN (the overflow sink)
         if self.reducer is not None:
-            out = self.gflat.clone()
+            out, _ = mv.scale_f32(self.gflat, self._one(), invert=False)
         else:
-            out, _ = mv.scale_f32(self.gflat, S, invert=True)                     # un-scale and copy in one pass
+            out, _ = mv.scale_f32(self.gflat, S, invert=True)
+        mv.overflow_update(self.overflow, self.scaler_state, shared_slot=slot)
         grads = [out[self.offsets[i]:self.offsets[i] + p.numel()].view_as(p)
                  for i, p in enumerate(self.params)]
         return dpos, dcls, grads
+
+    def _one(self):
+        if getattr(self, "_one_t", None) is None:
+            self._one_t = torch.ones(1, dtype=torch.float32, device=self.dev)
+        return self._one_t
 
 
     # ------------------------------------------------- 32-bit formats (TF32 / FP32)
@@ -382,9 +417,8 @@ class EncoderEngine:
         # the fp16 attention backward wants its gradient operand inside fp16's range: same
         # power-of-two scale as the 16-bit path, removed from the parameter gradients at the end
         gx = gx.reshape(M, D)
-        amax = gx.abs().amax().clamp_min(1e-30)
-        S = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).clamp(2.0 ** -60, 2.0 ** 60)
-        dx = gx * S
+        S = self._gradient_scale(gx)
+        dx, _ = mv.scale_f32(gx, S)
         self.gflat.zero_()
         last = cfg.depth - 1
         mv.colsum(dx, g[2 + PER_LAYER * last + 11].view(-1))

@@ -121,6 +121,24 @@ def _need_cuda(*ts):
             raise MvError("myrtle-vision_b200 kernels need CUDA tensors (there is no CPU fallback)")
 
 
+def set_overflow_flag(flag):
+    """Register the device int32 the backward kernels raise on fp16 saturation / non-finite gradients (None: off)."""
+    if flag is not None:
+        _need_cuda(flag)
+        assert flag.dtype == torch.int32 and flag.numel() >= 1
+    _check(lib().mv_set_overflow_flag(_ptr(flag)), "mv_set_overflow_flag")
+
+
+def overflow_update(flag, state, shared_slot=None, backoff=1.0 / 16, growth=2.0, growth_interval=2000,
+                    min_target=2.0 ** -10, max_target=1024.0):
+    """state fp32 [3] = {found_inf, scale_target, good_steps} (mv_overflow_update in include/mv_b200.h)."""
+    _need_cuda(flag, state)
+    assert state.dtype == torch.float32 and state.numel() == 3 and flag.dtype == torch.int32
+    _check(lib().mv_overflow_update(_ptr(flag), _ptr(shared_slot), _ptr(state), ctypes.c_float(backoff),
+                                    ctypes.c_float(growth), int(growth_interval), ctypes.c_float(min_target),
+                                    ctypes.c_float(max_target), _stream()), "mv_overflow_update")
+
+
 def launch_count():
     return int(lib().mv_launch_count())
 

@@ -30,8 +30,12 @@ class GradReducer:
 
     def reduce_slice(self, flat, inv_scale=1.0):
         """flat <- mean over ranks of (flat * inv_scale); asynchronous on the comm stream."""
-        flat.mul_(inv_scale / self.world if not torch.is_tensor(inv_scale)
-                  else inv_scale / self.world)
+        if flat.is_cuda and torch.is_tensor(inv_scale):
+            # one pass: un-scale, divide by the world size and test for inf / NaN (the library's overflow sink)
+            import mv_native as mv
+            mv.scale_f32(flat, (inv_scale / self.world).reshape(1).float(), out=flat)
+        else:
+            flat.mul_(inv_scale / self.world)
         self.buckets_reduced += 1
         if self.world == 1:
             return

@@ -206,7 +206,13 @@ def train_deit(rank, num_gpus, config, task=None, max_iterations=None):
             n_accum += 1
             if n_accum == n_batch_accum:
                 n_accum = 0
-                optimizer.step()
+                if hasattr(optimizer, "_operands"):
+                    # FusedAdamW: the backward's device-side overflow flag skips the update exactly like
+                    # GradScaler.step() in the reference (classification/train.py:274-277), without a host sync
+                    optimizer.step(found_inf=vit.engine().found_inf)
+                    vit.engine().found_inf.zero_()
+                else:
+                    optimizer.step()
                 iteration += 1
                 if rank == 0 and iteration % log_every == 0:
                     history.append(float(loss.detach()))

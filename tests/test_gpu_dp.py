@@ -46,6 +46,16 @@ def _worker(rank, world, port, ret):
             else:
                 assert p.grad is None, n
         ret[rank] = worst
+        # overflow flag under data parallelism: a saturation that only rank 1 sees reaches every rank through the slot
+        # in front of the last gradient bucket (no extra collective), so all replicas skip the same step
+        eng = model.engine()
+        assert float(eng.found_inf) == 0.0
+        if rank == 1:
+            eng.scaler_state[1] = 2.0 ** 40               # rank 1 only: its fp16 gradient operands saturate
+        model.zero_grad()
+        F.cross_entropy(dp(img[shard].to(dev)), y[shard].to(dev)).backward()
+        torch.cuda.synchronize()
+        ret["found_inf_%d" % rank] = float(eng.found_inf)
     finally:
         dist.destroy_process_group()
 
@@ -59,3 +69,4 @@ def test_two_rank_gradients_match_single_gpu():
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     # fp16 tensor-core operands with per-rank power-of-two scales: 5e-3 relative L2
     assert ret[0] < 5e-3 and ret[1] < 5e-3, dict(ret)
+    assert ret["found_inf_0"] == 1.0 and ret["found_inf_1"] == 1.0, dict(ret)

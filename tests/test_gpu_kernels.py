@@ -143,7 +143,8 @@ def test_layernorm_q(D):
 
 @pytest.mark.parametrize("sn", [1, 0])
 @pytest.mark.parametrize("B,H,N", [(1, 1, 64), (1, 1, 128), (2, 2, 257), (2, 3, 197), (1, 2, 1000), (1, 1, 17),
-                                   (2, 1, 130), (2, 1, 131), (2, 1, 256), (1, 2, 272), (1, 1, 273), (40, 6, 257)])
+                                   (2, 1, 130), (2, 1, 131), (2, 1, 256), (1, 2, 272), (1, 1, 273), (40, 6, 257),
+                                   (1, 6, 2501)])      # last: BASELINE config 5 (800 x 800 -> N = 2501), both det settings
 def test_attention_fwd_bwd(B, H, N, sn, request):
     """sn=1: short-sequence kernels (attention_sn.cu, N <= 272); sn=0: the general streaming kernels."""
     import mv_native as mv

@@ -109,3 +109,48 @@ def test_ptq_eval_flow_from_an_fp32_checkpoint(tmp_path):
     for m in vit.modules():
         if isinstance(m, (nn.Linear, nn.LayerNorm)):
             assert torch.equal(m.weight, m.weight.half().float())
+
+
+def test_overflow_flag_skips_the_step_and_backs_off():
+    """The device-side replacement of the reference's GradScaler (classification/train.py:167, 259-277): an inf in the
+    incoming gradient or a saturated fp16 gradient operand raises found_inf without a host sync, FusedAdamW skips the
+    update, the operand scale backs off by 16 and recovers after clean steps."""
+    import torch.nn.functional as F
+    from myrtle_vision.models.vit import ViT
+    from myrtle_vision.utils.fused_adamw import FusedAdamW
+    from myrtle_vision.utils.optim import add_weight_decay
+    dev = "cuda"
+    torch.manual_seed(2)
+    m = ViT(decoder="classification", image_size=80, patch_size=16, num_classes=5, dim=128, depth=2, heads=2,
+            mlp_dim=256, q_format="FP16_32").to(dev).train()
+    opt = FusedAdamW(add_weight_decay(m, 0.05), lr=1e-2, model=m)
+    img = torch.randn(4, 3, 80, 80, device=dev).clamp(-1, 1)
+    tgt = torch.randint(0, 5, (4,), device=dev)
+    eng = m.engine()
+
+    def step(scale=1.0):
+        m.zero_grad(set_to_none=True)
+        (F.cross_entropy(m(img), tgt) * scale).backward()
+        found = float(eng.found_inf)
+        opt.step(found_inf=eng.found_inf)
+        eng.found_inf.zero_()
+        return found
+
+    w = dict(m.named_parameters())["transformer.layers.0.0.fn.fn.to_qkv.1.weight"]
+    w0 = w.detach().clone()
+    assert step() == 0.0 and float(eng.scaler_state[1]) == 1024.0
+    w1 = w.detach().clone()
+    assert not torch.equal(w1, w0)                                   # a clean step updates
+    assert step(float("inf")) == 1.0                                 # inf / NaN in the incoming gradient
+    assert torch.equal(w, w1) and float(eng.scaler_state[1]) == 64.0  # skipped, scale backed off by 16
+    eng.scaler_state[1] = 2.0 ** 40                                  # operands far outside fp16: saturation
+    assert step() == 1.0
+    assert torch.equal(w, w1) and float(eng.scaler_state[1]) == 2.0 ** 36
+    eng.scaler_state[1] = 1024.0
+    assert step() == 0.0 and not torch.equal(w, w1)
+    # growth after `growth_interval` clean backwards (mv_overflow_update)
+    import mv_native
+    eng.scaler_state[1] = 64.0
+    for _ in range(3):
+        mv_native.overflow_update(eng.overflow.zero_(), eng.scaler_state, growth_interval=3)
+    assert float(eng.scaler_state[1]) == 128.0 and float(eng.scaler_state[2]) == 0.0
