@@ -34,8 +34,11 @@ for _p in (ROOT, os.path.join(ROOT, "myrtle-vision_b200")):
 ARCH = dict(dim=384, depth=12, heads=6, mlp_dim=1536)
 IMAGE, PATCH, CLASSES = 256, 16, 45
 METRIC = "train images/sec, quantised ViT fwd+bwd"
-DTYPES = {"FP16_32": "f16 operands (exact fake-quant containers), f32 accumulate",
-          "FP16_16": "f16 operands (exact fake-quant containers), f32 accumulate",
+DTYPES = {"FP16_32": "f16 tensor-core operands, f32 accumulate: fake-quantised tensors are exact in their f16 containers; the "
+                     "tensors the reference leaves in f32 (qkv, attention probabilities, activation gradients) are also "
+                     "rounded to f16 (11 significant bits, f16 range; saturation raises the device overflow flag)",
+          "FP16_16": "f16 tensor-core operands (exact fake-quant containers; attention probabilities and activation "
+                     "gradients rounded to f16, overflow flagged), f32 accumulate",
           "TF32": "tf32 operands (exact (8,10) fake-quant values in f32 containers), f32 accumulate",
           "FP32": "tf32 tensor-core products of f32 operands, f32 accumulate"}
 
@@ -213,6 +216,202 @@ def cpu_baseline_subprocess(q_format):
 
 
 # ------------------------------------------------------------------------------------------
+def roofline_entries(kern, work, steps, peaks):
+    """Per kernel class: launches, ms per step and — from the ALGORITHMIC flop / bytes of one launch (recorded by
+    mv_native at call time) — the roofline that bounds it: whichever of flop / tensor peak and
+    bytes / HBM peak is the longer time.  Returns (breakdown dict, entry of the class with the most time)."""
+    t_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    h_peak = peaks.get("hbm_gbs", 6650.0)
+    breakdown, top = {}, None
+    for name, (cnt, tot) in sorted(kern.items(), key=lambda kv: -kv[1][1]):
+        entry = {"launches_per_step": cnt / steps, "ms_per_step": tot / steps}
+        flop, nbytes = work.get(name, (0.0, 0.0))
+        if cnt and (flop or nbytes):
+            avg_ms = tot / cnt
+            t_tensor = flop / (t_peak * 1e9)          # ms at the sustained tensor peak
+            t_hbm = nbytes / (h_peak * 1e6)           # ms at the measured copy bandwidth
+            if t_tensor >= t_hbm:
+                entry.update({"bound": "tensor", "achieved": flop / avg_ms / 1e9, "unit": "TFLOP/s", "peak": t_peak,
+                              "frac": t_tensor / avg_ms})
+            else:
+                entry.update({"bound": "hbm", "achieved": nbytes / avg_ms / 1e6, "unit": "GB/s", "peak": h_peak,
+                              "frac": t_hbm / avg_ms})
+            entry.update({"avg_launch_ms": avg_ms, "floor_ms": max(t_tensor, t_hbm),
+                          "algorithmic_flop": flop, "algorithmic_bytes": nbytes})
+            if top is None:
+                top = dict(entry, kernel=name)
+        breakdown[name] = entry
+    return breakdown, top
+
+
+def build_task(task, q_format, batch, dev, arch=None):
+    """(model, criterion, [two device batches]) of a BASELINE.json config: classification 256^2 / 45 classes,
+    segmentation 256^2 / 17 classes (fused upsample + CE), detection 800^2 / 20 classes (N = 2501, padded targets,
+    device matching).  Synthetic RESISC45 / DLRSD / DIOR-shaped data, random-init weights."""
+    import torch
+    from myrtle_vision.datasets.synthetic import SyntheticVision, detection_collate
+    from myrtle_vision.models.vit import ViT
+    from myrtle_vision.utils.trainer import build_criterion, to_device
+    size, classes = {"classification": (IMAGE, CLASSES), "segmentation": (256, 17), "detection": (800, 20)}[task]
+    torch.manual_seed(1234)
+    model = ViT(decoder=task, image_size=size, patch_size=PATCH, num_classes=classes, q_format=q_format,
+                **(arch or ARCH)).to(dev).train()
+    if task == "classification":
+        g = torch.Generator().manual_seed(1234)
+        batches = [(torch.randn(batch, 3, size, size, generator=g).clamp(-1, 1),
+                    torch.randint(0, classes, (batch,), generator=g)) for _ in range(2)]
+    else:
+        ds = SyntheticVision(task, 2 * batch, size, classes, seed=1234)
+        items = [ds[i] for i in range(2 * batch)]
+        if task == "detection":
+            from myrtle_vision.models.matcher import pad_targets
+            batches = [detection_collate(items[:batch]), detection_collate(items[batch:])]
+            cap = -(-max(int(t["boxes"].shape[0]) for _, ts in batches for t in ts) // 16) * 16
+            batches = [(img, pad_targets(ts, capacity=cap)) for img, ts in batches]
+        else:
+            batches = [(torch.stack([a for a, _ in part]), torch.stack([b for _, b in part]))
+                       for part in (items[:batch], items[batch:])]
+    batches = [(img.to(dev), to_device(t, dev)) for img, t in batches]
+    cfg = {"loss_ce": 1.0, "class_error": 0.0, "loss_bbox": 5.0, "loss_giou": 2.0, "cardinality_error": 0.0,
+           "eos_coef": 0.1, "fused_seg_loss": True}
+    criterion = build_criterion(task, cfg, classes, dev)
+    if task == "segmentation":
+        model.decoder.fused_loss = True
+    return model, criterion, batches, (size // PATCH) ** 2 + 1
+
+
+def time_config(name, task, q_format, batch, dev, steps, peaks):
+    """One secondary BASELINE.json config on this GPU: a short eager leg for the per-kernel roofline, then the step
+    as one CUDA graph, `steps` timed replays after 10 warm-up replays (inputs resident, alternating batches)."""
+    import torch
+    import mv_native
+    from myrtle_vision.utils.graph import GraphedTrainStep
+    model, criterion, batches, n_tok = build_task(task, q_format, batch, dev)
+
+    def eager(img, tgt):
+        model.zero_grad(set_to_none=True)
+        loss = criterion(model(img), tgt)
+        loss.backward()
+        return loss
+
+    for i in range(3):
+        eager(*batches[i % 2])
+    torch.cuda.synchronize()
+    mv_native.enable_timing(True)
+    for i in range(2):
+        eager(*batches[i % 2])
+    torch.cuda.synchronize()
+    breakdown, top = roofline_entries(mv_native.timing_summary(), mv_native.work_summary(), 2, peaks)
+    mv_native.enable_timing(False)
+    gs = GraphedTrainStep(model, criterion, *batches[0])
+    for i in range(10):
+        gs(*batches[i % 2])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        gs(*batches[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    fl = flops_per_image(n_tok, ARCH["dim"], ARCH["depth"], ARCH["mlp_dim"], 0)
+    out = {"workload": name, "images_per_s": batch / ms * 1e3, "ms_per_step": ms, "batch": batch, "tokens": n_tok,
+           "q_format": q_format, "steps": steps, "model_tflops": batch / ms * 1e3 * fl / 1e12,
+           "dominant_kernel": ({k: top[k] for k in ("kernel", "bound", "achieved", "unit", "frac", "avg_launch_ms")}
+                               if top else None),
+           "top_kernels_ms_per_step": {k: round(v["ms_per_step"], 3) for k, v in list(breakdown.items())[:6]}}
+    del gs, model, criterion, batches
+    torch.cuda.empty_cache()
+    return out
+
+
+def quant_microbench(dev, peaks):
+    """Second half of BASELINE.json's metric: HBM GB/s of the standalone fake-quant kernels, SURVEY.md section 8d set.
+    Input (i): 2^28 fp32 = 1 GiB, randn * exp(U(-12, 8)) (normal, subnormal and saturating branches all run);
+    algorithmic bytes per element: 8 (fp32 -> fp32), 6 (fp16 container), 12 (block: max pass + quant pass).  Every
+    launch moves >= 1.5 GiB, far beyond the 126 MB L2.  Input (ii): model-shaped tensors, rotated over enough
+    buffers that consecutive launches never find their data in L2."""
+    import torch
+    import mv_native
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    gq = torch.Generator(device=dev).manual_seed(1234)
+    nq = 1 << 28
+    xq = torch.randn(nq, device=dev, generator=gq)
+    xq.mul_(torch.exp(torch.empty(nq, device=dev).uniform_(-12, 8, generator=gq)))
+    oq = torch.empty_like(xq)
+    oh = torch.empty(nq, dtype=torch.float16, device=dev)
+    x2 = xq.view(16384, 16384)
+    quant = {"unit": "GB/s", "elements": nq, "peak": hbm_peak,
+             "peak_source": "MEASURED_PEAKS.json (hbm_gbs)" if peaks else "fallback",
+             "input": "randn * exp(U(-12, 8)), 2^28 fp32, seed 1234"}
+
+    def timed(fn, bytes_per_launch, reps=10):
+        for _ in range(3):
+            fn()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(reps):
+            fn()
+        q1.record()
+        torch.cuda.synchronize()
+        gbs = bytes_per_launch * reps / q0.elapsed_time(q1) / 1e6
+        return {"value": gbs, "frac": gbs / hbm_peak, "bytes_per_element": bytes_per_launch / nq}
+
+    st = dict(rounding="stochastic", seed=1234, offset=0)
+    cases = [
+        ("float(5,10) nearest", lambda: mv_native.float_quantize(xq, 5, 10, out=oq), 8),
+        ("float(5,10) stochastic", lambda: mv_native.float_quantize(xq, 5, 10, out=oq, **st), 8),
+        ("float(8,10) nearest", lambda: mv_native.float_quantize(xq, 8, 10, out=oq), 8),
+        ("float(8,10) stochastic", lambda: mv_native.float_quantize(xq, 8, 10, out=oq, **st), 8),
+        ("float(5,10) nearest -> fp16 container", lambda: mv_native.float_quantize(xq, 5, 10, out=oh), 6),
+        ("float(5,10) stochastic -> fp16 container", lambda: mv_native.float_quantize(xq, 5, 10, out=oh, **st), 6),
+    ]
+    for fl in (9, 8, 7):                      # the reference's three 11-bit fixed-point formats (utils/quantize.py:58-72)
+        cases.append(("fixed(11,%d) nearest" % fl, lambda fl=fl: mv_native.fixed_point_quantize(xq, 11, fl, out=oq), 8))
+        cases.append(("fixed(11,%d) stochastic" % fl,
+                      lambda fl=fl: mv_native.fixed_point_quantize(xq, 11, fl, out=oq, **st), 8))
+    cases += [
+        ("block(wl=8, dim=-1) nearest", lambda: mv_native.block_quantize(xq, 8, dim=-1, out=oq), 12),
+        ("block(wl=8, dim=0) nearest", lambda: mv_native.block_quantize(x2, 8, dim=0, out=oq.view(16384, 16384)), 12),
+        ("block(wl=8, dim=0) stochastic",
+         lambda: mv_native.block_quantize(x2, 8, dim=0, out=oq.view(16384, 16384), **st), 12),
+    ]
+    for label, fn, bpe in cases:
+        quant[label] = timed(fn, float(bpe) * nq)
+    # (ii) model-shaped activations / weights of ViT-Small at batch 256, float(5,10) nearest, rotating buffers
+    shaped = {}
+    for shape in ((256, 257, 384), (256, 257, 1536), (256, 256, 768), (1536, 384)):
+        n = 1
+        for d in shape:
+            n *= d
+        copies = max(2, min(64, (1 << 28) // n))
+        ins = [xq[i * n:(i + 1) * n].view(shape) for i in range(copies)]
+        outs = [oq[i * n:(i + 1) * n].view(shape) for i in range(copies)]
+        it = {"i": 0}
+
+        def fn():
+            k = it["i"] % copies
+            it["i"] += 1
+            mv_native.float_quantize(ins[k], 5, 10, out=outs[k])
+        for _ in range(copies):
+            fn()
+        reps = 4 * copies
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(reps):
+            fn()
+        q1.record()
+        torch.cuda.synchronize()
+        us = q0.elapsed_time(q1) / reps * 1e3
+        shaped["x".join(str(d) for d in shape)] = {"us_per_launch": us, "value": 8.0 * n / us / 1e3,
+                                                   "frac": 8.0 * n / us / 1e3 / hbm_peak, "buffers": copies}
+    quant["model_shaped float(5,10) nearest"] = shaped
+    del xq, oq, oh
+    torch.cuda.empty_cache()
+    return quant
+
+
+# ------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -272,7 +471,7 @@ def run_b200(args):
     barrier()
     ms_eager = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     launches_per_step = (mv_native.launch_count() - n0) // args.steps
-    kern = mv_native.timing_summary()
+    kern, work = mv_native.timing_summary(), mv_native.work_summary()
     mv_native.enable_timing(False)
 
     # ---- timed region 1 (`value`): the same step captured in a CUDA graph, inputs resident in HBM
@@ -299,6 +498,26 @@ def run_b200(args):
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     launches = launches_per_step * args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # data parallel: the same graph without the gradient all-reduces -> the communication time that backward does
+    # not hide (exposed_comm_ms), measured in this run instead of inferred from a separate N = 1 run
+    exposed_comm_ms = None
+    if world > 1 and use_graph:
+        eng = model.engine()
+        saved_reducer, eng.reducer = eng.reducer, None
+        g2 = GraphedTrainStep(model, F.cross_entropy, resident[0][0], resident[0][1])
+        for i in range(10):
+            g2(*resident[i % 2])
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            g2(*resident[i % 2])
+        e1.record()
+        barrier()
+        ms_nocomm = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        exposed_comm_ms = ms_step - ms_nocomm
+        eng.reducer = saved_reducer
+        del g2
 
     # ---- timed region 2 (e2e): every step copies its batch from pinned host memory (prefetched one
     # step ahead on a copy stream) and reads the loss back to the host
@@ -349,20 +568,7 @@ def run_b200(args):
     with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
         peaks = json.load(f) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     n_tok = (IMAGE // PATCH) ** 2 + 1
-    M, D, Mm, H, L = B * n_tok, ARCH["dim"], ARCH["mlp_dim"], ARCH["heads"], ARCH["depth"]
-    def per_launch_work(name):
-        """(bound, ALGORITHMIC flop or bytes of ONE launch) — DESIGN.md §4 per-unit figures x units per launch."""
-        if name.startswith("gemm_"):
-            m, n, k = (int(v) for v in name.rsplit("_", 1)[1].split("x"))
-            return "tensor", 2.0 * m * n * k
-        table = {
-            "attn_fwd": ("tensor", 4.0 * B * H * n_tok * n_tok * 64),
-            "attn_bwd": ("tensor", 10.0 * B * H * n_tok * n_tok * 64),
-            "ln_fwd": ("hbm", M * D * 6.0),
-            "ln_bwd": ("hbm", M * D * 16.0),      # x 4 + dy 2 (fp16) + dres 4 read, dx 4 + fp16 copy 2 written
-        }
-        return table.get(name, (None, None))
-
+    D, Mm, L = ARCH["dim"], ARCH["mlp_dim"], ARCH["depth"]
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -370,50 +576,40 @@ def run_b200(args):
             traffic = json.load(f).get("dram_bytes_per_launch", {})
     breakdown, roofline = {}, None
     if kern:
-        for name, (cnt, tot) in sorted(kern.items(), key=lambda kv: -kv[1][1]):
-            entry = {"launches_per_step": cnt / args.steps, "ms_per_step": tot / args.steps}
-            bound, work = per_launch_work(name)
-            if bound is not None:
-                avg_ms = tot / cnt
-                if bound == "tensor":
-                    peak, ach, unit = peaks.get("bf16_tflops_sustained", 1400.0), work / avg_ms / 1e9, "TFLOP/s"
-                else:
-                    peak, ach, unit = peaks.get("hbm_gbs", 6650.0), work / avg_ms / 1e6, "GB/s"
-                entry.update({"bound": bound, "achieved": ach, "unit": unit, "frac": ach / peak,
-                              "avg_launch_ms": avg_ms})
-                if roofline is None:              # the dominant kernel (most time per step)
-                    roofline = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
-                                "frac": ach / peak, "traffic": traffic.get(name),
-                                "peak_source": "MEASURED_PEAKS.json (sustained)" if peaks else "fallback",
-                                "avg_launch_ms": avg_ms, "algorithmic_per_launch": work}
-            breakdown[name] = entry
+        breakdown, top = roofline_entries(kern, work, args.steps, peaks)
+        if top is not None:              # the dominant kernel (most time per step)
+            roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"],
+                        "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
+                        "traffic": traffic.get(top["kernel"]),
+                        "peak_source": "MEASURED_PEAKS.json (%s)" % ("bf16_tflops_sustained" if top["bound"] == "tensor"
+                                                                     else "hbm_gbs") if peaks else "fallback",
+                        "avg_launch_ms": top["avg_launch_ms"],
+                        "algorithmic_per_launch": top["algorithmic_flop"] if top["bound"] == "tensor"
+                        else top["algorithmic_bytes"]}
 
-    # second half of BASELINE.json's metric: HBM GB/s of the standalone fake-quant kernels (SURVEY.md §8d input:
-    # 2^28 fp32 = 1 GiB, randn * exp(U(-12, 8)) so that normal, subnormal and saturating branches all run;
-    # 8 algorithmic bytes per element, timed with CUDA events, 2 GiB per launch >> 126 MB L2)
-    quant = None
-    if world == 1 and not args.no_quant_bench:
-        gq = torch.Generator(device=dev).manual_seed(1234)
-        nq = 1 << 28
-        xq = torch.randn(nq, device=dev, generator=gq)
-        xq.mul_(torch.exp(torch.empty(nq, device=dev).uniform_(-12, 8, generator=gq)))
-        oq = torch.empty_like(xq)
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        quant = {"unit": "GB/s", "elements": nq, "bytes_per_element": 8, "peak": hbm_peak,
-                 "peak_source": "MEASURED_PEAKS.json (hbm_gbs)" if peaks else "fallback"}
-        for label, kw in (("float(5,10) nearest", dict(rounding="nearest")),
-                          ("float(5,10) stochastic", dict(rounding="stochastic", seed=1234, offset=0))):
-            for _ in range(3):
-                mv_native.float_quantize(xq, 5, 10, out=oq, **kw)
-            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            q0.record()
-            for _ in range(10):
-                mv_native.float_quantize(xq, 5, 10, out=oq, **kw)
-            q1.record()
-            torch.cuda.synchronize()
-            gbs = 8.0 * nq * 10 / q0.elapsed_time(q1) / 1e6
-            quant[label] = {"value": gbs, "frac": gbs / hbm_peak}
-        del xq, oq
+    # the main model is done: release it before the secondary workloads
+    if world == 1:
+        del model, net, resident, bufs
+        if use_graph:
+            del gstep, run_step
+        torch.cuda.empty_cache()
+
+    # BASELINE.json's other configs and the secondary formats of config 2, on this GPU, same harness
+    # (segmentation/train.py:254-290, detection/train.py:247-287)
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = {}
+        for name, task, fmt, bsz in (("cls256 FP16_16", "classification", "FP16_16", args.batch),
+                                     ("cls256 TF32", "classification", "TF32", args.batch),
+                                     ("seg256 (config 4)", "segmentation", args.q_format, args.batch),
+                                     ("det800 (config 5)", "detection", args.q_format, 8)):
+            try:
+                configs[name] = time_config(name, task, fmt, bsz, dev, max(3, min(args.steps, 10)), peaks)
+            except Exception as e:       # a secondary workload must not cost the headline line
+                configs[name] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
+
+    quant = quant_microbench(dev, peaks) if world == 1 and not args.no_quant_bench else None
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -441,11 +637,13 @@ def run_b200(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "last_loss": loss_host},
         "gpu_launches": launches,
         "cuda_graph": use_graph,
+        "exposed_comm_ms": exposed_comm_ms,
         "eager_ms_per_step": ms_eager,
         "host_enqueue_ms_per_step_eager": host_enqueue_ms,
         "model_tflops": value * fl / 1e12,
         "roofline": roofline,
         "kernels": breakdown,
+        "configs": configs,
         "quant_kernels": quant,
         "cpu_baseline": cpu,
     }
@@ -468,6 +666,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-quant-bench", action="store_true", help="skip the fake-quant kernel GB/s microbench")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary workloads (FP16_16, TF32, seg256, det800)")
     ap.add_argument("--no-graph", action="store_true", help="time the eagerly launched step instead of the CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -75,11 +75,19 @@ def _check(rc, what):
 
 # Optional per-kernel-class CUDA-event timing (bench.py's roofline leg).  Off by default.
 _TIMERS = None
+_WORK = {}      # class -> (algorithmic flop, algorithmic HBM bytes) of ONE launch (DESIGN.md section 4 figures)
 
 
 def enable_timing(on=True):
     global _TIMERS
     _TIMERS = {} if on else None
+    if on:
+        _WORK.clear()
+
+
+def work_summary():
+    """{class: (flop per launch, bytes per launch)} for the classes timed since enable_timing(True)."""
+    return dict(_WORK)
 
 
 def timing_summary():
@@ -91,8 +99,10 @@ def timing_summary():
 
 
 class _timed:
-    def __init__(self, name):
+    def __init__(self, name, flop=0.0, nbytes=0.0):
         self.name = name
+        if _TIMERS is not None:
+            _WORK[name] = (float(flop), float(nbytes))
 
     def __enter__(self):
         if _TIMERS is not None:
@@ -161,10 +171,12 @@ def float_quantize(x, exp, man, rounding="nearest", seed=0, offset=0, out=None,
 
 
 def fixed_point_quantize(x, wl, fl, clamp=True, symmetric=False, rounding="nearest", seed=0,
-                         offset=0, with_mask=False):
+                         offset=0, with_mask=False, out=None):
     _need_cuda(x)
     x = x.contiguous().float()
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == x.numel()
     mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if with_mask else None
     rc = lib().mv_fixed_point_quantize(_ptr(x), _ptr(out), _ptr(mask), ctypes.c_int64(x.numel()),
                                        int(wl), int(fl), int(bool(clamp)), int(bool(symmetric)),
@@ -174,10 +186,12 @@ def fixed_point_quantize(x, wl, fl, clamp=True, symmetric=False, rounding="neare
     return (out, mask) if with_mask else out
 
 
-def block_quantize(x, wl, dim=-1, rounding="nearest", seed=0, offset=0):
+def block_quantize(x, wl, dim=-1, rounding="nearest", seed=0, offset=0, out=None):
     _need_cuda(x)
     x = x.contiguous().float()
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == x.numel()
     if dim is None or dim < 0:
         outer, dsize, inner, whole = 1, 1, x.numel(), 1
     else:
@@ -263,9 +277,20 @@ def gemm(A, B, out, *, a_major=0, b_major=0, bias=None, residual=None, aux=None,
         a.colsum = colsum.data_ptr()
     kind = "gemm_wgrad" if accumulate else ("gemm_dgrad" if epilogue == EPI_DGELU or tag == "dgrad"
                                             else "gemm_fwd")
+    flop = nbytes = 0.0
     if _TIMERS is not None:
         kind = "%s_%dx%dx%d" % (kind, M, N, K)    # one roofline line per GEMM shape (M x N x K)
-    with _timed(kind):
+        # algorithmic traffic: both operands once, every output once, epilogue operands once
+        flop = 2.0 * M * N * K
+        nbytes = (M * K * A.element_size() + N * K * B.element_size() + M * N * out.element_size()
+                  * (2 if accumulate else 1))
+        if residual is not None:
+            nbytes += (rows_per_img if rows_per_img else M) * N * 4
+        if aux is not None:
+            nbytes += M * N * 2
+        if out2 is not None:
+            nbytes += M * N * out2.element_size()
+    with _timed(kind, flop, nbytes):
         _check(lib().mv_gemm(ctypes.byref(a), _stream()), "mv_gemm")
     return out
 
@@ -286,7 +311,7 @@ def layernorm_q_fwd(x, gamma, beta, *, q_in=None, q_post=None, out_dtype=torch.f
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     qi, qp = _fmt(q_in), _fmt(q_post)
-    with _timed("ln_fwd"):
+    with _timed("ln_fwd", 0.0, rows * D * (4 + y.element_size())):
         rc = lib().mv_layernorm_q_fwd(_ptr(x2), ctypes.c_int64(x2.stride(0)), _ptr(gamma), _ptr(beta),
                                       _ptr(y), ctypes.c_int64(D), _DT[out_dtype], _ptr(mean), _ptr(rstd),
                                       rows, D, ctypes.c_float(eps), qi[0], qi[1], qp[0], qp[1], _stream())
@@ -307,7 +332,9 @@ def layernorm_q_bwd(dy, x, gamma, mean, rstd, *, dres=None, q_in=None, dgamma=No
         dx_f16 = torch.empty(rows, D, dtype=torch.float16, device=x.device)
     dres2 = dres.reshape(-1, D) if dres is not None else None
     qi = _fmt(q_in)
-    with _timed("ln_bwd"):
+    # x 4 + dy + dres 4 read, dx 4 + fp16 copy 2 written
+    with _timed("ln_bwd", 0.0, rows * D * (4 + dy2.element_size() + (4 if dres is not None else 0) + 4
+                                            + (2 if dx_f16 is not None else 0))):
         rc = lib().mv_layernorm_q_bwd(_ptr(dy2), _DT[dy2.dtype], ctypes.c_int64(dy2.stride(0)), _ptr(x2),
                                       ctypes.c_int64(x2.stride(0)), _ptr(dres2),
                                       ctypes.c_int64(dres2.stride(0) if dres2 is not None else D),
@@ -322,7 +349,7 @@ def layernorm_q_bwd(dy, x, gamma, mean, rstd, *, dres=None, q_in=None, dgamma=No
 def colsum(x2d, out):
     _need_cuda(x2d, out)
     assert x2d.dim() == 2 and x2d.stride(1) == 1 and out.dtype == torch.float32
-    with _timed("colsum"):
+    with _timed("colsum", 0.0, x2d.numel() * x2d.element_size()):
         rc = lib().mv_colsum(_ptr(x2d), _DT[x2d.dtype], ctypes.c_int64(x2d.stride(0)), x2d.shape[0],
                              x2d.shape[1], _ptr(out), _stream())
     _check(rc, "mv_colsum")
@@ -336,7 +363,7 @@ def patchify_q(img, patch, q_in=None, out_dtype=torch.float16, cls_slot=False):
     rows = B * ((H // patch) * (W // patch) + (1 if cls_slot else 0))
     out = torch.empty(rows, patch * patch * C, dtype=out_dtype, device=img.device)
     q = _fmt(q_in)
-    with _timed("patchify"):
+    with _timed("patchify", 0.0, img.numel() * 4 + out.numel() * out.element_size()):
         _check(lib().mv_patchify_q(_ptr(img), _ptr(out), _DT[out_dtype], B, C, H, W, patch, q[0], q[1],
                                    int(bool(cls_slot)), _stream()), "mv_patchify_q")
     return out
@@ -450,7 +477,7 @@ def attention_fwd(qkv, B, H, N, *, scale=0.125, q_out=None, out_dtype=torch.floa
     if lse is None:
         lse = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
     q = _fmt(q_out)
-    with _timed("attn_fwd"):
+    with _timed("attn_fwd", 4.0 * B * H * N * N * 64, B * N * H * 64 * (3 * 2 + out.element_size())):
         rc = lib().mv_attention_fwd(_ptr(qkv), _ptr(out), _DT[out.dtype], _ptr(lse), B, H, N,
                                     ctypes.c_float(scale), q[0], q[1], _stream())
     _check(rc, "mv_attention_fwd")
@@ -472,7 +499,7 @@ def attention_bwd(qkv, o, d_o, lse, B, H, N, *, scale=0.125, dqkv=None, delta=No
         assert dbias.dtype == torch.float32 and dbias.is_contiguous() and dbias.numel() == 3 * H * 64
     if not deterministic and dq_accum is None:
         dq_accum = torch.empty(B * N, H * 64, dtype=torch.float32, device=qkv.device)
-    with _timed("attn_bwd"):
+    with _timed("attn_bwd", 10.0 * B * H * N * N * 64, B * N * H * 64 * 2 * (3 + 1 + 1 + 3)):
         rc = lib().mv_attention_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(delta),
                                     None if deterministic else _ptr(dq_accum), _ptr(dqkv), _ptr(dbias), B,
                                     H, N, ctypes.c_float(scale), _stream())
