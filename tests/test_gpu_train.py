@@ -151,6 +151,7 @@ def test_overflow_flag_skips_the_step_and_backs_off():
     # growth after `growth_interval` clean backwards (mv_overflow_update)
     import mv_native
     eng.scaler_state[1] = 64.0
+    eng.scaler_state[2] = 0.0
     for _ in range(3):
         mv_native.overflow_update(eng.overflow.zero_(), eng.scaler_state, growth_interval=3)
     assert float(eng.scaler_state[1]) == 128.0 and float(eng.scaler_state[2]) == 0.0
