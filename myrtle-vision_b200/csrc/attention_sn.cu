@@ -663,7 +663,15 @@ constexpr int kSnFwdSmem = 4 * kSnKVBytes + 2 * kSnTile + kSnTailWarps * (64 + k
 // and the 512 TMEM columns hold two blocks in flight (one per math group of 4 warps) + 4 accumulators.
 // Rows >= 256 (the 257th token) form a 16-wide tail block; their dQ has no TMEM accumulator and is
 // reduced on the CUDA cores into shared memory.  Keys beyond N are zero rows (TMA fill) and fall out.
-constexpr int kSnBwdThreads = 32 * (2 + 8);
+// 16 math warps: two per TMEM lane quadrant and block in flight (each takes 32 of the block's 64 columns), four per
+// scheduler, so that one warp's TMEM read / exp / TMEM write chain hides under the others'.  576 threads: 112 registers.
+// Two more warps do nothing but the per-row statistics (L, Delta) of the NEXT pair — cold global reads, kept a whole
+// pair ahead of the math warps.  Code that runs once per pass or pair (tail block, epilogues, statistics) is kept small
+// on purpose: the kernel is far larger than the instruction caches, and a rarely executed, fully unrolled section costs
+// more in instruction-fetch misses than in arithmetic (the 16-wide tail block took 5 000 cycles that way).
+constexpr int kSnBwdMathWarps = 16, kSnBwdStatWarps = 2;
+constexpr int kSnBwdMathThreads = 32 * kSnBwdMathWarps, kSnBwdStatThreads = 32 * kSnBwdStatWarps;
+constexpr int kSnBwdThreads = 32 * (2 + kSnBwdMathWarps + kSnBwdStatWarps);
 constexpr int kSnQBytes = kSnMaxKeys * 128;            // Q or dO of one pair: 272 rows x 128 B
 constexpr int kSnOffQ = 4 * kSnTile;
 constexpr int kSnOffDO = kSnOffQ + kSnQBytes;
@@ -716,7 +724,9 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     uint64_t* acc_empty = bars + 11;
     uint64_t* dq_full = bars + 12;
     uint64_t* dq_empty = bars + 13;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* st_full = bars + 14;      // [2] statistics buffer (pair parity) written by the stats warps
+    uint64_t* st_empty = bars + 16;     // [2] ... no longer read by the math warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     [[maybe_unused]] int trace_n = 0;
@@ -731,11 +741,12 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         tma_prefetch_desc(&tm_do128); tma_prefetch_desc(&tm_do16);
         for (int s = 0; s < 2; s++) {
             mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
-            mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], 4);
+            mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], kSnBwdMathWarps / 2);
         }
         mbar_init(qdo_full, 1); mbar_init(qdo_empty, 1);
-        mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
-        mbar_init(dq_full, 1); mbar_init(dq_empty, 8);
+        mbar_init(acc_full, 1); mbar_init(acc_empty, kSnBwdMathWarps);
+        mbar_init(dq_full, 1); mbar_init(dq_empty, kSnBwdMathWarps);
+        for (int s = 0; s < 2; s++) { mbar_init(&st_full[s], kSnBwdStatWarps); mbar_init(&st_empty[s], kSnBwdMathWarps); }
         fence_barrier_init();
     }
     // the dS^T tiles feed a K dimension: rows of keys that no thread writes must hold finite values
@@ -882,58 +893,44 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                 }
             }
         }
-    } else {
-        // ================================ math: two groups of four warps, one thread per key ================================
-        const int quad = warp & 3;
-        const int g = (warp - 2) >> 2;
-        const int lr = quad * 32 + lane;                     // key row within the 128-key tile = TMEM lane
-        const int mt = threadIdx.x - 64;                     // 0..255
-        const uint32_t lane_off = uint32_t(quad * 32) << 16;
-        const uint32_t tS = tmem_base + g * 128 + lane_off, tdP = tS + 64;
-        int gb0 = 0, pc0 = 0;
-        // Fused to_qkv bias gradient (p.dbias != NULL; the host then sizes the grid so that a CTA stays on one head
-        // and the sums are flushed once, after the last pair):
-        //   q: column sums of the dQ rows this warp stores (cs_q) and, per thread, columns 2 * lane, 2 * lane + 1 of
-        //      the dQ rows >= 256 (cs_t0 / cs_t1);
-        //   k: nothing to add — sum_k dS[q, k] = sum_k P (dP - Delta_q) = 0, the key bias never reaches the softmax;
-        //   v: sum_k dV[k, :] = sum_q (sum_k P[q, k]) dO[q, :] = the column sums of dO, which stats_rows has in
-        //      registers anyway (cs_v: this thread's 16-byte chunk of the head, every row it visits).
-        float cs_q[2][8], cs_v[8], cs_t0 = 0.f, cs_t1 = 0.f;
-        float amax = 0.f;                                   // largest |dqkv| value stored (overflow sink)
+    } else if (warp >= 2 + kSnBwdMathWarps) {
+        // ================================ statistics warps ================================
+        // Per-row statistics of every pair (L from the forward, Delta = rowsum(dO * O)); rows >= N get L = +inf so that
+        // their P is exactly 0.  Double-buffered by pair parity and written a whole pair ahead of the math warps, so the
+        // cold global reads never sit on anybody's critical path.  Eight lanes share a row (one 16-byte chunk of the
+        // head's 128 B each): a warp instruction reads four whole lines; four row groups are in flight per thread.
+        // cs_v: column sums of dO (this lane's chunk, every row it visits) — the v part of the fused bias gradient,
+        //   sum_k dV[k, :] = sum_q (sum_k P[q, k]) dO[q, :] = the column sums of dO (rows of P sum to one).
+        const int tid = threadIdx.x - 32 * (2 + kSnBwdMathWarps);
+        const int sub = tid >> 3, ch = tid & 7;              // 8 rows per sweep step and warp pair
+        float cs_v[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { cs_q[0][k] = cs_q[1][k] = cs_v[k] = 0.f; }
-        const bool do_cs = p.dbias != nullptr;
-        for (int n = 0; n < n_local; n++, gb0 += nb_bh, pc0 += p.n_pass) {
+        for (int k = 0; k < 8; k++) cs_v[k] = 0.f;
+        for (int n = 0; n < n_local; n++) {
             const int bh = blockIdx.x + n * gridDim.x;
             const int b = bh / p.H, h = bh % p.H;
-            // Per-row statistics (L from the forward, Delta = rowsum(dO * O)); rows >= N get L = +inf so that
-            // their P is exactly 0.  They are double-buffered: the first pair's are computed here, every
-            // later pair's during the previous pair's pass-boundary waits (stats_rows below), so the cold
-            // global reads never sit on the critical path.
-            float* sL = (n & 1) ? sLD1 : sLD0;
-            float* sDelta = sL + kSnMaxKeys;
-            float* nL = (n & 1) ? sLD0 : sLD1;
-            const int bh_next = bh + gridDim.x;
-            // Eight lanes share a row (one 16-byte chunk of the head's 128 B each), so a warp instruction reads
-            // four whole lines instead of one sector from each of 32 rows; three row groups are in flight.
-            auto stats_rows = [&](int bh_t, int base, float* dL) {
-                const int sub = mt >> 3, ch = mt & 7;
-                const int b_t = bh_t / p.H, h_t = bh_t % p.H;
-                uint4 xa[3], ya[3];
-                float Lr[3];
+            float* dL = (n & 1) ? sLD1 : sLD0;
+            if (n >= 2) mbar_wait_relaxed(&st_empty[n & 1], ((n >> 1) - 1) & 1);     // the math warps are done with pair n - 2
+            const __half* pdo = p.d_o + int64_t(b) * p.N * p.D + h * 64;
+            const __half* po = p.o + int64_t(b) * p.N * p.D + h * 64;
+            const float* pl = p.lse + (int64_t(b) * p.H + h) * p.N;
+#pragma unroll 1
+            for (int base = 0; base < kSnMaxKeys; base += 4 * (kSnBwdStatThreads >> 3)) {
+                uint4 xa[4], ya[4];
+                float Lr[4];
 #pragma unroll
-                for (int u = 0; u < 3; u++) {
-                    const int r = base + u * 32 + sub;
+                for (int u = 0; u < 4; u++) {
+                    const int r = base + u * (kSnBwdStatThreads >> 3) + sub;
                     xa[u] = make_uint4(0u, 0u, 0u, 0u); ya[u] = xa[u]; Lr[u] = INFINITY;
                     if (r < p.N) {
-                        xa[u] = reinterpret_cast<const uint4*>(p.d_o + (int64_t(b_t) * p.N + r) * p.D + h_t * 64)[ch];
-                        ya[u] = reinterpret_cast<const uint4*>(p.o + (int64_t(b_t) * p.N + r) * p.D + h_t * 64)[ch];
-                        if (ch == 0) Lr[u] = p.lse[(int64_t(b_t) * p.H + h_t) * p.N + r];
+                        xa[u] = reinterpret_cast<const uint4*>(pdo + int64_t(r) * p.D)[ch];
+                        ya[u] = reinterpret_cast<const uint4*>(po + int64_t(r) * p.D)[ch];
+                        if (ch == 0) Lr[u] = pl[r];
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 3; u++) {
-                    const int r = base + u * 32 + sub;
+                for (int u = 0; u < 4; u++) {
+                    const int r = base + u * (kSnBwdStatThreads >> 3) + sub;
                     const __half2* xh = reinterpret_cast<const __half2*>(&xa[u]);
                     const __half2* yh = reinterpret_cast<const __half2*>(&ya[u]);
                     float dl = 0.f;
@@ -948,14 +945,82 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     dl += __shfl_xor_sync(0xffffffffu, dl, 4);
                     if (ch == 0 && r < kSnMaxKeys) { dL[r] = Lr[u]; dL[kSnMaxKeys + r] = dl; }
                 }
-            };
-            SN_TRACE(quad == 0 && lane == 0, 1 + g, 19, n);                 // pair starts
-            if (n == 0)
-                for (int base = 0; base < kSnMaxKeys; base += 96) stats_rows(bh, base, sL);
-            int next_base = 0;                                              // rows of the next pair done so far
-            for (int i = mt; i < 16 * 64; i += 256) sdQt[i] = 0.f;
-            SN_TRACE(quad == 0 && lane == 0, 1 + g, 11, n);                 // statistics of the pair computed
-            named_bar_sync(1, 256);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&st_full[n & 1]);
+        }
+        if (p.dbias != nullptr && n_local > 0) {
+            const int h = blockIdx.x % p.H;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {                                   // lanes l, l ^ 8, l ^ 16, l ^ 24 share a chunk
+                cs_v[k] += __shfl_xor_sync(0xffffffffu, cs_v[k], 8);
+                cs_v[k] += __shfl_xor_sync(0xffffffffu, cs_v[k], 16);
+            }
+            if (lane < 8) {
+                float* dv = p.dbias + 2 * p.D + h * 64 + lane * 8;
+                sn_red_add_v4(dv, cs_v[0], cs_v[1], cs_v[2], cs_v[3]);
+                sn_red_add_v4(dv + 4, cs_v[4], cs_v[5], cs_v[6], cs_v[7]);
+            }
+        }
+    } else {
+        // ================================ math: 16 warps, one thread per key ================================
+        // group g = block parity (which of the two S^T / dP^T regions), half = which 32 of the block's 64 columns
+        const int idx = warp - 2;
+        const int quad = warp & 3;
+        const int g = (idx >> 2) & 1, half = idx >> 3;
+        const int slice = 2 * g + half;                      // 16-column slice of the accumulators this warp stores
+        const int lr = quad * 32 + lane;                     // key row within the 128-key tile = TMEM lane
+        const int mt = threadIdx.x - 64;                     // 0..511
+        const uint32_t lane_off = uint32_t(quad * 32) << 16;
+        const uint32_t tS = tmem_base + g * 128 + lane_off, tdP = tS + 64;
+        int gb0 = 0, pc0 = 0;
+        // Fused to_qkv bias gradient (p.dbias != NULL; the host then sizes the grid so that a CTA stays on one head
+        // and the sums are flushed once, after the last pair):
+        //   q: column sums of the dQ values this thread stores (cs_q: its 16 columns, every row it writes) and, per
+        //      thread, columns 2 * lane, 2 * lane + 1 of the dQ rows >= 256 (cs_t0 / cs_t1);
+        //   k: nothing to add — sum_k dS[q, k] = sum_k P (dP - Delta_q) = 0, the key bias never reaches the softmax;
+        //   v: the column sums of dO (statistics warps).
+        float cs_q[16], cs_t0 = 0.f, cs_t1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; k++) cs_q[k] = 0.f;
+        const bool do_cs = p.dbias != nullptr;
+        float amax = 0.f;                                    // largest |dqkv| value stored (overflow sink)
+        // One row per thread, 16 columns: the row's two 16-byte stores fill one 32-byte sector each, so the slice needs
+        // no staging through shared memory (the 64-column rows of the 8-warp version made every store instruction of a
+        // warp touch 32 half-filled lines and went through a staging tile instead).
+        auto store_slice = [&](uint32_t taddr, __half* dst, bool live, bool sum) {
+            uint32_t v[16];
+            tmem_ld_32x16(taddr, v);
+            tmem_ld_wait();
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float a = __uint_as_float(v[2 * i]), c = __uint_as_float(v[2 * i + 1]);
+                amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(c)));
+                w[i] = pack_h2_satf(a, c);
+            }
+            if (live) {
+                reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                if (sum) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                        cs_q[2 * i] += f.x; cs_q[2 * i + 1] += f.y;
+                    }
+                }
+            }
+        };
+        for (int n = 0; n < n_local; n++, gb0 += nb_bh, pc0 += p.n_pass) {
+            const int bh = blockIdx.x + n * gridDim.x;
+            const int b = bh / p.H, h = bh % p.H;
+            const float* sL = (n & 1) ? sLD1 : sLD0;
+            const float* sDelta = sL + kSnMaxKeys;
+            SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 19, n);                 // pair starts
+            for (int i = mt; i < 16 * 64; i += kSnBwdMathThreads) sdQt[i] = 0.f;
+            mbar_wait(&st_full[n & 1], (n >> 1) & 1);                                    // this pair's statistics are written
+            SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 11, n);
+            named_bar_sync(1, kSnBwdMathThreads);
             for (int j = 0; j < p.n_pass; j++) {
                 const int pc = pc0 + j, st = pc & 1;
                 const bool warp_live = j * 128 + quad * 32 < p.N;      // some key of this warp exists
@@ -963,17 +1028,15 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     const int gb = gb0 + j * nblk + c;
                     if ((gb & 1) != g) continue;
                     const bool regular = c < p.n_reg;
-                    const int width = regular ? 64 : p.tail_w;
                     const int row0 = regular ? 64 * c : 256;
-                    SN_TRACE(quad == 0 && lane == 0, 1 + g, 5, gb);         // math group starts waiting for S^T / dP^T
+                    SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 5, gb);         // math group starts waiting for S^T / dP^T
                     mbar_wait(&sdp_full[g], (gb >> 1) & 1);
-                    SN_TRACE(quad == 0 && lane == 0, 1 + g, 6, gb);         // S^T / dP^T ready
+                    SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 6, gb);         // S^T / dP^T ready
                     tc_fence_after();
                     if (warp_live) {
                         uint8_t* ds_row = sdS + ((j * p.n_reg + c) & 3) * kSnTile + lr * 128;
                         // 16 columns (query rows) of S^T / dP^T -> P^T / dS^T (fp16, in place in TMEM; dS^T also to
-                        // shared memory for the dQ MMA).  The TMEM loads of the next 16 columns are issued before
-                        // the arithmetic of the current ones, so their latency hides behind it.
+                        // shared memory for the dQ MMA).  de: optionally the fp32 dS values (tail block).
                         auto math16 = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int c0) {
                             uint32_t wp[8], wd[8];
 #pragma unroll
@@ -998,61 +1061,50 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                                     make_uint4(wd[4 * t], wd[4 * t + 1], wd[4 * t + 2], wd[4 * t + 3]);
                         };
                         if (regular) {
+                            // Columns: half 0 takes fp32 chunks [0, 16) and [32, 48), half 1 takes [16, 32) and [48, 64).
+                            // The fp16 results go back IN PLACE at columns c0 / 2 .. c0 / 2 + 7: the results of chunk
+                            // [16, 32) land in the partner's first chunk [0, 16), those of chunk [32, 48) in the
+                            // partner's first chunk [16, 32) — the two warps of a lane quadrant meet on a named barrier
+                            // after their first loads, before anything is written back.  The second chunk is requested
+                            // before the arithmetic of the first, so its TMEM latency hides behind it.
+                            const int cb = 16 * half;
                             uint32_t sA[16], dA[16], sB[16], dB[16];
+                            tmem_ld_32x16(tS + cb, sA); tmem_ld_32x16(tdP + cb, dA);
+                            tmem_ld_wait();
+                            tmem_ld_32x16(tS + cb + 32, sB); tmem_ld_32x16(tdP + cb + 32, dB);
+                            named_bar_sync(3 + 4 * g + quad, 64);
+                            math16(sA, dA, cb);
+                            tmem_ld_wait();
+                            math16(sB, dB, cb + 32);
+                        } else if (half == 0) {
+                            // 16-wide tail block: rows 256 .. 271 (tail_w == 16).  Same arithmetic through math16; the
+                            // dQ of these rows has no TMEM accumulator: sum over this warp's 32 keys of
+                            // dS[row, key] K[key, :] on the CUDA cores (lane l owns dims 2l, 2l+1), from the fp16 dS^T row
+                            // this lane has just written to shared memory, accumulated in shared memory.
+                            uint32_t sA[16], dA[16];
                             tmem_ld_32x16(tS, sA); tmem_ld_32x16(tdP, dA);
                             tmem_ld_wait();
-                            tmem_ld_32x16(tS + 16, sB); tmem_ld_32x16(tdP + 16, dB);
                             math16(sA, dA, 0);
-                            tmem_ld_wait();
-                            tmem_ld_32x16(tS + 32, sA); tmem_ld_32x16(tdP + 32, dA);
-                            math16(sB, dB, 16);
-                            tmem_ld_wait();
-                            tmem_ld_32x16(tS + 48, sB); tmem_ld_32x16(tdP + 48, dB);
-                            math16(sA, dA, 32);
-                            tmem_ld_wait();
-                            math16(sB, dB, 48);
-                        }
-                        for (int c0 = 0; c0 < (regular ? 0 : width); c0 += 16) {
-                            {
-                                // 16-wide tail block: rows 256 .. 271
-                                uint32_t sv[16], dv[16], wp[8], wd[8];
-                                tmem_ld_32x16(tS + c0, sv);
-                                tmem_ld_32x16(tdP + c0, dv);
-                                tmem_ld_wait();
-                                float de[16];
-#pragma unroll
-                                for (int u = 0; u < 16; u++) {
-                                    const float pe = ex2_fast(fmaf(__uint_as_float(sv[u]), p.scale_log2, -sL[row0 + c0 + u]));
-                                    de[u] = pe * (__uint_as_float(dv[u]) - sDelta[row0 + c0 + u]) * p.scale;
-                                    sv[u] = __float_as_uint(pe);
+                            __syncwarp();
+                            const int nrows = min(16, p.N - 256);
+                            const int cl = lane >> 2, wi = (lane & 3) * 4;
+                            const uint8_t* kt = sK + st * kSnTile;
+                            const uint8_t* dsw = sdS + ((j * p.n_reg + c) & 3) * kSnTile + quad * 32 * 128;   // this warp's 32 key rows
+#pragma unroll 1
+                            for (int u = 0; u < nrows; u++) {
+                                float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+                                for (int kk = 0; kk < 32; kk++) {
+                                    const int kr = quad * 32 + kk;
+                                    // dS^T[key kr][row u]: fp16 element u of the key's 128-byte row (16-byte chunk u >> 3)
+                                    const float v = __half2float(*reinterpret_cast<const __half*>(
+                                        dsw + kk * 128 + (((u >> 3) ^ (kr & 7)) << 4) + (u & 7) * 2));
+                                    const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(
+                                        kt + kr * 128 + ((cl ^ (kr & 7)) << 4) + wi));
+                                    a0 = fmaf(v, kf.x, a0); a1 = fmaf(v, kf.y, a1);
                                 }
-#pragma unroll
-                                for (int u = 0; u < 8; u++) {
-                                    wp[u] = pack_h2_rn(__uint_as_float(sv[2 * u]), __uint_as_float(sv[2 * u + 1]));
-                                    wd[u] = pack_h2_satf(de[2 * u], de[2 * u + 1]);
-                                }
-                                tmem_st_32x8(tS + (c0 >> 1), wp);
-                                tmem_st_32x8(tdP + (c0 >> 1), wd);
-                                // dQ of these rows: sum over this warp's 32 keys of dS[row, key] K[key, :] on the
-                                // CUDA cores (lane l owns dims 2l, 2l+1), accumulated in shared memory
-                                const int nrows = min(16, p.N - (row0 + c0));
-                                const int cl = lane >> 2, wi = (lane & 3) * 4;
-#pragma unroll
-                                for (int u = 0; u < 16; u++) {
-                                    if (u < nrows) {
-                                        float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-                                        for (int kk = 0; kk < 32; kk++) {
-                                            const float v = __shfl_sync(0xffffffffu, de[u], kk);
-                                            const int kr = quad * 32 + kk;
-                                            const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(
-                                                sK + st * kSnTile + kr * 128 + ((cl ^ (kr & 7)) << 4) + wi));
-                                            a0 = fmaf(v, kf.x, a0); a1 = fmaf(v, kf.y, a1);
-                                        }
-                                        atomicAdd(&sdQt[(c0 + u) * 64 + 2 * lane], a0);
-                                        atomicAdd(&sdQt[(c0 + u) * 64 + 2 * lane + 1], a1);
-                                    }
-                                }
+                                atomicAdd(&sdQt[u * 64 + 2 * lane], a0);
+                                atomicAdd(&sdQt[u * 64 + 2 * lane + 1], a1);
                             }
                         }
                         tmem_st_wait();
@@ -1061,89 +1113,71 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&pds_full[g]);
-                    SN_TRACE(quad == 0 && lane == 0, 1 + g, 7, gb);         // P^T / dS^T written
+                    SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 7, gb);         // P^T / dS^T written
                 }
-                // ---- pass epilogue: group 0 stores dV_j, group 1 stores dK_j
-                SN_TRACE(quad == 0 && lane == 0, 1 + g, 8, pc);
-                if (n + 1 < n_local) {
-                    // the last post-MMAs of the pass are still in flight: next pair's statistics, a share per pass
-                    const int upto = (j + 1 == p.n_pass) ? kSnMaxKeys : ((j + 1) * kSnMaxKeys / p.n_pass);
-                    for (; next_base < upto; next_base += 96) stats_rows(bh_next, next_base, nL);
-                }
+                // ---- pass epilogue: every warp stores its 16-column slice of dV_j and of dK_j
+                SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 8, pc);
                 mbar_wait(acc_full, pc & 1);
-                SN_TRACE(quad == 0 && lane == 0, 1 + g, 9, pc);             // dV / dK of the pass complete
+                SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 9, pc);             // dV / dK of the pass complete
                 tc_fence_after();
                 {
-                    uint32_t v0[32], v1[32];
-                    const uint32_t src = (g == 0 ? tdV : tdK) + lane_off;
-                    tmem_ld_32x32(src, v0);
-                    tmem_ld_32x32(src + 32, v1);
-                    tmem_ld_wait();
+                    const int key = j * 128 + lr;
+                    __half* dst = p.dqkv + (int64_t(b) * p.N + key) * p.ld_dqkv + h * 64 + 16 * slice;
+                    store_slice(tdV + lane_off + 16 * slice, dst + 2 * p.D, key < p.N, false);
+                    store_slice(tdK + lane_off + 16 * slice, dst + p.D, key < p.N, false);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty);
-                    {
-                        const int key0 = j * 128 + quad * 32;            // first key row of this warp
-                        __half* dst0 = p.dqkv + (int64_t(b) * p.N + key0) * p.ld_dqkv + (g == 0 ? 2 : 1) * p.D + h * 64;
-                        sn_store_rows<false>(sStg + (warp - 2) * 32 * kSnStgPitch, v0, v1, dst0, p.ld_dqkv, p.N - key0, lane, cs_q, amax);
-                    }
                 }
             }
-            // ---- pair epilogue: group g stores dQ of query rows [128 g, 128 g + 128)
+            if (lane == 0) mbar_arrive(&st_empty[n & 1]);                                // this pair's statistics are consumed
+            // ---- pair epilogue: dQ of query rows [128 t, 128 t + 128), every warp its 16-column slice
             mbar_wait(dq_full, n & 1);
-            SN_TRACE(quad == 0 && lane == 0, 1 + g, 10, n);
+            SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 10, n);
             tc_fence_after();
-            {
-                uint32_t v0[32], v1[32];
-                const bool have = g < (p.n_reg >> 1);
-                if (have) {
-                    tmem_ld_32x32(tdQ + g * 64 + lane_off, v0);
-                    tmem_ld_32x32(tdQ + g * 64 + 32 + lane_off, v1);
-                    tmem_ld_wait();
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(dq_empty);
-                if (have) {
-                    const int row0 = g * 128 + quad * 32;
-                    __half* dst0 = p.dqkv + (int64_t(b) * p.N + row0) * p.ld_dqkv + h * 64;
-                    uint8_t* stg = sStg + (warp - 2) * 32 * kSnStgPitch;
-                    if (do_cs) sn_store_rows<true>(stg, v0, v1, dst0, p.ld_dqkv, p.N - row0, lane, cs_q, amax);
-                    else sn_store_rows<false>(stg, v0, v1, dst0, p.ld_dqkv, p.N - row0, lane, cs_q, amax);
-                }
+#pragma unroll 1
+            for (int t = 0; t < (p.n_reg >> 1); t++) {
+                const int row = t * 128 + lr;
+                store_slice(tdQ + t * 64 + lane_off + 16 * slice,
+                            p.dqkv + (int64_t(b) * p.N + row) * p.ld_dqkv + h * 64 + 16 * slice, row < p.N, do_cs);
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_empty);
             // rows >= 256: dQ from the shared-memory accumulators
-            SN_TRACE(quad == 0 && lane == 0, 1 + g, 16, n);                 // dQ rows stored
-            named_bar_sync(1, 256);
-            SN_TRACE(quad == 0 && lane == 0, 1 + g, 17, n);
-            for (int i = mt; i < (p.N - 256) * 32; i += 256) {
-                const int r = i >> 5, l2 = i & 31;
-                amax = fmaxf(amax, fmaxf(fabsf(sdQt[r * 64 + 2 * l2]), fabsf(sdQt[r * 64 + 2 * l2 + 1])));
-                const uint32_t pk = pack_h2_satf(sdQt[r * 64 + 2 * l2], sdQt[r * 64 + 2 * l2 + 1]);
-                *reinterpret_cast<uint32_t*>(p.dqkv + (int64_t(b) * p.N + 256 + r) * p.ld_dqkv + h * 64 + 2 * l2) = pk;
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk));
-                cs_t0 += f.x; cs_t1 += f.y;                                 // l2 == lane for every i of this thread
+            SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 16, n);                 // dQ rows stored
+            if (p.tail_w > 0) {
+                named_bar_sync(1, kSnBwdMathThreads);
+                for (int i = mt; i < (p.N - 256) * 32; i += kSnBwdMathThreads) {
+                    const int r = i >> 5, l2 = i & 31;
+                    amax = fmaxf(amax, fmaxf(fabsf(sdQt[r * 64 + 2 * l2]), fabsf(sdQt[r * 64 + 2 * l2 + 1])));
+                    const uint32_t pk = pack_h2_satf(sdQt[r * 64 + 2 * l2], sdQt[r * 64 + 2 * l2 + 1]);
+                    *reinterpret_cast<uint32_t*>(p.dqkv + (int64_t(b) * p.N + 256 + r) * p.ld_dqkv + h * 64 + 2 * l2) = pk;
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+                    cs_t0 += f.x; cs_t1 += f.y;                                 // l2 == lane for every i of this thread
+                }
+                named_bar_sync(1, kSnBwdMathThreads);
             }
-            named_bar_sync(1, 256);
-            SN_TRACE(quad == 0 && lane == 0, 1 + g, 18, n);                 // pair finished
+            SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 18, n);                 // pair finished
         }
         raise_overflow(p.ovf, amax);
         if (do_cs && n_local > 0) {
             const int h = blockIdx.x % p.H;
-            sn_flush_colsum(cs_q, p.dbias + h * 64, lane);
+            // this thread's 16 dQ columns, summed over its rows: reduce over the warp's 32 rows, one red.add per column group
+#pragma unroll 1
+            for (int k = 0; k < 16; k += 4) {
+                float c4[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    c4[i] = cs_q[k + i];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c4[i] += __shfl_xor_sync(0xffffffffu, c4[i], o);
+                }
+                if (lane == 0) sn_red_add_v4(p.dbias + h * 64 + 16 * slice + k, c4[0], c4[1], c4[2], c4[3]);
+            }
             if (cs_t0 != 0.f || cs_t1 != 0.f) {
                 atomicAdd(p.dbias + h * 64 + 2 * lane, cs_t0);
                 atomicAdd(p.dbias + h * 64 + 2 * lane + 1, cs_t1);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {                                   // lanes l, l ^ 8, l ^ 16, l ^ 24 share a chunk
-                cs_v[k] += __shfl_xor_sync(0xffffffffu, cs_v[k], 8);
-                cs_v[k] += __shfl_xor_sync(0xffffffffu, cs_v[k], 16);
-            }
-            if (lane < 8) {
-                float* dv = p.dbias + 2 * p.D + h * 64 + lane * 8;
-                sn_red_add_v4(dv, cs_v[0], cs_v[1], cs_v[2], cs_v[3]);
-                sn_red_add_v4(dv + 4, cs_v[4], cs_v[5], cs_v[6], cs_v[7]);
             }
         }
     }

@@ -39,6 +39,55 @@ struct FixedParams {
     int clamp;
 };
 
+// float_quantize, stochastic, formats that drop at most 16 mantissa bits (man_bits >= 7): the rounding needs
+// 23 - man_bits <= 16 random bits per element, so one Philox4x32-10 call (128 bits) serves EIGHT elements instead of
+// four — element i takes half-word (i & 7) of philox(seed, i >> 3, offset) (include/mv_b200.h, "16-bit stream").  Ten
+// Philox rounds per 4 elements were the bound of the stochastic kernel (0.65 - 0.74 of copy bandwidth); a thread now
+// owns two adjacent 16-byte vectors (32 contiguous bytes) per Philox call.
+template <typename OutT>
+__global__ void __launch_bounds__(kQThreads)
+quant_vec16_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t n, int exp_bits, int man_bits,
+                   uint64_t seed, uint64_t offset) {
+    const int64_t n8 = n >> 3;
+    constexpr int kU = 2;                                   // 2 x 32 B in flight per thread
+    const int64_t stride = int64_t(gridDim.x) * kQThreads * kU;
+    for (int64_t base = int64_t(blockIdx.x) * kQThreads * kU + threadIdx.x; base < n8; base += stride) {
+        float4 v[kU][2];
+#pragma unroll
+        for (int j = 0; j < kU; j++) {
+            const int64_t i = base + int64_t(j) * kQThreads;
+            if (i < n8) {
+                v[j][0] = __ldcs(reinterpret_cast<const float4*>(in) + 2 * i);
+                v[j][1] = __ldcs(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kU; j++) {
+            const int64_t i = base + int64_t(j) * kQThreads;
+            if (i >= n8) continue;
+            const uint4 r = philox4x32_10(seed, uint64_t(i), offset);
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                float4 o;
+                o.x = float_quantize_elem<true>(v[j][h].x, w[2 * h] & 0xFFFFu, exp_bits, man_bits);
+                o.y = float_quantize_elem<true>(v[j][h].y, w[2 * h] >> 16, exp_bits, man_bits);
+                o.z = float_quantize_elem<true>(v[j][h].z, w[2 * h + 1] & 0xFFFFu, exp_bits, man_bits);
+                o.w = float_quantize_elem<true>(v[j][h].w, w[2 * h + 1] >> 16, exp_bits, man_bits);
+                Vec4Store<OutT>::st(out + 8 * i + 4 * h, o);
+            }
+        }
+    }
+}
+// scalar companion (tails, unaligned buffers): the same 16-bit stream
+template <typename OutT>
+__global__ void quant_scalar16_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t begin, int64_t n,
+                                      int exp_bits, int man_bits, uint64_t seed, uint64_t offset) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = begin + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = cvt_out<OutT>(float_quantize_elem<true>(in[i], philox_half16(seed, uint64_t(i), offset), exp_bits, man_bits));
+}
+
 // MODE 0: float_quantize ; MODE 1: fixed_point_quantize
 template <int MODE, bool STOCH, typename OutT>
 __global__ void __launch_bounds__(kQThreads)
@@ -125,6 +174,26 @@ static inline int grid_for(int64_t work_items, int per_block) {
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return int(blocks);
+}
+
+template <typename OutT>
+static int launch_quant16(const float* in, OutT* out, int64_t n, int exp_bits, int man_bits, uint64_t seed,
+                          uint64_t offset, cudaStream_t st) {
+    if (n == 0) return 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(OutT)) == 0);
+    int64_t done = 0;
+    if (aligned && n >= 8) {
+        const int64_t n8 = n >> 3;
+        quant_vec16_kernel<OutT><<<grid_for(n8, kQThreads * 2), kQThreads, 0, st>>>(in, out, n, exp_bits, man_bits, seed, offset);
+        g_launches++;
+        done = n8 << 3;
+    }
+    if (done < n) {
+        quant_scalar16_kernel<OutT><<<grid_for(n - done, 256), 256, 0, st>>>(in, out, done, n, exp_bits, man_bits, seed, offset);
+        g_launches++;
+    }
+    return check_cuda(cudaGetLastError(), "quant launch");
 }
 
 template <int MODE, bool STOCH, typename OutT>

@@ -166,6 +166,14 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr, uint
     }
     return make_uint4(c0, c1, c2, c3);
 }
+// "16-bit stream" of stochastic float_quantize for formats with man_bits >= 7: element i takes half-word (i & 7) of
+// philox(seed, i >> 3, offset) — low half of word ((i & 7) >> 1) when i is even, high half when odd.
+__device__ __forceinline__ uint32_t philox_half16(uint64_t seed, uint64_t i, uint64_t offset) {
+    const uint4 w = philox4x32_10(seed, i >> 3, offset);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    const uint32_t word = ws[(i & 7) >> 1];
+    return (i & 1) ? (word >> 16) : (word & 0xFFFFu);
+}
 __device__ __forceinline__ float bits_to_uniform(uint32_t b) {
     return float(b >> 8) * (1.0f / 16777216.0f);
 }
