@@ -665,20 +665,23 @@ constexpr int kSnFwdSmem = 4 * kSnKVBytes + 2 * kSnTile + kSnTailWarps * (64 + k
 // reduced on the CUDA cores into shared memory.  Keys beyond N are zero rows (TMA fill) and fall out.
 // 16 math warps: two per TMEM lane quadrant and block in flight (each takes 32 of the block's 64 columns), four per
 // scheduler, so that one warp's TMEM read / exp / TMEM write chain hides under the others'.  576 threads: 112 registers.
-// Two more warps do nothing but the per-row statistics (L, Delta) of the NEXT pair — cold global reads, kept a whole
+// One more warp does nothing but the per-row statistics (L, Delta) of the NEXT pair — cold global reads, kept a whole
 // pair ahead of the math warps.  Code that runs once per pass or pair (tail block, epilogues, statistics) is kept small
 // on purpose: the kernel is far larger than the instruction caches, and a rarely executed, fully unrolled section costs
 // more in instruction-fetch misses than in arithmetic (the 16-wide tail block took 5 000 cycles that way).
-constexpr int kSnBwdMathWarps = 16, kSnBwdStatWarps = 2;
+constexpr int kSnBwdMathWarps = 16, kSnBwdStatWarps = 1, kSnStatU = 6;   // 20 warps: 5 per scheduler, 96 registers
 constexpr int kSnBwdMathThreads = 32 * kSnBwdMathWarps, kSnBwdStatThreads = 32 * kSnBwdStatWarps;
-constexpr int kSnBwdThreads = 32 * (2 + kSnBwdMathWarps + kSnBwdStatWarps);
+// One more warp owns the TMA stores: the math warps park dV_j / dK_j / dQ_i as fp16 in 128-byte-swizzled tiles (idle slots
+// of the dS^T ring) and go on; written straight from the registers — one accumulator row per thread — every 16-byte
+// store instruction of a warp touches 32 different lines and the LSU serialises them (4 000 cycles per pass epilogue,
+// 17 000 of a pair's 43 000, clock64 timeline).
+constexpr int kSnBwdThreads = 32 * (2 + kSnBwdMathWarps + kSnBwdStatWarps + 1);
 constexpr int kSnQBytes = kSnMaxKeys * 128;            // Q or dO of one pair: 272 rows x 128 B
 constexpr int kSnOffQ = 4 * kSnTile;
 constexpr int kSnOffDO = kSnOffQ + kSnQBytes;
 constexpr int kSnOffDS = kSnOffDO + kSnQBytes;
 constexpr int kSnOffVec = kSnOffDS + 4 * kSnTile;      // L[272], Delta[272], dQ tail accumulators [16][64]
-constexpr int kSnOffStg = kSnOffVec + (2 * kSnMaxKeys + 16 * 64) * 4;   // 8 math warps x 32 rows x kSnStgPitch
-constexpr int kSnOffVec2 = kSnOffStg + 8 * 32 * kSnStgPitch;           // L / Delta of the next pair (double buffer)
+constexpr int kSnOffVec2 = kSnOffVec + (2 * kSnMaxKeys + 16 * 64) * 4;  // L / Delta of the next pair (double buffer)
 constexpr int kSnOffBar = kSnOffVec2 + 2 * kSnMaxKeys * 4;
 constexpr int kSnBwdSmem = kSnOffBar + 256 + 1024;
 static_assert(kSnBwdSmem <= 232448, "attention bwd (short sequences): shared memory over the 227 KB limit");
@@ -701,7 +704,7 @@ struct SnBwdDev {
 __global__ void __launch_bounds__(kSnBwdThreads, 1)
 attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv16,
                    const __grid_constant__ CUtensorMap tm_do128, const __grid_constant__ CUtensorMap tm_do16,
-                   const __grid_constant__ SnBwdDev p) {
+                   const __grid_constant__ CUtensorMap tm_dqkv128, const __grid_constant__ SnBwdDev p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; offset arithmetic keeps the shared address space
     uint8_t* sK = smem;                                   // [2 stages][128 x 128 B]
@@ -712,7 +715,6 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     float* sLD0 = reinterpret_cast<float*>(smem + kSnOffVec);     // L[272], Delta[272] of even pairs
     float* sLD1 = reinterpret_cast<float*>(smem + kSnOffVec2);    // ... of odd pairs
     float* sdQt = sLD0 + 2 * kSnMaxKeys;
-    uint8_t* sStg = smem + kSnOffStg;                            // per math warp: 32 rows x kSnStgPitch
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSnOffBar);
     uint64_t* kv_full = bars;           // [2]
     uint64_t* kv_empty = bars + 2;      // [2]
@@ -726,7 +728,13 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     uint64_t* dq_empty = bars + 13;
     uint64_t* st_full = bars + 14;      // [2] statistics buffer (pair parity) written by the stats warps
     uint64_t* st_empty = bars + 16;     // [2] ... no longer read by the math warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    // Staging tiles for the TMA stores = slots of the dS^T ring, idle at an epilogue.  "hi" (slots 2, 3 — the ones the
+    // following blocks write last): dV_j / dK_j of every pass but a pair's last one, then the pair's dQ tiles, which stay
+    // parked longer (column sums).  "lo" (slots 0, 1): dV_j / dK_j of the last pass.  hi events are numbered by the pass
+    // counter pc, lo events by the pair counter n.
+    uint64_t* sg_full = bars + 18;      // [2] lo / hi: all math warps have parked their slices
+    uint64_t* sg_free = bars + 20;      // [2] lo / hi: the TMA engine has read the tiles
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     [[maybe_unused]] int trace_n = 0;
@@ -738,7 +746,8 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_qkv128); tma_prefetch_desc(&tm_qkv16);
-        tma_prefetch_desc(&tm_do128); tma_prefetch_desc(&tm_do16);
+        tma_prefetch_desc(&tm_do128); tma_prefetch_desc(&tm_do16); tma_prefetch_desc(&tm_dqkv128);
+        for (int s = 0; s < 2; s++) { mbar_init(&sg_full[s], kSnBwdMathWarps); mbar_init(&sg_free[s], 1); }
         for (int s = 0; s < 2; s++) {
             mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
             mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], kSnBwdMathWarps / 2);
@@ -893,16 +902,64 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                 }
             }
         }
+    } else if (warp == 2 + kSnBwdMathWarps + kSnBwdStatWarps) {
+        // ================================ store warp ================================
+        // one lane: waits until the 16 math warps have parked an epilogue's tiles, hands them to the TMA engine and
+        // releases the tiles once they have been read.  Rows >= N of a box are clipped by the tensor map.
+        // While the dQ tiles are parked the whole warp also sums their columns — the q part of the fused to_qkv bias
+        // gradient (lane l owns columns 2l, 2l + 1; rows >= N are exact zeros) — kept in registers for the whole kernel
+        // (the host sizes the grid so that a CTA stays on one head) and flushed once.
+        const int q_tiles = p.n_reg >> 1;
+        float cq0 = 0.f, cq1 = 0.f;
+        const bool do_cs = p.dbias != nullptr;
+        int pc = 0;
+        for (int n = 0; n < n_local; n++) {
+            const int bh = blockIdx.x + n * gridDim.x;
+            const int b = bh / p.H, h = bh % p.H;
+            if (lane == 0) {
+                for (int j = 0; j < p.n_pass; j++, pc++) {
+                    const bool last = j == p.n_pass - 1;
+                    const uint8_t* src = sdS + (last ? 0 : 2 * kSnTile);
+                    if (last) mbar_wait(&sg_full[0], n & 1); else mbar_wait(&sg_full[1], pc & 1);
+                    tma_store_3d(&tm_dqkv128, src, 2 * p.D + h * 64, j * 128, b);
+                    tma_store_3d(&tm_dqkv128, src + kSnTile, p.D + h * 64, j * 128, b);
+                    tma_store_commit();
+                    tma_store_wait_read();
+                    mbar_arrive(&sg_free[last ? 0 : 1]);
+                }
+                mbar_wait(&sg_full[1], (pc - 1) & 1);                      // the dQ tiles: hi event of the last pass
+                for (int t = 0; t < q_tiles; t++) tma_store_3d(&tm_dqkv128, sdS + (2 + t) * kSnTile, h * 64, t * 128, b);
+                tma_store_commit();
+            }
+            __syncwarp();
+            if (do_cs) {
+                const uint8_t* tile = sdS + 2 * kSnTile;
+#pragma unroll 8
+                for (int r = 0; r < q_tiles * 128; r++) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(
+                        tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4));
+                    cq0 += f.x; cq1 += f.y;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { tma_store_wait_read(); mbar_arrive(&sg_free[1]); }
+        }
+        if (lane == 0) tma_store_wait_all();
+        if (do_cs && n_local > 0) {
+            const int h = blockIdx.x % p.H;
+            atomicAdd(p.dbias + h * 64 + 2 * lane, cq0);
+            atomicAdd(p.dbias + h * 64 + 2 * lane + 1, cq1);
+        }
     } else if (warp >= 2 + kSnBwdMathWarps) {
         // ================================ statistics warps ================================
         // Per-row statistics of every pair (L from the forward, Delta = rowsum(dO * O)); rows >= N get L = +inf so that
         // their P is exactly 0.  Double-buffered by pair parity and written a whole pair ahead of the math warps, so the
         // cold global reads never sit on anybody's critical path.  Eight lanes share a row (one 16-byte chunk of the
-        // head's 128 B each): a warp instruction reads four whole lines; four row groups are in flight per thread.
+        // head's 128 B each): a warp instruction reads four whole lines; eight row groups are in flight per thread.
         // cs_v: column sums of dO (this lane's chunk, every row it visits) — the v part of the fused bias gradient,
         //   sum_k dV[k, :] = sum_q (sum_k P[q, k]) dO[q, :] = the column sums of dO (rows of P sum to one).
         const int tid = threadIdx.x - 32 * (2 + kSnBwdMathWarps);
-        const int sub = tid >> 3, ch = tid & 7;              // 8 rows per sweep step and warp pair
+        const int sub = tid >> 3, ch = tid & 7;              // 4 rows per load instruction
         float cs_v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) cs_v[k] = 0.f;
@@ -915,21 +972,22 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             const __half* po = p.o + int64_t(b) * p.N * p.D + h * 64;
             const float* pl = p.lse + (int64_t(b) * p.H + h) * p.N;
 #pragma unroll 1
-            for (int base = 0; base < kSnMaxKeys; base += 4 * (kSnBwdStatThreads >> 3)) {
-                uint4 xa[4], ya[4];
-                float Lr[4];
+            for (int base = 0; base < kSnMaxKeys; base += kSnStatU * (kSnBwdStatThreads >> 3)) {
+                uint4 xa[kSnStatU], ya[kSnStatU];
+                float Lr[kSnStatU];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < kSnStatU; u++) {
                     const int r = base + u * (kSnBwdStatThreads >> 3) + sub;
                     xa[u] = make_uint4(0u, 0u, 0u, 0u); ya[u] = xa[u]; Lr[u] = INFINITY;
                     if (r < p.N) {
-                        xa[u] = reinterpret_cast<const uint4*>(pdo + int64_t(r) * p.D)[ch];
-                        ya[u] = reinterpret_cast<const uint4*>(po + int64_t(r) * p.D)[ch];
-                        if (ch == 0) Lr[u] = pl[r];
+                        // streamed once: keep them out of the small L1 (227 KB of it is shared memory)
+                        xa[u] = __ldcs(reinterpret_cast<const uint4*>(pdo + int64_t(r) * p.D) + ch);
+                        ya[u] = __ldcs(reinterpret_cast<const uint4*>(po + int64_t(r) * p.D) + ch);
+                        if (ch == 0) Lr[u] = __ldcs(pl + r);
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < kSnStatU; u++) {
                     const int r = base + u * (kSnBwdStatThreads >> 3) + sub;
                     const __half2* xh = reinterpret_cast<const __half2*>(&xa[u]);
                     const __half2* yh = reinterpret_cast<const __half2*>(&ya[u]);
@@ -976,22 +1034,16 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         int gb0 = 0, pc0 = 0;
         // Fused to_qkv bias gradient (p.dbias != NULL; the host then sizes the grid so that a CTA stays on one head
         // and the sums are flushed once, after the last pair):
-        //   q: column sums of the dQ values this thread stores (cs_q: its 16 columns, every row it writes) and, per
-        //      thread, columns 2 * lane, 2 * lane + 1 of the dQ rows >= 256 (cs_t0 / cs_t1);
+        //   q: column sums of the parked dQ tiles (store warp) and, per thread, columns 2 * lane, 2 * lane + 1 of the dQ
+        //      rows >= 256 (cs_t0 / cs_t1);
         //   k: nothing to add — sum_k dS[q, k] = sum_k P (dP - Delta_q) = 0, the key bias never reaches the softmax;
         //   v: the column sums of dO (statistics warps).
-        float cs_q[16], cs_t0 = 0.f, cs_t1 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; k++) cs_q[k] = 0.f;
+        float cs_t0 = 0.f, cs_t1 = 0.f;
         const bool do_cs = p.dbias != nullptr;
         float amax = 0.f;                                    // largest |dqkv| value stored (overflow sink)
-        // One row per thread, 16 columns: the row's two 16-byte stores fill one 32-byte sector each, so the slice needs
-        // no staging through shared memory (the 64-column rows of the 8-warp version made every store instruction of a
-        // warp touch 32 half-filled lines and went through a staging tile instead).
-        auto store_slice = [&](uint32_t taddr, __half* dst, bool live, bool sum) {
-            uint32_t v[16];
-            tmem_ld_32x16(taddr, v);
-            tmem_ld_wait();
+        // Epilogues: this thread's accumulator row, its 16-column slice -> fp16 -> two 16-byte chunks of a 128-byte-swizzled
+        // [128 rows][64 columns] staging tile (8 consecutive lanes cover the 8 chunk positions: conflict-free).
+        auto park_slice = [&](const uint32_t (&v)[16], uint8_t* tile) {
             uint32_t w[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -999,18 +1051,15 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                 amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(c)));
                 w[i] = pack_h2_satf(a, c);
             }
-            if (live) {
-                reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                if (sum) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-                        cs_q[2 * i] += f.x; cs_q[2 * i + 1] += f.y;
-                    }
-                }
-            }
+            uint8_t* row = tile + lr * 128;
+            *reinterpret_cast<uint4*>(row + (((2 * slice) ^ (lr & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(row + (((2 * slice + 1) ^ (lr & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
         };
+        // Staging events handed to the store warp (lo / hi tiles): has this warp seen the latest one released?  Checked
+        // before anything is written to the dS^T ring or to a staging tile; a warp is never more than one event behind
+        // (it waits for event k before it takes part in event k + 1).  The latest hi event is always number pc - 1
+        // (pc: the current pass), the latest lo event number n - 1.
+        bool pend_lo = false, pend_hi = false;
         for (int n = 0; n < n_local; n++, gb0 += nb_bh, pc0 += p.n_pass) {
             const int bh = blockIdx.x + n * gridDim.x;
             const int b = bh / p.H, h = bh % p.H;
@@ -1033,6 +1082,10 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     mbar_wait(&sdp_full[g], (gb >> 1) & 1);
                     SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 6, gb);         // S^T / dP^T ready
                     tc_fence_after();
+                    auto staging_released = [&]() {
+                        if (pend_lo) { mbar_wait(&sg_free[0], (n - 1) & 1); pend_lo = false; }
+                        if (pend_hi) { mbar_wait(&sg_free[1], (pc - 1) & 1); pend_hi = false; }
+                    };
                     if (warp_live) {
                         uint8_t* ds_row = sdS + ((j * p.n_reg + c) & 3) * kSnTile + lr * 128;
                         // 16 columns (query rows) of S^T / dP^T -> P^T / dS^T (fp16, in place in TMEM; dS^T also to
@@ -1055,6 +1108,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                             }
                             tmem_st_32x8(tS + (c0 >> 1), wp);
                             tmem_st_32x8(tdP + (c0 >> 1), wd);
+                            staging_released();                  // (first write into the dS^T ring after an epilogue)
 #pragma unroll
                             for (int t = 0; t < 2; t++)
                                 *reinterpret_cast<uint4*>(ds_row + ((((c0 >> 3) + t) ^ (lr & 7)) << 4)) =
@@ -1065,17 +1119,19 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                             // The fp16 results go back IN PLACE at columns c0 / 2 .. c0 / 2 + 7: the results of chunk
                             // [16, 32) land in the partner's first chunk [0, 16), those of chunk [32, 48) in the
                             // partner's first chunk [16, 32) — the two warps of a lane quadrant meet on a named barrier
-                            // after their first loads, before anything is written back.  The second chunk is requested
-                            // before the arithmetic of the first, so its TMEM latency hides behind it.
+                            // after their first loads, before anything is written back.  (Requesting the second chunk
+                            // before the arithmetic of the first — 64 more live registers — spills at the 96 registers
+                            // that 20 warps leave a thread, and the spills cost more than the exposed TMEM latency:
+                            // 0.234 vs 0.213 ms.)
                             const int cb = 16 * half;
-                            uint32_t sA[16], dA[16], sB[16], dB[16];
+                            uint32_t sA[16], dA[16];
                             tmem_ld_32x16(tS + cb, sA); tmem_ld_32x16(tdP + cb, dA);
                             tmem_ld_wait();
-                            tmem_ld_32x16(tS + cb + 32, sB); tmem_ld_32x16(tdP + cb + 32, dB);
-                            named_bar_sync(3 + 4 * g + quad, 64);
+                            named_bar_sync(3 + 4 * g + quad, 64);         // the partner has read its first chunk too
                             math16(sA, dA, cb);
-                            tmem_ld_wait();
-                            math16(sB, dB, cb + 32);
+                            tmem_ld_32x16(tS + cb + 32, sA); tmem_ld_32x16(tdP + cb + 32, dA);
+                            tmem_ld_wait();                               // (the fp16 results only ever land in columns [0, 32))
+                            math16(sA, dA, cb + 32);
                         } else if (half == 0) {
                             // 16-wide tail block: rows 256 .. 271 (tail_w == 16).  Same arithmetic through math16; the
                             // dQ of these rows has no TMEM accumulator: sum over this warp's 32 keys of
@@ -1110,6 +1166,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                         tmem_st_wait();
                         fence_proxy_async();
                     }
+                    staging_released();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&pds_full[g]);
@@ -1121,29 +1178,50 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                 SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 9, pc);             // dV / dK of the pass complete
                 tc_fence_after();
                 {
-                    const int key = j * 128 + lr;
-                    __half* dst = p.dqkv + (int64_t(b) * p.N + key) * p.ld_dqkv + h * 64 + 16 * slice;
-                    store_slice(tdV + lane_off + 16 * slice, dst + 2 * p.D, key < p.N, false);
-                    store_slice(tdK + lane_off + 16 * slice, dst + p.D, key < p.N, false);
+                    uint32_t va[16], vb[16];
+                    tmem_ld_32x16(tdV + lane_off + 16 * slice, va);
+                    tmem_ld_32x16(tdK + lane_off + 16 * slice, vb);
+                    tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty);
+                    SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 20, pc);        // accumulators in registers
+                    const bool last = j == p.n_pass - 1;
+                    if (last) { if (pend_lo) { mbar_wait(&sg_free[0], (n - 1) & 1); pend_lo = false; } }
+                    else if (pend_hi) { mbar_wait(&sg_free[1], (pc - 1) & 1); pend_hi = false; }
+                    SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 21, pc);        // staging tiles free
+                    uint8_t* tile = sdS + (last ? 0 : 2 * kSnTile);
+                    park_slice(va, tile);
+                    park_slice(vb, tile + kSnTile);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sg_full[last ? 0 : 1]);
+                    if (last) pend_lo = true; else pend_hi = true;
+                    SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 22, pc);        // parked
                 }
             }
             if (lane == 0) mbar_arrive(&st_empty[n & 1]);                                // this pair's statistics are consumed
             // ---- pair epilogue: dQ of query rows [128 t, 128 t + 128), every warp its 16-column slice
+            const int pc_last = pc0 + p.n_pass - 1;
             mbar_wait(dq_full, n & 1);
             SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 10, n);
             tc_fence_after();
-#pragma unroll 1
-            for (int t = 0; t < (p.n_reg >> 1); t++) {
-                const int row = t * 128 + lr;
-                store_slice(tdQ + t * 64 + lane_off + 16 * slice,
-                            p.dqkv + (int64_t(b) * p.N + row) * p.ld_dqkv + h * 64 + 16 * slice, row < p.N, do_cs);
+            {
+                uint32_t va[16], vb[16];
+                tmem_ld_32x16(tdQ + lane_off + 16 * slice, va);
+                if (p.n_reg > 2) tmem_ld_32x16(tdQ + 64 + lane_off + 16 * slice, vb);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dq_empty);
+                if (pend_hi) { mbar_wait(&sg_free[1], (pc_last - 1) & 1); pend_hi = false; }
+                park_slice(va, sdS + 2 * kSnTile);
+                if (p.n_reg > 2) park_slice(vb, sdS + 3 * kSnTile);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sg_full[1]);
+                pend_hi = true;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dq_empty);
             // rows >= 256: dQ from the shared-memory accumulators
             SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 16, n);                 // dQ rows stored
             if (p.tail_w > 0) {
@@ -1163,18 +1241,6 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         raise_overflow(p.ovf, amax);
         if (do_cs && n_local > 0) {
             const int h = blockIdx.x % p.H;
-            // this thread's 16 dQ columns, summed over its rows: reduce over the warp's 32 rows, one red.add per column group
-#pragma unroll 1
-            for (int k = 0; k < 16; k += 4) {
-                float c4[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    c4[i] = cs_q[k + i];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) c4[i] += __shfl_xor_sync(0xffffffffu, c4[i], o);
-                }
-                if (lane == 0) sn_red_add_v4(p.dbias + h * 64 + 16 * slice + k, c4[0], c4[1], c4[2], c4[3]);
-            }
             if (cs_t0 != 0.f || cs_t1 != 0.f) {
                 atomicAdd(p.dbias + h * 64 + 2 * lane, cs_t0);
                 atomicAdd(p.dbias + h * 64 + 2 * lane + 1, cs_t1);
@@ -1249,6 +1315,8 @@ int mv_attention_bwd_sn(const void* qkv, const void* o, const void* d_o, const f
     if (make_tmap_3d(&q16, qkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 16, 1)) return 1;
     if (make_tmap_3d(&d128, d_o, MV_F16, D, N, B, D, uint64_t(N) * D, 64, 128, 1)) return 1;
     if (make_tmap_3d(&d16, d_o, MV_F16, D, N, B, D, uint64_t(N) * D, 64, 16, 1)) return 1;
+    CUtensorMap s128;                              // dqkv, stored by TMA from the staging tiles (rows >= N clipped)
+    if (make_tmap_3d(&s128, dqkv, MV_F16, 3 * D, N, B, 3 * D, uint64_t(N) * 3 * D, 64, 128, 1)) return 1;
     (void)delta;                                   // Delta is computed inside the kernel
     SnBwdDev p;
     p.trace = g_sn_trace;
@@ -1268,7 +1336,7 @@ int mv_attention_bwd_sn(const void* qkv, const void* o, const void* d_o, const f
     const int grid = n_bh <= kNumSMs ? n_bh : (fuse ? (kNumSMs / H) * H : kNumSMs);
     p.dbias = fuse ? dbias : nullptr;
     p.ovf = g_overflow;
-    attn_bwd_sn_kernel<<<grid, kSnBwdThreads, kSnBwdSmem, st>>>(q128, q16, d128, d16, p);
+    attn_bwd_sn_kernel<<<grid, kSnBwdThreads, kSnBwdSmem, st>>>(q128, q16, d128, d16, s128, p);
     g_launches++;
     if (check_cuda(cudaGetLastError(), "attention bwd (short-sequence) launch")) return 1;
     if (dbias != nullptr && !fuse) return mv_colsum(dqkv, MV_F16, 3 * D, B * N, 3 * D, dbias, stream);

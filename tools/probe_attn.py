@@ -4,6 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "myrtle-vision_b200")); sys.path.insert(0, ROOT)
 import torch
 import mv_native as mv
+if os.environ.get("MV_ALT_LIB"):        # a variant built by tools/build_variant.sh
+    mv._SO = os.path.join(ROOT, "myrtle-vision_b200", "csrc", os.environ["MV_ALT_LIB"])
 dev = "cuda"
 torch.manual_seed(0)
 def rel(a, b):

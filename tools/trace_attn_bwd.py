@@ -5,6 +5,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "myrtle-vision_b200")); sys.path.insert(0, ROOT)
 import torch
 import mv_native as mv
+if os.environ.get("MV_ALT_LIB"):        # a variant built by tools/build_variant.sh
+    mv._SO = os.path.join(ROOT, "myrtle-vision_b200", "csrc", os.environ["MV_ALT_LIB"])
+if os.environ.get("MV_TRACE_LIB"):      # tools/build_variant.sh attention_sn.cu trace -DMV_SN_TRACE
+    mv._SO = os.path.join(ROOT, "myrtle-vision_b200", "csrc", "libmv_b200_trace.so")
 B, H, N = 256, 6, 257
 D = H * 64
 torch.manual_seed(0)
@@ -20,7 +24,7 @@ torch.cuda.synchronize()
 mv.lib().mv_debug_set_attn_trace(None)
 t = buf.cpu().view(3, 1024, 3)
 names = {1: "pre issued", 2: "issuer waits math", 3: "issuer sees math done", 4: "post issued", 5: "math waits S", 6: "S ready",
-         7: "math done", 12: "max pass done (fwd)", 16: "dq stored", 17: "bar after dq", 18: "pair finished", 19: "stats start", 12: "pre enter", 13: "pre fenced", 14: "pre 2 MMAs issued", 15: "pre 8 MMAs issued", 8: "waits acc", 9: "acc ready", 10: "dq ready", 11: "stats done"}
+         7: "math done", 12: "max pass done (fwd)", 16: "dq stored", 17: "bar after dq", 18: "pair finished", 19: "stats start", 12: "pre enter", 13: "pre fenced", 14: "pre 2 MMAs issued", 15: "pre 8 MMAs issued", 8: "waits acc", 9: "acc ready", 10: "dq ready", 11: "stats done", 20: "epi acc in regs", 21: "epi staging free", 22: "epi parked", 23: "blk staging free"}
 ev = []
 for r in range(3):
     for e, i, c in t[r].tolist():
