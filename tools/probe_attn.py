@@ -29,7 +29,7 @@ def case(B, H, N, gscale=1.0):
     torch.cuda.synchronize()
     g = dqkv.double().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
     print("   bwd: dq rel %.3e  dk rel %.3e  dv rel %.3e  nan %d" % (rel(g[0], q.grad), rel(g[1], k.grad), rel(g[2], v.grad), int(torch.isnan(dqkv.float()).sum())), flush=True)
-for args in [(1, 1, 128), (1, 1, 64), (2, 2, 257), (1, 1, 300), (2, 3, 197), (1, 2, 1000)]:
+for args in [(1, 1, 128), (1, 1, 64), (2, 2, 257), (40, 6, 257), (2, 2, 258), (3, 3, 260), (2, 1, 261), (1, 1, 300), (2, 3, 197), (1, 2, 1000)]:
     try:
         case(*args)
     except Exception as e:

@@ -24,7 +24,7 @@ torch.cuda.synchronize()
 mv.lib().mv_debug_set_attn_trace(None)
 t = buf.cpu().view(3, 1024, 3)
 names = {1: "pre issued", 2: "issuer waits math", 3: "issuer sees math done", 4: "post issued", 5: "math waits S", 6: "S ready",
-         7: "math done", 12: "max pass done (fwd)", 16: "dq stored", 17: "bar after dq", 18: "pair finished", 19: "stats start", 12: "pre enter", 13: "pre fenced", 14: "pre 2 MMAs issued", 15: "pre 8 MMAs issued", 8: "waits acc", 9: "acc ready", 10: "dq ready", 11: "stats done", 20: "epi acc in regs", 21: "epi staging free", 22: "epi parked", 23: "blk staging free"}
+         7: "math done", 12: "max pass done (fwd)", 16: "dq stored", 17: "bar after dq", 18: "pair finished", 19: "stats start", 12: "pre enter", 13: "pre fenced", 14: "pre 2 MMAs issued", 15: "pre 8 MMAs issued", 8: "waits acc", 9: "acc ready", 10: "dq ready", 11: "stats done", 24: "odd keys done", 25: "odd: k,v copied", 26: "odd: A done", 27: "odd: B done", 20: "epi acc in regs", 21: "epi staging free", 22: "epi parked", 23: "blk staging free"}
 ev = []
 for r in range(3):
     for e, i, c in t[r].tolist():
@@ -35,3 +35,7 @@ t0 = ev[0][0]
 # first two (image, head) pairs of CTA 0
 for c, r, e, i in ev[:260]:
     print("%8d  %-7s %-22s %d" % (c - t0, ["issuer", "math g0", "math g1"][r], names[e], i))
+# per-pair summary over everything recorded (math g0): when each pair finished, and the kernel's clock rate
+fin = [c - t0 for c, r, e, i in ev if r == 1 and e == 18]
+print("pairs finished at:", fin)
+print("cycles per pair:", [b - a for a, b in zip(fin, fin[1:])])
