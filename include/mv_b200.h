@@ -43,8 +43,12 @@ int64_t mv_launch_count(void);
 /* ---------------------------------------------------------------- fake-quant (B2)
  * qtorch.quant.float_quantize(x, exp, man, rounding)   [quant_cuda.float_quantize_*]
  * in: fp32 [n]; out: container out_dtype [n] (MV_F32, or MV_F16 when the format fits fp16:
- * exp<=5, man<=10).  Stochastic rounding: element i uses word (i&3) of
- * Philox4x32-10(key=seed, counter={i>>2, offset}).  in == out is allowed for MV_F32. */
+ * exp<=5, man<=10).  Stochastic rounding adds random bits to the 23 - man bits that are dropped.
+ *   man >= 7 (at most 16 bits dropped — every format the reference configures): the "16-bit stream": element i uses
+ *     half-word (i&7) of Philox4x32-10(key=seed, counter={i>>3, offset}) — the low half of word (i&7)>>1 for even i,
+ *     the high half for odd i — so that one Philox call serves eight elements (mv_philox_bits16 dumps it);
+ *   man <  7: the "32-bit stream": word (i&3) of Philox4x32-10(key=seed, counter={i>>2, offset}) (mv_philox_bits).
+ * in == out is allowed for MV_F32. */
 int mv_float_quantize(const float* in, void* out, int out_dtype, int64_t n, int exp_bits,
                       int man_bits, int rounding, uint64_t seed, uint64_t offset, void* stream);
 
@@ -57,13 +61,16 @@ int mv_fixed_point_quantize(const float* in, float* out, uint8_t* mask, int64_t 
 
 /* qtorch.quant.block_quantize(x, wl, dim, rounding).  The tensor is viewed as
  * [outer, dsize, inner] with `dim` the middle axis; whole_tensor != 0 means dim = -1 (one block).
- * workspace: max(dsize,1) floats of scratch. */
+ * workspace: max(dsize,1) floats of scratch.  Stochastic rounding draws its tail bits like mv_float_quantize with
+ * man = wl: the 16-bit stream for wl >= 7, the 32-bit stream below. */
 int mv_block_quantize(const float* in, float* out, float* workspace, int64_t outer, int64_t dsize,
                       int64_t inner, int whole_tensor, int wl, int rounding, uint64_t seed,
                       uint64_t offset, void* stream);
 
 /* debug: dump the 32-bit random stream the stochastic kernels consume for elements [0,n) */
 int mv_philox_bits(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+/* ... and the 16-bit stream of mv_float_quantize for man >= 7 (one value in [0, 65536) per element) */
+int mv_philox_bits16(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
 
 /* weight_fake_quant for a Linear weight W fp32 [rows, cols] (torch.nn.qat.Linear.forward):
  * writes q(W) into `out` [rows, cols] and, if out_t != NULL, q(W)^T into out_t [cols, rows]

@@ -30,6 +30,22 @@ template <> struct Vec4Store<__half> {
         __stcs(reinterpret_cast<uint2*>(p), u);
     }
 };
+// eight consecutive values: two 16-byte stores (fp32) or one (fp16 container)
+template <typename T> struct Vec8Store;
+template <> struct Vec8Store<float> {
+    static __device__ __forceinline__ void st(float* p, float4 a, float4 b) {
+        __stcs(reinterpret_cast<float4*>(p), a);
+        __stcs(reinterpret_cast<float4*>(p) + 1, b);
+    }
+};
+template <> struct Vec8Store<__half> {
+    static __device__ __forceinline__ void st(__half* p, float4 a, float4 b) {
+        const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+        const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+        __stcs(reinterpret_cast<uint4*>(p), make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                                        *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3)));
+    }
+};
 template <typename T> __device__ __forceinline__ T cvt_out(float v);
 template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
@@ -49,7 +65,7 @@ __global__ void __launch_bounds__(kQThreads)
 quant_vec16_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t n, int exp_bits, int man_bits,
                    uint64_t seed, uint64_t offset) {
     const int64_t n8 = n >> 3;
-    constexpr int kU = 2;                                   // 2 x 32 B in flight per thread
+    constexpr int kU = 4;                                   // 4 x 32 B in flight per thread
     const int64_t stride = int64_t(gridDim.x) * kQThreads * kU;
     for (int64_t base = int64_t(blockIdx.x) * kQThreads * kU + threadIdx.x; base < n8; base += stride) {
         float4 v[kU][2];
@@ -67,15 +83,15 @@ quant_vec16_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t
             if (i >= n8) continue;
             const uint4 r = philox4x32_10(seed, uint64_t(i), offset);
             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+            float4 o[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                float4 o;
-                o.x = float_quantize_elem<true>(v[j][h].x, w[2 * h] & 0xFFFFu, exp_bits, man_bits);
-                o.y = float_quantize_elem<true>(v[j][h].y, w[2 * h] >> 16, exp_bits, man_bits);
-                o.z = float_quantize_elem<true>(v[j][h].z, w[2 * h + 1] & 0xFFFFu, exp_bits, man_bits);
-                o.w = float_quantize_elem<true>(v[j][h].w, w[2 * h + 1] >> 16, exp_bits, man_bits);
-                Vec4Store<OutT>::st(out + 8 * i + 4 * h, o);
+                o[h].x = float_quantize_elem<true>(v[j][h].x, w[2 * h] & 0xFFFFu, exp_bits, man_bits);
+                o[h].y = float_quantize_elem<true>(v[j][h].y, w[2 * h] >> 16, exp_bits, man_bits);
+                o[h].z = float_quantize_elem<true>(v[j][h].z, w[2 * h + 1] & 0xFFFFu, exp_bits, man_bits);
+                o[h].w = float_quantize_elem<true>(v[j][h].w, w[2 * h + 1] >> 16, exp_bits, man_bits);
             }
+            Vec8Store<OutT>::st(out + 8 * i, o[0], o[1]);
         }
     }
 }
@@ -180,12 +196,11 @@ template <typename OutT>
 static int launch_quant16(const float* in, OutT* out, int64_t n, int exp_bits, int man_bits, uint64_t seed,
                           uint64_t offset, cudaStream_t st) {
     if (n == 0) return 0;
-    const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) &&
-                         (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(OutT)) == 0);
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
     int64_t done = 0;
     if (aligned && n >= 8) {
         const int64_t n8 = n >> 3;
-        quant_vec16_kernel<OutT><<<grid_for(n8, kQThreads * 2), kQThreads, 0, st>>>(in, out, n, exp_bits, man_bits, seed, offset);
+        quant_vec16_kernel<OutT><<<grid_for(n8, kQThreads * 4), kQThreads, 0, st>>>(in, out, n, exp_bits, man_bits, seed, offset);
         g_launches++;
         done = n8 << 3;
     }
@@ -256,6 +271,32 @@ __global__ void absmax_lastdim_kernel(const float* __restrict__ in, int64_t oute
     for (int64_t u = blockIdx.y; u < outer; u += gridDim.y) m = fmaxf(m, fabsf(in[u * dsize + d]));
     atomicMax(mx + d, __float_as_uint(m));
 }
+// the same maxima with 16-byte loads (inner a multiple of 4, 16-byte aligned input): whole tensor (dsize = 1, one
+// "slab" of n elements split over gridDim.x) or one (outer, d) slab per blockIdx.y
+__global__ void __launch_bounds__(256)
+absmax_vec_kernel(const float* __restrict__ in, int64_t dsize, int64_t inner4, int64_t nslabs, uint32_t* __restrict__ mx) {
+    for (int64_t slab = blockIdx.y; slab < nslabs; slab += gridDim.y) {
+        const float4* p = reinterpret_cast<const float4*>(in) + slab * inner4;
+        float m = 0.f;
+        const int64_t stride = int64_t(gridDim.x) * 256 * 4;
+        for (int64_t j0 = int64_t(blockIdx.x) * 256 * 4 + threadIdx.x; j0 < inner4; j0 += stride) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t j = j0 + u * 256;
+                v[u] = j < inner4 ? __ldg(p + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                m = fmaxf(m, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+        }
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(mx + slab % dsize, __float_as_uint(m));
+    }
+}
+
+// Random tail bits of block_quantize, as for float_quantize (include/mv_b200.h): wl >= 7 drops at most 16 bits and uses
+// the 16-bit stream (eight elements per Philox call), wl < 7 the 32-bit stream.
 template <bool STOCH>
 __global__ void block_quant_kernel(const float* __restrict__ in, float* __restrict__ out,
                                    const float* __restrict__ mx, int64_t n, int64_t dsize,
@@ -266,11 +307,58 @@ __global__ void block_quant_kernel(const float* __restrict__ in, float* __restri
         const float m = whole ? mx[0] : mx[(i / inner) % dsize];
         uint32_t r = 0;
         if (STOCH) {
-            const uint4 w = philox4x32_10(seed, uint64_t(i >> 2), offset);
-            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-            r = ws[i & 3];
+            if (wl >= 7) {
+                r = philox_half16(seed, uint64_t(i), offset);
+            } else {
+                const uint4 w = philox4x32_10(seed, uint64_t(i >> 2), offset);
+                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                r = ws[i & 3];
+            }
         }
         out[i] = block_quantize_elem<STOCH>(in[i], m, r, wl);
+    }
+}
+
+// Vectorised: a thread owns 8 consecutive elements (two 16-byte vectors) of one slab.  kLast: `dim` is the last axis
+// (inner = 1, a "slab" = one outer row of dsize elements, the eight maxima are loaded as two vectors); otherwise the
+// slab's maximum is looked up once per slab — no per-element divide.  Slabs (dsize * outer of them, or 1) on grid.y.
+template <bool STOCH, bool kLast>
+__global__ void __launch_bounds__(256)
+block_quant_vec_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ mx,
+                       int64_t dsize, int64_t len8, int64_t nslabs, int wl, uint64_t seed, uint64_t offset) {
+    for (int64_t slab = blockIdx.y; slab < nslabs; slab += gridDim.y) {
+        const float ms = kLast ? 0.f : mx[slab % dsize];
+        const int64_t base8 = slab * len8;                           // index of the slab's first 8-element group
+        const int64_t stride = int64_t(gridDim.x) * 256;
+        for (int64_t j = int64_t(blockIdx.x) * 256 + threadIdx.x; j < len8; j += stride) {
+            const int64_t g8 = base8 + j;
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(in) + 2 * g8);
+            const float4 b = __ldcs(reinterpret_cast<const float4*>(in) + 2 * g8 + 1);
+            float4 ma = make_float4(ms, ms, ms, ms), mb = ma;
+            if (kLast) {
+                ma = __ldg(reinterpret_cast<const float4*>(mx) + 2 * j);
+                mb = __ldg(reinterpret_cast<const float4*>(mx) + 2 * j + 1);
+            }
+            uint32_t r[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (STOCH) {
+                if (wl >= 7) {
+                    const uint4 w = philox4x32_10(seed, uint64_t(g8), offset);
+                    r[0] = w.x & 0xFFFFu; r[1] = w.x >> 16; r[2] = w.y & 0xFFFFu; r[3] = w.y >> 16;
+                    r[4] = w.z & 0xFFFFu; r[5] = w.z >> 16; r[6] = w.w & 0xFFFFu; r[7] = w.w >> 16;
+                } else {
+                    const uint4 w0 = philox4x32_10(seed, uint64_t(2 * g8), offset);
+                    const uint4 w1 = philox4x32_10(seed, uint64_t(2 * g8 + 1), offset);
+                    r[0] = w0.x; r[1] = w0.y; r[2] = w0.z; r[3] = w0.w; r[4] = w1.x; r[5] = w1.y; r[6] = w1.z; r[7] = w1.w;
+                }
+            }
+            float4 oa, ob;
+            oa.x = block_quantize_elem<STOCH>(a.x, ma.x, r[0], wl); oa.y = block_quantize_elem<STOCH>(a.y, ma.y, r[1], wl);
+            oa.z = block_quantize_elem<STOCH>(a.z, ma.z, r[2], wl); oa.w = block_quantize_elem<STOCH>(a.w, ma.w, r[3], wl);
+            ob.x = block_quantize_elem<STOCH>(b.x, mb.x, r[4], wl); ob.y = block_quantize_elem<STOCH>(b.y, mb.y, r[5], wl);
+            ob.z = block_quantize_elem<STOCH>(b.z, mb.z, r[6], wl); ob.w = block_quantize_elem<STOCH>(b.w, mb.w, r[7], wl);
+            __stcs(reinterpret_cast<float4*>(out) + 2 * g8, oa);
+            __stcs(reinterpret_cast<float4*>(out) + 2 * g8 + 1, ob);
+        }
     }
 }
 
@@ -281,6 +369,12 @@ __global__ void philox_dump_kernel(uint32_t* out, int64_t n, uint64_t seed, uint
         const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
         out[i] = ws[i & 3];
     }
+}
+
+__global__ void philox_dump16_kernel(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = philox_half16(seed, uint64_t(i), offset);
 }
 
 // --------------------------------------------------------- weight quant (+ transpose)
@@ -322,7 +416,10 @@ extern "C" int mv_float_quantize(const float* in, void* out, int out_dtype, int6
     MV_CHECK(n == 0 || (in && out), "mv_float_quantize: null buffer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FixedParams fp{};
+    // stochastic rounding of a tail of at most 16 bits: the 16-bit stream (eight elements per Philox call)
+    const bool s16 = rounding == MV_ROUND_STOCHASTIC && man_bits >= 7;
     if (out_dtype == MV_F32) {
+        if (s16) return launch_quant16<float>(in, (float*)out, n, exp_bits, man_bits, seed, offset, st);
         return rounding == MV_ROUND_STOCHASTIC
                    ? launch_quant<0, true, float>(in, (float*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st)
                    : launch_quant<0, false, float>(in, (float*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st);
@@ -331,6 +428,7 @@ extern "C" int mv_float_quantize(const float* in, void* out, int out_dtype, int6
     MV_CHECK(exp_bits <= 5 && man_bits <= 10,
              "mv_float_quantize: (exp=%d, man=%d) is not exactly representable in an fp16 container",
              exp_bits, man_bits);
+    if (s16) return launch_quant16<__half>(in, (__half*)out, n, exp_bits, man_bits, seed, offset, st);
     return rounding == MV_ROUND_STOCHASTIC
                ? launch_quant<0, true, __half>(in, (__half*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st)
                : launch_quant<0, false, __half>(in, (__half*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st);
@@ -366,7 +464,25 @@ extern "C" int mv_block_quantize(const float* in, float* out, float* workspace, 
     uint32_t* mx = reinterpret_cast<uint32_t*>(workspace);
     const int64_t nblk = whole_tensor ? 1 : dsize;
     MV_CUDA(cudaMemsetAsync(mx, 0, sizeof(uint32_t) * nblk, st));
-    if (whole_tensor) {
+    // vector paths: 16-byte aligned buffers and slabs that are multiples of 8 elements
+    const bool al16 = reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(workspace) % 16 == 0;
+    const bool vec_whole = al16 && whole_tensor && n % 8 == 0;
+    const bool vec_slab = al16 && !whole_tensor && inner > 1 && inner % 8 == 0;
+    const bool vec_last = al16 && !whole_tensor && inner == 1 && dsize % 8 == 0;
+    auto grid2 = [](int64_t len_items, int per_block, int64_t nslabs) {
+        int64_t gx = (len_items + per_block - 1) / per_block;
+        const int64_t gy = nslabs < 65535 ? nslabs : 65535;
+        const int64_t cap = (int64_t(kNumSMs) * 16 + gy - 1) / gy;              // about 16 CTAs per SM in total
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        return dim3((unsigned)gx, (unsigned)gy);
+    };
+    if (vec_whole) {
+        absmax_vec_kernel<<<grid2(n / 4, 256 * 4, 1), 256, 0, st>>>(in, 1, n / 4, 1, mx);
+    } else if (vec_slab) {
+        absmax_vec_kernel<<<grid2(inner / 4, 256 * 4, outer * dsize), 256, 0, st>>>(in, dsize, inner / 4, outer * dsize, mx);
+    } else if (whole_tensor) {
         absmax_whole_kernel<<<grid_for(n, 256 * 8), 256, 0, st>>>(in, n, mx);
     } else if (inner == 1) {
         dim3 grid((unsigned)((dsize + 255) / 256), (unsigned)(outer < 64 ? outer : 64));
@@ -376,6 +492,22 @@ extern "C" int mv_block_quantize(const float* in, float* out, float* workspace, 
         absmax_dim_kernel<<<(unsigned)(outer * dsize), 128, 0, st>>>(in, dsize, inner, mx);
     }
     g_launches++;
+    const bool stoch = rounding == MV_ROUND_STOCHASTIC;
+    if (vec_whole || vec_slab || vec_last) {
+        const int64_t nslabs = vec_whole ? 1 : (vec_slab ? outer * dsize : outer);
+        const int64_t len8 = (vec_whole ? n : (vec_slab ? inner : dsize)) / 8;
+        const int64_t ds = vec_whole ? 1 : dsize;
+        const dim3 grid = grid2(len8, 256, nslabs);
+        if (vec_last) {
+            if (stoch) block_quant_vec_kernel<true, true><<<grid, 256, 0, st>>>(in, out, workspace, ds, len8, nslabs, wl, seed, offset);
+            else block_quant_vec_kernel<false, true><<<grid, 256, 0, st>>>(in, out, workspace, ds, len8, nslabs, wl, seed, offset);
+        } else {
+            if (stoch) block_quant_vec_kernel<true, false><<<grid, 256, 0, st>>>(in, out, workspace, ds, len8, nslabs, wl, seed, offset);
+            else block_quant_vec_kernel<false, false><<<grid, 256, 0, st>>>(in, out, workspace, ds, len8, nslabs, wl, seed, offset);
+        }
+        g_launches++;
+        return check_cuda(cudaGetLastError(), "block quant launch");
+    }
     if (rounding == MV_ROUND_STOCHASTIC)
         block_quant_kernel<true><<<grid_for(n, 256 * 4), 256, 0, st>>>(in, out, workspace, n, dsize, inner, whole_tensor, wl, seed, offset);
     else
@@ -384,6 +516,12 @@ extern "C" int mv_block_quantize(const float* in, float* out, float* workspace, 
     return check_cuda(cudaGetLastError(), "block quant launch");
 }
 
+extern "C" int mv_philox_bits16(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+    if (n <= 0) return 0;
+    philox_dump16_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, offset);
+    g_launches++;
+    return check_cuda(cudaGetLastError(), "philox dump launch");
+}
 extern "C" int mv_philox_bits(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
     if (n <= 0) return 0;
     philox_dump_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, offset);

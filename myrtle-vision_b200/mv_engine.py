@@ -23,11 +23,32 @@ Gradients travel as fp16 tensor-core operands scaled by a power of two S chosen 
 the incoming gradient (the reference itself trains under GradScaler(65536), classification/
 train.py:167); parameter gradients are un-scaled in fp32 before they are returned.
 """
+import contextlib
 import os
 
 import torch
 
 import mv_native as mv
+
+
+class _Range:
+    """`profile=True` of the reference's ViT (models/vit.py:115-124, 205-213: autograd-profiler record_function
+    contexts): the same five labels, as a record_function (torch profiler) AND an NVTX range (nsys / ncu)."""
+
+    def __init__(self, name):
+        self.name = name
+        self.rf = None
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+        self.rf = torch.autograd.profiler.record_function(self.name)
+        self.rf.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.rf.__exit__(*exc)
+        torch.cuda.nvtx.range_pop()
+        return False
 
 
 class EngineConfig:
@@ -45,6 +66,10 @@ class EncoderEngine:
         self.cfg = cfg
         self.params = list(params)
         assert len(self.params) == 2 + PER_LAYER * cfg.depth
+        # debugging aids of the reference's model, off the training path: profile ranges and, per block, the module
+        # the reference passes the softmax probabilities through (models/vit.py:80-82, 94 — a hook point)
+        self.profile = False
+        self.probes = None
         plan = cfg.plan
         if plan.inp not in ((5, 10), (8, 10), None):
             raise NotImplementedError("no tensor-core operand container for input format %r" % (plan.inp,))
@@ -179,6 +204,19 @@ class EncoderEngine:
         return torch.exp2(torch.floor(torch.log2(self.scaler_state[1] / amax))).clamp(2.0 ** -60, 2.0 ** 60)
 
     # ------------------------------------------------------------------ forward
+    def _range(self, name):
+        return _Range(name) if self.profile else contextlib.nullcontext()
+
+    def _probe_attention(self, l, qkv, B, H, N):
+        """Debug only: if forward hooks are registered on block l's `attn_output` module, hand it the softmax
+        probabilities [B, H, N, N] (computed unfused from the same qkv; the fused kernels never materialise them).
+        The training arithmetic is not touched; Python hooks do not replay inside a captured CUDA graph."""
+        m = None if self.probes is None else self.probes[l]
+        if m is None or not (m._forward_hooks or m._forward_pre_hooks):
+            return
+        q, k = qkv.view(B, N, 3, H, 64).float().permute(2, 0, 3, 1, 4)[:2]
+        m(torch.softmax(torch.matmul(q, k.transpose(-2, -1)) * 0.125, dim=-1))
+
     def forward(self, img, pos_full, cls_token, save):
         # a training forward opens an overflow window that its backward closes (mv_overflow_update); inference
         # forwards report nothing
@@ -197,34 +235,39 @@ class EncoderEngine:
         f16 = torch.float16
         dev = img.device
 
-        patches = mv.patchify_q(img, P, q_in=fmt, cls_slot=True)            # [M, P*P*C], zero cls rows
-        x = torch.empty(M, D, dtype=torch.float32, device=dev)
-        pos32 = pos_full.detach().reshape(N, D).contiguous()
-        mv.gemm(patches, wq[0][0], x, bias=prm[1], q_out=plan.out, residual=pos32, q_res=plan.ff,
-                rows_per_img=N)
-        mv.cls_rows(cls_token.detach().reshape(D).contiguous(), pos32, x, B, N, D, q_ff=plan.ff)
+        with self._range("patch_to_embedding"):
+            patches = mv.patchify_q(img, P, q_in=fmt, cls_slot=True)            # [M, P*P*C], zero cls rows
+            x = torch.empty(M, D, dtype=torch.float32, device=dev)
+            pos32 = pos_full.detach().reshape(N, D).contiguous()
+            mv.gemm(patches, wq[0][0], x, bias=prm[1], q_out=plan.out, residual=pos32, q_res=plan.ff,
+                    rows_per_img=N)
+            mv.cls_rows(cls_token.detach().reshape(D).contiguous(), pos32, x, B, N, D, q_ff=plan.ff)
 
         saved = {"B": B, "N": N, "patches": patches, "layers": []} if save else None
-        for l in range(cfg.depth):
-            b0 = 2 + PER_LAYER * l
-            xn1, mean1, rstd1 = mv.layernorm_q_fwd(x, prm[b0], prm[b0 + 1], q_in=fmt, q_post=fmt)
-            qkv = torch.empty(M, 3 * D, dtype=f16, device=dev)
-            mv.gemm(xn1, wq[b0 + 2][0], qkv, bias=prm[b0 + 3], q_out=plan.out)
-            att, lse = mv.attention_fwd(qkv, B, H, N, scale=0.125, q_out=fmt)
-            x1 = torch.empty(M, D, dtype=torch.float32, device=dev)
-            mv.gemm(att, wq[b0 + 4][0], x1, bias=prm[b0 + 5], q_out=plan.out, residual=x,
-                    q_res=plan.ff)
-            xn2, mean2, rstd2 = mv.layernorm_q_fwd(x1, prm[b0 + 6], prm[b0 + 7], q_in=fmt, q_post=fmt)
-            u = torch.empty(M, Mm, dtype=f16, device=dev)
-            h = torch.empty(M, Mm, dtype=f16, device=dev)
-            mv.gemm(xn2, wq[b0 + 8][0], h, bias=prm[b0 + 9], q_out=plan.out, aux=u,
-                    epilogue=mv.EPI_GELU, q_res=fmt)
-            x2 = torch.empty(M, D, dtype=torch.float32, device=dev)
-            mv.gemm(h, wq[b0 + 10][0], x2, bias=prm[b0 + 11], q_out=plan.out, residual=x1,
-                    q_res=plan.ff)
-            if save:
-                saved["layers"].append((x, xn1, mean1, rstd1, qkv, att, lse, x1, xn2, mean2, rstd2, u, h))
-            x = x2
+        with self._range("transformer"):
+            for l in range(cfg.depth):
+                b0 = 2 + PER_LAYER * l
+                with self._range("transformer:attention"):
+                    xn1, mean1, rstd1 = mv.layernorm_q_fwd(x, prm[b0], prm[b0 + 1], q_in=fmt, q_post=fmt)
+                    qkv = torch.empty(M, 3 * D, dtype=f16, device=dev)
+                    mv.gemm(xn1, wq[b0 + 2][0], qkv, bias=prm[b0 + 3], q_out=plan.out)
+                    self._probe_attention(l, qkv, B, H, N)
+                    att, lse = mv.attention_fwd(qkv, B, H, N, scale=0.125, q_out=fmt)
+                    x1 = torch.empty(M, D, dtype=torch.float32, device=dev)
+                    mv.gemm(att, wq[b0 + 4][0], x1, bias=prm[b0 + 5], q_out=plan.out, residual=x,
+                            q_res=plan.ff)
+                with self._range("transformer:feedforward"):
+                    xn2, mean2, rstd2 = mv.layernorm_q_fwd(x1, prm[b0 + 6], prm[b0 + 7], q_in=fmt, q_post=fmt)
+                    u = torch.empty(M, Mm, dtype=f16, device=dev)
+                    h = torch.empty(M, Mm, dtype=f16, device=dev)
+                    mv.gemm(xn2, wq[b0 + 8][0], h, bias=prm[b0 + 9], q_out=plan.out, aux=u,
+                            epilogue=mv.EPI_GELU, q_res=fmt)
+                    x2 = torch.empty(M, D, dtype=torch.float32, device=dev)
+                    mv.gemm(h, wq[b0 + 10][0], x2, bias=prm[b0 + 11], q_out=plan.out, residual=x1,
+                            q_res=plan.ff)
+                if save:
+                    saved["layers"].append((x, xn1, mean1, rstd1, qkv, att, lse, x1, xn2, mean2, rstd2, u, h))
+                x = x2
         return x.view(B, N, D), saved
 
     # ----------------------------------------------------------------- backward
@@ -352,6 +395,7 @@ class EncoderEngine:
                                                    out_dtype=f32)
             qkv = torch.empty(M, 3 * D, dtype=f32 if ex else f16, device=dev)
             mv.gemm(A_(xn1), wq[b0 + 2][0], qkv, bias=prm[b0 + 3], q_out=plan.out)
+            self._probe_attention(l, qkv, B, H, N)
             if ex:
                 att, lse = self._attention_exact_fwd(qkv, B, H, N)           # lse slot holds the probabilities
                 att16 = att

@@ -213,10 +213,11 @@ def block_quantize(x, wl, dim=-1, rounding="nearest", seed=0, offset=0, out=None
     return out
 
 
-def philox_bits(n, seed, offset=0, device="cuda"):
+def philox_bits(n, seed, offset=0, device="cuda", half=False):
+    """The random stream of the stochastic kernels; half=True: the 16-bit stream of float_quantize for man >= 7."""
     out = torch.empty(n, dtype=torch.int32, device=device)
-    _check(lib().mv_philox_bits(_ptr(out), ctypes.c_int64(n), ctypes.c_uint64(seed),
-                                ctypes.c_uint64(offset), _stream()), "mv_philox_bits")
+    fn = lib().mv_philox_bits16 if half else lib().mv_philox_bits
+    _check(fn(_ptr(out), ctypes.c_int64(n), ctypes.c_uint64(seed), ctypes.c_uint64(offset), _stream()), "mv_philox_bits")
     return out
 
 

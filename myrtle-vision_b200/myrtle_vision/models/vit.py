@@ -51,6 +51,10 @@ class Attention(nn.Module):
         self.scale = dim_head ** -0.5
         self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=True)
         self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout))
+        # the reference passes the softmax probabilities through this module so that forward hooks can read the
+        # attention maps (models/vit.py:80-82, 94); a hook registered here switches that block's probabilities on
+        # (mv_engine.EncoderEngine._probe_attention, debug only)
+        self.attn_output = nn.Identity()
 
 
 class Transformer(nn.Module):
@@ -197,6 +201,8 @@ class ViT(nn.Module):
             cfg = mv_engine.EngineConfig(self.dim, self.heads, self.mlp_dim, self.depth,
                                          self.patch_size, self.quantizer.plan)
             self._engine = mv_engine.EncoderEngine(cfg, self._engine_params())
+            self._engine.profile = self.profile
+            self._engine.probes = [block[0].fn.fn.attn_output for block in self.transformer.layers]
         return self._engine
 
     # ------------------------------------------------------------------- forward
@@ -262,7 +268,8 @@ class ViT(nn.Module):
         pos_full = self._pos_full(h // p, w // p)
         x = mv_engine.EncoderFunction.apply(engine, img, pos_full, self.cls_token,
                                             *engine.params)
-        return self._decode(x, (h, w))
+        with engine._range("mlp_head"):
+            return self._decode(x, (h, w))
 
     def convert(self) -> None:
         self.quantizer.convert()

@@ -242,6 +242,17 @@ void mvo_philox_bits(uint32_t* r, int64_t n, uint64_t seed, uint64_t offset) {
 }
 
 /* uniform [0,1) floats derived from the same bits: (bits >> 8) * 2^-24 */
+/* the 16-bit stream (float_quantize, man_bits >= 7): element i takes half-word (i & 7) of philox(seed, i >> 3, offset) —
+ * low half of word (i & 7) >> 1 for even i, high half for odd i */
+void mvo_philox_bits16(uint32_t* r, int64_t n, uint64_t seed, uint64_t offset) {
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int64_t i = 0; i < n; i++) {
+        if ((i & 7) == 0) philox4x32_10(seed, (uint64_t)(i >> 3), offset, w);
+        const uint32_t word = w[(i & 7) >> 1];
+        r[i] = (i & 1) ? (word >> 16) : (word & 0xFFFFu);
+    }
+}
+
 void mvo_philox_uniform(float* r, int64_t n, uint64_t seed, uint64_t offset) {
     uint32_t w[4];
     for (int64_t i = 0; i < n; i++) {

@@ -114,9 +114,12 @@ def block_quantize(x, wl, dim=-1, rounding="nearest", rbits=None):
     return o
 
 
-def philox_bits(n, seed, offset=0):
+def philox_bits(n, seed, offset=0, half=False):
+    """32 random bits per element (word i&3 of philox(i>>2)); half=True: the 16-bit stream the CUDA float_quantize uses
+    for man >= 7 (half-word i&7 of philox(i>>3)) — include/mv_b200.h."""
     r = np.empty(int(n), dtype=np.uint32)
-    lib().mvo_philox_bits(_p(r), ctypes.c_int64(n), ctypes.c_uint64(seed), ctypes.c_uint64(offset))
+    fn = lib().mvo_philox_bits16 if half else lib().mvo_philox_bits
+    fn(_p(r), ctypes.c_int64(n), ctypes.c_uint64(seed), ctypes.c_uint64(offset))
     return r
 
 

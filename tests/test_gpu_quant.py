@@ -29,17 +29,27 @@ def test_float_quantize_nearest_bit_exact(exp, man, n):
     assert np.array_equal(bits(got), bits(qo.float_quantize(x.numpy(), exp, man)))
 
 
-@pytest.mark.parametrize("exp,man", [(5, 10), (8, 10), (4, 3)])
+@pytest.mark.parametrize("exp,man", [(5, 10), (8, 10), (8, 7), (4, 3), (5, 6)])
 def test_float_quantize_stochastic_same_stream_bit_exact(exp, man):
+    """man >= 7 consumes the 16-bit stream (eight elements per Philox call), man < 7 the 32-bit one (mv_b200.h)."""
     import mv_native as mv
     from oracle import quant_oracle as qo
     n = 300001                                  # ragged: exercises the scalar tail
     x = lognormal(n)
+    half = man >= 7
     for seed, off in ((77, 5), (2 ** 40 + 3, 2 ** 33)):
-        r = qo.philox_bits(n, seed, off)
-        assert np.array_equal(mv.philox_bits(n, seed, off).cpu().numpy().view(np.uint32), r)
+        r = qo.philox_bits(n, seed, off, half=half)
+        assert np.array_equal(mv.philox_bits(n, seed, off, half=half).cpu().numpy().view(np.uint32), r)
+        want = qo.float_quantize(x.numpy(), exp, man, "stochastic", r)
         got = mv.float_quantize(x.cuda(), exp, man, "stochastic", seed=seed, offset=off).cpu().numpy()
-        assert np.array_equal(bits(got), bits(qo.float_quantize(x.numpy(), exp, man, "stochastic", r)))
+        assert np.array_equal(bits(got), bits(want))
+        xu = torch.cat([torch.zeros(1), x]).cuda()[1:]          # 4-byte aligned only: the scalar kernel, same stream
+        got = mv.float_quantize(xu, exp, man, "stochastic", seed=seed, offset=off).cpu().numpy()
+        assert np.array_equal(bits(got), bits(want))
+        if exp <= 5 and man <= 10:                               # fp16 container: same values
+            got = mv.float_quantize(x.cuda(), exp, man, "stochastic", seed=seed, offset=off,
+                                    out_dtype=torch.float16).float().cpu().numpy()
+            assert np.array_equal(bits(got), bits(want))
 
 
 def test_unaligned_views_and_fp16_container():
@@ -75,16 +85,18 @@ def test_fixed_point_bit_exact(fl):
     assert np.array_equal(o.cpu().numpy(), wo) and np.array_equal(m.cpu().numpy(), wm)
 
 
+@pytest.mark.parametrize("shape", [(64, 96, 40), (7, 9, 5)])     # 16-byte vector kernels; ragged: the scalar kernels
 @pytest.mark.parametrize("dim", [-1, 0, 1, 2])
-def test_block_quantize_bit_exact(dim):
+def test_block_quantize_bit_exact(dim, shape):
     import mv_native as mv
     from oracle import quant_oracle as qo
-    x = lognormal(64 * 96 * 40, specials=False).reshape(64, 96, 40)
+    x = lognormal(shape[0] * shape[1] * shape[2], specials=False).reshape(shape)
     got = mv.block_quantize(x.cuda(), 8, dim).cpu().numpy()
     assert np.array_equal(bits(got), bits(qo.block_quantize(x.numpy(), 8, dim)))
-    r = qo.philox_bits(x.numel(), 9, 2)
-    got = mv.block_quantize(x.cuda(), 8, dim, "stochastic", seed=9, offset=2).cpu().numpy()
-    assert np.array_equal(bits(got), bits(qo.block_quantize(x.numpy(), 8, dim, "stochastic", r)))
+    for wl in (8, 5):                       # 16-bit stream (wl >= 7) and 32-bit stream
+        r = qo.philox_bits(x.numel(), 9, 2, half=wl >= 7)
+        got = mv.block_quantize(x.cuda(), wl, dim, "stochastic", seed=9, offset=2).cpu().numpy()
+        assert np.array_equal(bits(got), bits(qo.block_quantize(x.numpy(), wl, dim, "stochastic", r)))
 
 
 def test_weight_quant_and_transpose():

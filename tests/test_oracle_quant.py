@@ -93,6 +93,15 @@ def test_half_outputs_are_fp16_representable():
     assert np.array_equal(q.astype(np.float16).astype(np.float32), q)
 
 
+def test_philox_16bit_stream_is_the_half_words_of_the_same_generator():
+    n = 1000
+    w = qo.philox_bits(n, seed=11, offset=2)                 # word (j & 3) of philox(j >> 2): philox(c) = w[4c : 4c + 4]
+    h = qo.philox_bits(n, seed=11, offset=2, half=True)      # half-word (i & 7) of philox(i >> 3)
+    for i in range(n // 2):
+        word = int(w[4 * (i >> 3) + ((i & 7) >> 1)])
+        assert int(h[i]) == ((word >> 16) if (i & 1) else (word & 0xFFFF))
+
+
 def test_philox_known_answer():
     # Random123 KAT for philox4x32-10: counter = 0, key = 0
     r = qo.philox_bits(4, seed=0, offset=0)

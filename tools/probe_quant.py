@@ -15,7 +15,7 @@ for (e, m) in [(5, 10), (8, 10), (4, 3), (5, 2), (8, 7)]:
     got = mv.float_quantize(xd, e, m).cpu().numpy()
     want = qo.float_quantize(x.numpy(), e, m)
     print("float nearest (%d,%d): mismatches %d" % (e, m, int((got.view(np.uint32) != want.view(np.uint32)).sum())))
-    r = qo.philox_bits(n, 77, 5)
+    r = qo.philox_bits(n, 77, 5, half=m >= 7)
     got = mv.float_quantize(xd, e, m, "stochastic", seed=77, offset=5).cpu().numpy()
     want = qo.float_quantize(x.numpy(), e, m, "stochastic", r)
     print("float stochastic (%d,%d): mismatches %d" % (e, m, int((got.view(np.uint32) != want.view(np.uint32)).sum())))
@@ -58,3 +58,15 @@ for nn, label in [(1 << 28, "1GiB")]:
     ms = e0.elapsed_time(e1) / 10
     print("torch copy %s: %.3f ms %.0f GB/s" % (label, ms, nn * 8 / ms / 1e6), flush=True)
     del big, out
+# block quantise at the bench shapes (12 algorithmic bytes per element: max pass + quant pass)
+x2 = (torch.randn(16384, 16384, device=dev) * torch.exp(torch.empty(16384, 16384, device=dev).uniform_(-12, 8)))
+o2 = torch.empty_like(x2)
+for label, kw in [("dim=-1 nearest", dict(dim=-1)), ("dim=0 nearest", dict(dim=0)), ("dim=0 stochastic", dict(dim=0, rounding="stochastic", seed=5, offset=1)),
+                  ("dim=1 nearest", dict(dim=1)), ("dim=1 stochastic", dict(dim=1, rounding="stochastic", seed=5, offset=1))]:
+    for _ in range(3): mv.block_quantize(x2, 8, out=o2, **kw)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): mv.block_quantize(x2, 8, out=o2, **kw)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print("block wl=8 %s: %.3f ms  %.0f GB/s" % (label, ms, x2.numel() * 12 / ms / 1e6), flush=True)
