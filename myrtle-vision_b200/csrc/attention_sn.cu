@@ -36,6 +36,33 @@ constexpr int kSnFwdThreads = 32 * (2 + kSnMathWarps + kSnTailWarps);   // produ
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// warp-level MMA (m16n8k16, fp16 operands, fp32 accumulators) and its fragment loads: used where the problem is a few
+// rows or columns wide (the odd keys of the backward), far below a tcgen05 tile
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_row)));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+                 : "=r"(r0), "=r"(r1) : "r"(smem_u32(smem_row)));
+}
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ uint32_t pack_h2_rn(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -669,20 +696,28 @@ constexpr int kSnFwdSmem = 4 * kSnKVBytes + 2 * kSnTile + kSnTailWarps * (64 + k
 // pair ahead of the math warps.  Code that runs once per pass or pair (tail block, epilogues, statistics) is kept small
 // on purpose: the kernel is far larger than the instruction caches, and a rarely executed, fully unrolled section costs
 // more in instruction-fetch misses than in arithmetic (the 16-wide tail block took 5 000 cycles that way).
-constexpr int kSnBwdMathWarps = 16, kSnBwdStatWarps = 1, kSnStatU = 6;   // 20 warps: 5 per scheduler, 96 registers
+constexpr int kSnBwdMathWarps = 16, kSnBwdStatWarps = 2, kSnStatU = 4;   // 20 warps: 5 per scheduler, 96 registers
 constexpr int kSnBwdMathThreads = 32 * kSnBwdMathWarps, kSnBwdStatThreads = 32 * kSnBwdStatWarps;
 // One more warp owns the TMA stores: the math warps park dV_j / dK_j / dQ_i as fp16 in 128-byte-swizzled tiles (idle slots
 // of the dS^T ring) and go on; written straight from the registers — one accumulator row per thread — every 16-byte
 // store instruction of a warp touches 32 different lines and the LSU serialises them (4 000 cycles per pass epilogue,
 // 17 000 of a pair's 43 000, clock64 timeline).
-constexpr int kSnBwdThreads = 32 * (2 + kSnBwdMathWarps + kSnBwdStatWarps + 1);
+constexpr int kSnBwdThreads = 32 * (2 + kSnBwdMathWarps + kSnBwdStatWarps);
 constexpr int kSnQBytes = kSnMaxKeys * 128;            // Q or dO of one pair: 272 rows x 128 B
 constexpr int kSnOffQ = 4 * kSnTile;
 constexpr int kSnOffDO = kSnOffQ + kSnQBytes;
 constexpr int kSnOffDS = kSnOffDO + kSnQBytes;
-constexpr int kSnOffVec = kSnOffDS + 4 * kSnTile;      // L[272], Delta[272], dQ tail accumulators [16][64]
+// Odd keys (N = 256 + w, w <= kSnOddMax — the class token of the 256-patch configurations): instead of a third 128-key
+// pass with w live keys (a quarter of the kernel's time for one key), keys 256 .. 256 + w - 1 are handled on the CUDA
+// cores at the end of the pair's last pass, from the Q / dO rows resident in shared memory (odd_phase below).
+constexpr int kSnOddMax = 4;
+constexpr int kSnOffKo = kSnOffDS + 4 * kSnTile;       // K / V rows 256 .. 271 as the TMA leaves them (2 x 2 KB, 1024-aligned)
+constexpr int kSnOffVec = kSnOffKo + 4096;             // L[272], Delta[272], dQ tail accumulators [16][64]
 constexpr int kSnOffVec2 = kSnOffVec + (2 * kSnMaxKeys + 16 * 64) * 4;  // L / Delta of the next pair (double buffer)
-constexpr int kSnOffBar = kSnOffVec2 + 2 * kSnMaxKeys * 4;
+// odd keys: k_u, v_u in fp32 [w][64] each; p[u][row], dS[u][row] (fp32, [w][272] each); dV_u / dK_u sums [w][2][64]
+constexpr int kSnOffOdd = kSnOffVec2 + 2 * kSnMaxKeys * 4;
+constexpr int kSnOddFloats = kSnOddMax * (2 * 64 + 2 * kSnMaxKeys + 2 * 64);
+constexpr int kSnOffBar = kSnOffOdd + kSnOddFloats * 4;
 constexpr int kSnBwdSmem = kSnOffBar + 256 + 1024;
 static_assert(kSnBwdSmem <= 232448, "attention bwd (short sequences): shared memory over the 227 KB limit");
 
@@ -692,6 +727,7 @@ struct SnBwdDev {
     int n_pass;                 // 128-key tiles
     int n_reg;                  // regular 64-row blocks per pass (2 per 128 query rows below 256)
     int tail_w;                 // width (multiple of 16) of the tail block of rows [256, 256 + tail_w); 0 if N <= 256
+    int n_odd;                  // keys 256 .. 256 + n_odd - 1 handled by odd_phase instead of a third pass (0: none)
     float scale_log2, scale;
     const float* lse;
     const __half* o;            // forward output and its gradient, [B*N, D]: Delta = rowsum(dO * O) per head
@@ -715,6 +751,13 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     float* sLD0 = reinterpret_cast<float*>(smem + kSnOffVec);     // L[272], Delta[272] of even pairs
     float* sLD1 = reinterpret_cast<float*>(smem + kSnOffVec2);    // ... of odd pairs
     float* sdQt = sLD0 + 2 * kSnMaxKeys;
+    const uint8_t* sKo = smem + kSnOffKo;                          // K rows 256 .. 271 of the pair (128-byte swizzle)
+    const uint8_t* sVo = sKo + 2048;
+    float* kof = reinterpret_cast<float*>(smem + kSnOffOdd);       // [w][64] k_u as fp32
+    float* vof = kof + kSnOddMax * 64;
+    float* po = vof + kSnOddMax * 64;                              // [w][272] P[row, 256 + u]
+    float* dso = po + kSnOddMax * kSnMaxKeys;                      // [w][272] dS[row, 256 + u]
+    float* ored = dso + kSnOddMax * kSnMaxKeys;                    // [w][2][64] dV_u, dK_u
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSnOffBar);
     uint64_t* kv_full = bars;           // [2]
     uint64_t* kv_empty = bars + 2;      // [2]
@@ -752,7 +795,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
             mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], kSnBwdMathWarps / 2);
         }
-        mbar_init(qdo_full, 1); mbar_init(qdo_empty, 1);
+        mbar_init(qdo_full, 1); mbar_init(qdo_empty, p.n_odd > 0 ? 2 : 1);   // + the math warps' odd-key phase
         mbar_init(acc_full, 1); mbar_init(acc_empty, kSnBwdMathWarps);
         mbar_init(dq_full, 1); mbar_init(dq_empty, kSnBwdMathWarps);
         for (int s = 0; s < 2; s++) { mbar_init(&st_full[s], kSnBwdStatWarps); mbar_init(&st_empty[s], kSnBwdMathWarps); }
@@ -761,6 +804,7 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     // the dS^T tiles feed a K dimension: rows of keys that no thread writes must hold finite values
     for (int i = threadIdx.x; i < 4 * kSnTile / 16; i += kSnBwdThreads)
         reinterpret_cast<uint4*>(sdS)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 2 * kSnOddMax * kSnMaxKeys; i += kSnBwdThreads) po[i] = 0.f;     // P, dS of the odd keys: rows >= N stay zero
     fence_proxy_async();
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
@@ -772,33 +816,118 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     const uint32_t tdV = tmem_base + 256, tdK = tmem_base + 320, tdQ = tmem_base + 384;
 
     if (warp == 0) {
-        // ================================ TMA producer ================================
-        if (lane == 0) {
-            int pc = 0;
-            const int q_tiles = p.n_reg >> 1;
-            for (int n = 0; n < n_local; n++) {
-                const int bh = blockIdx.x + n * gridDim.x;
+        // ================================ TMA warp: loads and stores ================================
+        // One warp serves two independent in-order queues without ever blocking on either (20 warps is what 96
+        // registers per thread allow, and the per-row statistics need two of them):
+        //   loads   per pair: K / V of pass 0, Q / dO (+ the odd K / V rows), K / V of the later passes — each as soon as
+        //           its buffer is free;
+        //   stores  per pair: dV_j / dK_j of every pass, then the dQ tiles — as soon as the 16 math warps have parked them
+        //           (rows >= N of a box are clipped by the tensor map); the tiles are released once the TMA engine has
+        //           read them.  While the dQ tiles are parked the warp also sums their columns — the q part of the fused
+        //           to_qkv bias gradient (lane l owns columns 2l, 2l + 1; rows >= N are exact zeros) — in registers for the
+        //           whole kernel (the host sizes the grid so that a CTA stays on one head), 64 rows per turn so that a
+        //           load never waits long behind it.
+        const int q_tiles = p.n_reg >> 1;
+        const bool do_cs = p.dbias != nullptr;
+        float cq0 = 0.f, cq1 = 0.f;
+        int ln = 0, lk = 0;                       // load queue: pair, step (0: K/V of pass 0, 1: Q/dO, k >= 2: K/V of pass k - 1)
+        int en = 0, ek = 0, cs_row = -1;          // store queue: pair, event (j < n_pass: pass j, n_pass: dQ), column-sum progress
+        while (ln < n_local || en < n_local) {
+            bool progress = false;
+            if (ln < n_local) {
+                const int bh = blockIdx.x + ln * gridDim.x;
                 const int b = bh / p.H, h = bh % p.H;
-                for (int j = 0; j < p.n_pass; j++, pc++) {
-                    const int st = pc & 1;
-                    mbar_wait_relaxed(&kv_empty[st], ((pc >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&kv_full[st], 2 * kSnTile);
-                    tma_load_3d(sK + st * kSnTile, &tm_qkv128, &kv_full[st], p.D + h * 64, j * 128, b);
-                    tma_load_3d(sV + st * kSnTile, &tm_qkv128, &kv_full[st], 2 * p.D + h * 64, j * 128, b);
-                    if (j == 0) {
-                        mbar_wait_relaxed(qdo_empty, (n & 1) ^ 1);
-                        mbar_arrive_expect_tx(qdo_full, 2 * (q_tiles * kSnTile + p.tail_w * 128));
-                        for (int i = 0; i < q_tiles; i++) {
-                            tma_load_3d(sQ + i * kSnTile, &tm_qkv128, qdo_full, h * 64, i * 128, b);
-                            tma_load_3d(sdO + i * kSnTile, &tm_do128, qdo_full, h * 64, i * 128, b);
+                if (lk == 1) {
+                    if (mbar_test(qdo_empty, (ln & 1) ^ 1)) {
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(qdo_full, 2 * (q_tiles * kSnTile + p.tail_w * 128) + (p.n_odd > 0 ? 4096 : 0));
+                            if (p.n_odd > 0) {
+                                tma_load_3d(const_cast<uint8_t*>(sKo), &tm_qkv16, qdo_full, p.D + h * 64, 256, b);
+                                tma_load_3d(const_cast<uint8_t*>(sVo), &tm_qkv16, qdo_full, 2 * p.D + h * 64, 256, b);
+                            }
+                            for (int i = 0; i < q_tiles; i++) {
+                                tma_load_3d(sQ + i * kSnTile, &tm_qkv128, qdo_full, h * 64, i * 128, b);
+                                tma_load_3d(sdO + i * kSnTile, &tm_do128, qdo_full, h * 64, i * 128, b);
+                            }
+                            for (int r = 0; r < p.tail_w; r += 16) {
+                                tma_load_3d(sQ + (256 + r) * 128, &tm_qkv16, qdo_full, h * 64, 256 + r, b);
+                                tma_load_3d(sdO + (256 + r) * 128, &tm_do16, qdo_full, h * 64, 256 + r, b);
+                            }
                         }
-                        for (int r = 0; r < p.tail_w; r += 16) {
-                            tma_load_3d(sQ + (256 + r) * 128, &tm_qkv16, qdo_full, h * 64, 256 + r, b);
-                            tma_load_3d(sdO + (256 + r) * 128, &tm_do16, qdo_full, h * 64, 256 + r, b);
+                        progress = true;
+                        lk++;
+                    }
+                } else {
+                    const int j = lk == 0 ? 0 : lk - 1;
+                    const int pc = ln * p.n_pass + j, st = pc & 1;
+                    if (mbar_test(&kv_empty[st], ((pc >> 1) & 1) ^ 1)) {
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(&kv_full[st], 2 * kSnTile);
+                            tma_load_3d(sK + st * kSnTile, &tm_qkv128, &kv_full[st], p.D + h * 64, j * 128, b);
+                            tma_load_3d(sV + st * kSnTile, &tm_qkv128, &kv_full[st], 2 * p.D + h * 64, j * 128, b);
                         }
+                        progress = true;
+                        lk++;
                     }
                 }
+                if (lk > p.n_pass) { lk = 0; ln++; }
             }
+            if (en < n_local) {
+                const int bh = blockIdx.x + en * gridDim.x;
+                const int b = bh / p.H, h = bh % p.H;
+                const int pc_last = en * p.n_pass + p.n_pass - 1;
+                if (ek < p.n_pass) {
+                    const bool last = ek == p.n_pass - 1;
+                    if (last ? mbar_test(&sg_full[0], en & 1) : mbar_test(&sg_full[1], (en * p.n_pass + ek) & 1)) {
+                        if (lane == 0) {
+                            const uint8_t* src = sdS + (last ? 0 : 2 * kSnTile);
+                            tma_store_3d(&tm_dqkv128, src, 2 * p.D + h * 64, ek * 128, b);
+                            tma_store_3d(&tm_dqkv128, src + kSnTile, p.D + h * 64, ek * 128, b);
+                            tma_store_commit();
+                            tma_store_wait_read();
+                            mbar_arrive(&sg_free[last ? 0 : 1]);
+                        }
+                        progress = true;
+                        ek++;
+                    }
+                } else if (cs_row < 0) {
+                    if (mbar_test(&sg_full[1], pc_last & 1)) {                 // the dQ tiles: the hi event of the last pass
+                        if (lane == 0) {
+                            for (int t = 0; t < q_tiles; t++) tma_store_3d(&tm_dqkv128, sdS + (2 + t) * kSnTile, h * 64, t * 128, b);
+                            tma_store_commit();
+                        }
+                        progress = true;
+                        cs_row = do_cs ? 0 : q_tiles * 128;
+                    }
+                } else {
+                    if (cs_row < q_tiles * 128) {
+                        const uint8_t* tile = sdS + 2 * kSnTile;
+#pragma unroll 8
+                        for (int r = cs_row; r < cs_row + 64; r++) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(
+                                tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4));
+                            cq0 += f.x; cq1 += f.y;
+                        }
+                        cs_row += 64;
+                    }
+                    if (cs_row >= q_tiles * 128) {
+                        __syncwarp();
+                        if (lane == 0) { tma_store_wait_read(); mbar_arrive(&sg_free[1]); }
+                        cs_row = -1;
+                        ek = 0;
+                        en++;
+                    }
+                    progress = true;
+                }
+            }
+            __syncwarp();
+            if (!progress) __nanosleep(64);
+        }
+        if (lane == 0) tma_store_wait_all();
+        if (do_cs && n_local > 0) {
+            const int h = blockIdx.x % p.H;
+            atomicAdd(p.dbias + h * 64 + 2 * lane, cq0);
+            atomicAdd(p.dbias + h * 64 + 2 * lane + 1, cq1);
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
@@ -847,9 +976,10 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     if (++c_pre == nblk) { c_pre = 0; j_pre++; }
                     __syncwarp();
                 };
-                auto post = [&]() {
+                // post, first half: dV_j += P^T dO_c, dK_j += dS^T Q_c (A straight from TMEM)
+                auto post_vk = [&]() {
                     const int gb = gb_post, g = gb & 1, j = j_post, c = c_post;
-                    const int pc = pc0 + j, st = pc & 1;
+                    const int pc = pc0 + j;
                     const bool regular = c < p.n_reg;
                     const uint64_t roff = uint64_t(regular ? 64 * c : 256) * 8;
                     const uint32_t tS = tmem_base + g * 128, tdP = tS + 64;
@@ -857,32 +987,37 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     mbar_wait(&pds_full[g], (gb >> 1) & 1);
                     SN_TRACE(leader, 0, 3, gb);                             // math of block gb done (seen by issuer)
                     if (c == 0 && pc > 0) mbar_wait(acc_empty, (pc - 1) & 1);       // dV / dK of the previous pass were read
-                    if (c == 1 && j == 0 && n > 0) mbar_wait(dq_empty, (n - 1) & 1);  // dQ of the previous pair was read
                     tc_fence_after();
                     const uint32_t acc0 = c > 0 ? 1u : 0u;
                     if (leader) {
-                        if (regular) {
-                            const bool with_dq = (c & 1) != 0;
-                            // dQ_i += dS_i K_j for the block pair (c-1, c): A = the pair's dS^T tiles in shared memory
-                            // (M = 2 x 64 rows, K = 128 keys).  dV, dK, dQ are independent accumulators: round-robin.
+                        const int ksteps = regular ? 4 : (p.tail_w >> 4);
+                        for (int k = 0; k < ksteps; k++) {
+                            umma_f16_ts(tdV, tS + k * 8, bdo + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                            umma_f16_ts(tdK, tdP + k * 8, bq + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                        }
+                    }
+                    __syncwarp();
+                };
+                // post, second half — issued AFTER the S^T / dP^T MMAs of the group's next block, which the math warps are
+                // waiting for and which do not depend on it: dQ_i += dS_i K_j for the block pair (c - 1, c), A = the pair's
+                // dS^T tiles in shared memory (M = 2 x 64 rows, K = 128 keys); then the pass's / pair's commits
+                auto post_dq = [&]() {
+                    const int j = j_post, c = c_post;
+                    const int pc = pc0 + j, st = pc & 1;
+                    const bool regular = c < p.n_reg;
+                    const bool with_dq = regular && (c & 1) != 0;
+                    if (with_dq && c == 1 && j == 0 && n > 0) mbar_wait(dq_empty, (n - 1) & 1);  // dQ of the previous pair was read
+                    if (leader) {
+                        if (with_dq) {
                             const uint64_t ads = aS0 + uint64_t((rb_post - 1) & 3) * kTileOff;
                             const uint64_t bk = bK0 + st * kTileOff;
                             const uint32_t accq = j > 0 ? 1u : 0u;
                             const uint32_t tq = tdQ + (c >> 1) * 64;
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                umma_f16_ts(tdV, tS + k * 8, bdo + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
-                                umma_f16_ts(tdK, tdP + k * 8, bq + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
-                                if (with_dq) {
-                                    umma_f16(tq, ads + 128 * (2 * k), bk + 128 * (2 * k), idesc_tt, accq | uint32_t(k > 0));
-                                    umma_f16(tq, ads + 128 * (2 * k + 1), bk + 128 * (2 * k + 1), idesc_tt, 1u);
-                                }
-                            }
-                        } else {
-                            for (int k = 0; k < (p.tail_w >> 4); k++) umma_f16_ts(tdV, tS + k * 8, bdo + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
-                            for (int k = 0; k < (p.tail_w >> 4); k++) umma_f16_ts(tdK, tdP + k * 8, bq + 128 * k, idesc_mn, acc0 | uint32_t(k > 0));
+                            for (int k = 0; k < 8; k++)
+                                umma_f16(tq, ads + 128 * k, bk + 128 * k, idesc_tt, accq | uint32_t(k > 0));
                         }
-                        SN_TRACE(true, 0, 4, gb);                               // post MMAs issued
+                        SN_TRACE(true, 0, 4, gb_post);                          // post MMAs issued
                         if (c == nblk - 1) {
                             umma_commit(acc_full);
                             umma_commit(&kv_empty[st]);
@@ -897,58 +1032,16 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                 pre();
                 if (nb_bh > 1) pre();
                 for (int lb = 0; lb < nb_bh; lb++) {
-                    post();
+                    post_vk();
+#ifdef SN_NO_REORDER
+                    post_dq();
                     if (lb + 2 < nb_bh) pre();
+#else
+                    if (lb + 2 < nb_bh) pre();
+                    post_dq();
+#endif
                 }
             }
-        }
-    } else if (warp == 2 + kSnBwdMathWarps + kSnBwdStatWarps) {
-        // ================================ store warp ================================
-        // one lane: waits until the 16 math warps have parked an epilogue's tiles, hands them to the TMA engine and
-        // releases the tiles once they have been read.  Rows >= N of a box are clipped by the tensor map.
-        // While the dQ tiles are parked the whole warp also sums their columns — the q part of the fused to_qkv bias
-        // gradient (lane l owns columns 2l, 2l + 1; rows >= N are exact zeros) — kept in registers for the whole kernel
-        // (the host sizes the grid so that a CTA stays on one head) and flushed once.
-        const int q_tiles = p.n_reg >> 1;
-        float cq0 = 0.f, cq1 = 0.f;
-        const bool do_cs = p.dbias != nullptr;
-        int pc = 0;
-        for (int n = 0; n < n_local; n++) {
-            const int bh = blockIdx.x + n * gridDim.x;
-            const int b = bh / p.H, h = bh % p.H;
-            if (lane == 0) {
-                for (int j = 0; j < p.n_pass; j++, pc++) {
-                    const bool last = j == p.n_pass - 1;
-                    const uint8_t* src = sdS + (last ? 0 : 2 * kSnTile);
-                    if (last) mbar_wait(&sg_full[0], n & 1); else mbar_wait(&sg_full[1], pc & 1);
-                    tma_store_3d(&tm_dqkv128, src, 2 * p.D + h * 64, j * 128, b);
-                    tma_store_3d(&tm_dqkv128, src + kSnTile, p.D + h * 64, j * 128, b);
-                    tma_store_commit();
-                    tma_store_wait_read();
-                    mbar_arrive(&sg_free[last ? 0 : 1]);
-                }
-                mbar_wait(&sg_full[1], (pc - 1) & 1);                      // the dQ tiles: hi event of the last pass
-                for (int t = 0; t < q_tiles; t++) tma_store_3d(&tm_dqkv128, sdS + (2 + t) * kSnTile, h * 64, t * 128, b);
-                tma_store_commit();
-            }
-            __syncwarp();
-            if (do_cs) {
-                const uint8_t* tile = sdS + 2 * kSnTile;
-#pragma unroll 8
-                for (int r = 0; r < q_tiles * 128; r++) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(
-                        tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4));
-                    cq0 += f.x; cq1 += f.y;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) { tma_store_wait_read(); mbar_arrive(&sg_free[1]); }
-        }
-        if (lane == 0) tma_store_wait_all();
-        if (do_cs && n_local > 0) {
-            const int h = blockIdx.x % p.H;
-            atomicAdd(p.dbias + h * 64 + 2 * lane, cq0);
-            atomicAdd(p.dbias + h * 64 + 2 * lane + 1, cq1);
         }
     } else if (warp >= 2 + kSnBwdMathWarps) {
         // ================================ statistics warps ================================
@@ -1054,6 +1147,115 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             uint8_t* row = tile + lr * 128;
             *reinterpret_cast<uint4*>(row + (((2 * slice) ^ (lr & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(row + (((2 * slice + 1) ^ (lr & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+        };
+        // ---- odd keys (p.n_odd = w > 0): keys 256 .. 256 + w - 1 against every query row, by the math warps with warp-level
+        // MMAs, from the Q / dO rows resident in shared memory.  Runs after the last block of the pair's last pass, while
+        // its tcgen05 MMAs drain.  (The same sums as FMA loops on the CUDA cores cost 6 000 cycles per pair.)
+        //   A  s = q_row . k_u, dP = dO_row . v_u -> P, dS (fp32, shared memory): a warp per 16 rows
+        //   B  dV_u = sum_rows P dO_row, dK_u = sum_rows dS q_row: warp = (matrix, 8 columns)
+        //   C  dV_u / dK_u rows to global memory;  D (pair epilogue): dQ_row += dS k_u before the rows are parked or, for
+        //      rows >= 256, when their shared-memory accumulators are flushed
+        auto odd_phase = [&](int n, int b, int h, const float* sL, const float* sDelta) {
+            mbar_wait(qdo_full, n & 1);                  // the TMA writes of this pair's Q / dO / odd K, V rows, seen by this thread
+            SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 25, n);
+            {
+                // A: [16 rows x 64] x [64 x 8 keys] per warp and matrix: a warp-level MMA per 16 dims.  The B fragments are
+                // read straight from the TMA's K / V rows (row u of the 16-row box; rows >= N arrive as zeros).
+                const int gq = lane >> 2, tq = lane & 3;
+                for (int rt = idx; 16 * rt < p.N; rt += kSnBwdMathWarps) {
+                    // (one accumulator per 16 dims: eight independent MMAs instead of two chains of four)
+                    float cs4[4][4], cd4[4][4];
+                    const int lrow = 16 * rt + (lane & 7) + ((lane >> 3) & 1) * 8;      // ldmatrix: this lane's row address
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        float (&cs)[4] = cs4[kk];
+                        float (&cd)[4] = cd4[kk];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { cs[i] = 0.f; cd[i] = 0.f; }
+                        const int ch = 2 * kk + (lane >> 4);
+                        uint32_t aq[4], ao[4];
+                        ldmatrix_x4(aq, sQ + lrow * 128 + ((ch ^ (lrow & 7)) << 4));
+                        ldmatrix_x4(ao, sdO + lrow * 128 + ((ch ^ (lrow & 7)) << 4));
+                        const uint32_t off0 = gq * 128 + (((2 * kk) ^ gq) << 4) + 4 * tq;
+                        const uint32_t off1 = gq * 128 + (((2 * kk + 1) ^ gq) << 4) + 4 * tq;
+                        mma_16816(cs, aq, *reinterpret_cast<const uint32_t*>(sKo + off0), *reinterpret_cast<const uint32_t*>(sKo + off1));
+                        mma_16816(cd, ao, *reinterpret_cast<const uint32_t*>(sVo + off0), *reinterpret_cast<const uint32_t*>(sVo + off1));
+                    }
+                    float cs[4], cd[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        cs[i] = (cs4[0][i] + cs4[1][i]) + (cs4[2][i] + cs4[3][i]);
+                        cd[i] = (cd4[0][i] + cd4[1][i]) + (cd4[2][i] + cd4[3][i]);
+                    }
+                    // this lane: rows 16 rt + gq and + 8, keys u = 2 tq and 2 tq + 1
+#pragma unroll
+                    for (int hr = 0; hr < 2; hr++) {
+                        const int r = 16 * rt + gq + 8 * hr;
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int u = 2 * tq + e;
+                            if (u < p.n_odd && r < p.N) {
+                                const float pe = ex2_fast(fmaf(cs[2 * hr + e], p.scale_log2, -sL[r]));
+                                po[u * kSnMaxKeys + r] = pe;
+                                dso[u * kSnMaxKeys + r] = pe * (cd[2 * hr + e] - sDelta[r]) * p.scale;
+                            }
+                        }
+                    }
+                }
+            }
+            // k_u as fp32 for D (the rank-1 dQ updates of the pair epilogue), while the other warps finish A
+            for (int i = mt; i < p.n_odd * 64; i += kSnBwdMathThreads) {
+                const int u = i >> 6, d = i & 63;
+                kof[u * 64 + d] = __half2float(*reinterpret_cast<const __half*>(sKo + u * 128 + (((d >> 3) ^ u) << 4) + (d & 7) * 2));
+            }
+            named_bar_sync(1, kSnBwdMathThreads);
+            SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 26, n);
+            {
+                // B: [16 keys x 272 rows] x [272 x 8 columns] per warp = (matrix, 8-column chunk): one warp-level MMA per 16
+                // rows.  A = P / dS of the odd keys (fp16 like the tensor-core passes; keys >= w and rows >= N are zeros),
+                // B = the dO / Q rows through a transposing ldmatrix.
+                const int m = idx >> 3, cc = idx & 7;                          // m = 0: dV_u (P, dO); 1: dK_u (dS, Q)
+                const uint8_t* rows = m ? sQ : sdO;
+                const float* wgt = (m ? dso : po) + (lane >> 2) * kSnMaxKeys;
+                const bool has = (lane >> 2) < p.n_odd;
+                const int tq = lane & 3;
+                // 17 steps over the 272 resident rows (zeros beyond N), four independent accumulators
+                float acc4[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) acc4[a][i] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < kSnMaxKeys / 16; ks++) {
+                    float (&acc)[4] = acc4[ks & 3];
+                    uint32_t af[4] = {0u, 0u, 0u, 0u};
+                    if (has) {
+                        const float2 w0 = *reinterpret_cast<const float2*>(wgt + 16 * ks + 2 * tq);
+                        const float2 w1 = *reinterpret_cast<const float2*>(wgt + 16 * ks + 8 + 2 * tq);
+                        af[0] = pack_h2_rn(w0.x, w0.y); af[2] = pack_h2_rn(w1.x, w1.y);
+                    }
+                    const int r = 16 * ks + (lane & 15);                        // ldmatrix.x2: lanes 0..15 give the row addresses
+                    uint32_t b0, b1;
+                    ldmatrix_x2_trans(b0, b1, rows + r * 128 + ((cc ^ (r & 7)) << 4));
+                    mma_16816(acc, af, b0, b1);
+                }
+                if (has) {
+                    float* dst = ored + (2 * (lane >> 2) + m) * 64 + cc * 8 + 2 * tq;
+                    dst[0] = (acc4[0][0] + acc4[1][0]) + (acc4[2][0] + acc4[3][0]);
+                    dst[1] = (acc4[0][1] + acc4[1][1]) + (acc4[2][1] + acc4[3][1]);
+                }
+            }
+            named_bar_sync(1, kSnBwdMathThreads);
+            SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 27, n);
+            if (mt == 0) mbar_arrive(qdo_empty);         // Q, dO and the odd K / V rows are no longer read by the CUDA cores
+            for (int i = mt; i < p.n_odd * 64; i += kSnBwdMathThreads) {
+                const int u = i >> 6, m = (i >> 5) & 1, d2 = (i & 31) * 2;
+                float* src = ored + (2 * u + m) * 64 + d2;
+                const float a = src[0], c = src[1];
+                amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(c)));
+                *reinterpret_cast<uint32_t*>(p.dqkv + (int64_t(b) * p.N + 256 + u) * p.ld_dqkv + (m == 0 ? 2 : 1) * p.D + h * 64 + d2) =
+                    pack_h2_satf(a, c);
+            }
         };
         // Staging events handed to the store warp (lo / hi tiles): has this warp seen the latest one released?  Checked
         // before anything is written to the dS^T ring or to a staging tile; a warp is never more than one event behind
@@ -1172,6 +1374,10 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     if (lane == 0) mbar_arrive(&pds_full[g]);
                     SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 7, gb);         // P^T / dS^T written
                 }
+                if (p.n_odd > 0 && j == p.n_pass - 1) {
+                    odd_phase(n, b, h, sL, sDelta);
+                    SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 24, n);         // odd keys done
+                }
                 // ---- pass epilogue: every warp stores its 16-column slice of dV_j and of dK_j
                 SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 8, pc);
                 mbar_wait(acc_full, pc & 1);
@@ -1214,6 +1420,15 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(dq_empty);
+                for (int u = 0; u < p.n_odd; u++) {                   // dQ_row += dS[row, 256 + u] k_u
+                    const float d0 = dso[u * kSnMaxKeys + lr], d1 = dso[u * kSnMaxKeys + 128 + lr];
+                    const float* kk = kof + u * 64 + 16 * slice;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        va[i] = __float_as_uint(fmaf(d0, kk[i], __uint_as_float(va[i])));
+                        vb[i] = __float_as_uint(fmaf(d1, kk[i], __uint_as_float(vb[i])));
+                    }
+                }
                 if (pend_hi) { mbar_wait(&sg_free[1], (pc_last - 1) & 1); pend_hi = false; }
                 park_slice(va, sdS + 2 * kSnTile);
                 if (p.n_reg > 2) park_slice(vb, sdS + 3 * kSnTile);
@@ -1228,6 +1443,11 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                 named_bar_sync(1, kSnBwdMathThreads);
                 for (int i = mt; i < (p.N - 256) * 32; i += kSnBwdMathThreads) {
                     const int r = i >> 5, l2 = i & 31;
+                    for (int u = 0; u < p.n_odd; u++) {                 // the corner: odd keys against rows >= 256
+                        const float de = dso[u * kSnMaxKeys + 256 + r];
+                        sdQt[r * 64 + 2 * l2] = fmaf(de, kof[u * 64 + 2 * l2], sdQt[r * 64 + 2 * l2]);
+                        sdQt[r * 64 + 2 * l2 + 1] = fmaf(de, kof[u * 64 + 2 * l2 + 1], sdQt[r * 64 + 2 * l2 + 1]);
+                    }
                     amax = fmaxf(amax, fmaxf(fabsf(sdQt[r * 64 + 2 * l2]), fabsf(sdQt[r * 64 + 2 * l2 + 1])));
                     const uint32_t pk = pack_h2_satf(sdQt[r * 64 + 2 * l2], sdQt[r * 64 + 2 * l2 + 1]);
                     *reinterpret_cast<uint32_t*>(p.dqkv + (int64_t(b) * p.N + 256 + r) * p.ld_dqkv + h * 64 + 2 * l2) = pk;
@@ -1321,7 +1541,12 @@ int mv_attention_bwd_sn(const void* qkv, const void* o, const void* d_o, const f
     SnBwdDev p;
     p.trace = g_sn_trace;
     p.B = B; p.H = H; p.N = N; p.D = D;
-    p.n_pass = (N + 127) / 128;
+#ifdef SN_NO_ODD
+    p.n_odd = 0;
+#else
+    p.n_odd = (N > 256 && N - 256 <= kSnOddMax) ? N - 256 : 0;
+#endif
+    p.n_pass = p.n_odd > 0 ? 2 : (N + 127) / 128;
     p.n_reg = 2 * (((N < 256 ? N : 256) + 127) / 128);
     p.tail_w = N > 256 ? ((N - 256 + 15) & ~15) : 0;
     p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
