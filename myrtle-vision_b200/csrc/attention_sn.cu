@@ -823,13 +823,8 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         //           its buffer is free;
         //   stores  per pair: dV_j / dK_j of every pass, then the dQ tiles — as soon as the 16 math warps have parked them
         //           (rows >= N of a box are clipped by the tensor map); the tiles are released once the TMA engine has
-        //           read them.  While the dQ tiles are parked the warp also sums their columns — the q part of the fused
-        //           to_qkv bias gradient (lane l owns columns 2l, 2l + 1; rows >= N are exact zeros) — in registers for the
-        //           whole kernel (the host sizes the grid so that a CTA stays on one head), 64 rows per turn so that a
-        //           load never waits long behind it.
+        //           read them.
         const int q_tiles = p.n_reg >> 1;
-        const bool do_cs = p.dbias != nullptr;
-        float cq0 = 0.f, cq1 = 0.f;
         int ln = 0, lk = 0;                       // load queue: pair, step (0: K/V of pass 0, 1: Q/dO, k >= 2: K/V of pass k - 1)
         int en = 0, ek = 0, cs_row = -1;          // store queue: pair, event (j < n_pass: pass j, n_pass: dQ), column-sum progress
         while (ln < n_local || en < n_local) {
@@ -897,19 +892,9 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                             tma_store_commit();
                         }
                         progress = true;
-                        cs_row = do_cs ? 0 : q_tiles * 128;
+                        cs_row = q_tiles * 128;
                     }
                 } else {
-                    if (cs_row < q_tiles * 128) {
-                        const uint8_t* tile = sdS + 2 * kSnTile;
-#pragma unroll 8
-                        for (int r = cs_row; r < cs_row + 64; r++) {
-                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(
-                                tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4));
-                            cq0 += f.x; cq1 += f.y;
-                        }
-                        cs_row += 64;
-                    }
                     if (cs_row >= q_tiles * 128) {
                         __syncwarp();
                         if (lane == 0) { tma_store_wait_read(); mbar_arrive(&sg_free[1]); }
@@ -924,11 +909,6 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             if (!progress) __nanosleep(64);
         }
         if (lane == 0) tma_store_wait_all();
-        if (do_cs && n_local > 0) {
-            const int h = blockIdx.x % p.H;
-            atomicAdd(p.dbias + h * 64 + 2 * lane, cq0);
-            atomicAdd(p.dbias + h * 64 + 2 * lane + 1, cq1);
-        }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
         // the whole warp walks the schedule (uniform values live in uniform registers); one elected lane issues
@@ -1284,9 +1264,12 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     mbar_wait(&sdp_full[g], (gb >> 1) & 1);
                     SN_TRACE(quad == 0 && lane == 0 && half == 0, 1 + g, 6, gb);         // S^T / dP^T ready
                     tc_fence_after();
+                    // only the pair of ring slots this block writes: the dQ tiles stay parked in slots 2, 3 for the column
+                    // sums well into the next pair, whose first blocks write slots 0, 1
+                    const bool slot_hi = (((j * p.n_reg + c) & 3) >> 1) != 0;
                     auto staging_released = [&]() {
-                        if (pend_lo) { mbar_wait(&sg_free[0], (n - 1) & 1); pend_lo = false; }
-                        if (pend_hi) { mbar_wait(&sg_free[1], (pc - 1) & 1); pend_hi = false; }
+                        if (!slot_hi && pend_lo) { mbar_wait(&sg_free[0], (n - 1) & 1); pend_lo = false; }
+                        if (slot_hi && pend_hi) { mbar_wait(&sg_free[1], (pc - 1) & 1); pend_hi = false; }
                     };
                     if (warp_live) {
                         uint8_t* ds_row = sdS + ((j * p.n_reg + c) & 3) * kSnTile + lr * 128;
@@ -1432,6 +1415,21 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                 if (pend_hi) { mbar_wait(&sg_free[1], (pc_last - 1) & 1); pend_hi = false; }
                 park_slice(va, sdS + 2 * kSnTile);
                 if (p.n_reg > 2) park_slice(vb, sdS + 3 * kSnTile);
+                if (do_cs) {
+                    // q part of the fused to_qkv bias gradient: column sums of the parked tiles, 16 rows per warp, lane l
+                    // owns columns 2l, 2l + 1 (rows >= N are exact zeros).  (One warp doing all 256 rows kept the tiles
+                    // parked for 5 000 cycles and stalled the next pair's blocks that write these ring slots.)
+                    named_bar_sync(2, kSnBwdMathThreads);
+                    const uint8_t* tile = sdS + 2 * kSnTile;
+                    if (16 * idx < (p.n_reg >> 1) * 128) {
+#pragma unroll
+                        for (int r = 16 * idx; r < 16 * idx + 16; r++) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(
+                                tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4));
+                            cs_t0 += f.x; cs_t1 += f.y;
+                        }
+                    }
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sg_full[1]);
@@ -1461,9 +1459,16 @@ attn_bwd_sn_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         raise_overflow(p.ovf, amax);
         if (do_cs && n_local > 0) {
             const int h = blockIdx.x % p.H;
-            if (cs_t0 != 0.f || cs_t1 != 0.f) {
-                atomicAdd(p.dbias + h * 64 + 2 * lane, cs_t0);
-                atomicAdd(p.dbias + h * 64 + 2 * lane + 1, cs_t1);
+            // the 16 warps' sums meet in shared memory (the dQ tail accumulators are idle now), one global add per column
+            named_bar_sync(1, kSnBwdMathThreads);
+            if (idx == 0) { sdQt[2 * lane] = 0.f; sdQt[2 * lane + 1] = 0.f; }
+            named_bar_sync(1, kSnBwdMathThreads);
+            atomicAdd(&sdQt[2 * lane], cs_t0);
+            atomicAdd(&sdQt[2 * lane + 1], cs_t1);
+            named_bar_sync(1, kSnBwdMathThreads);
+            if (idx == 0) {
+                atomicAdd(p.dbias + h * 64 + 2 * lane, sdQt[2 * lane]);
+                atomicAdd(p.dbias + h * 64 + 2 * lane + 1, sdQt[2 * lane + 1]);
             }
         }
     }

@@ -15,11 +15,12 @@ torch.manual_seed(0)
 qkv = torch.randn(B * N, 3 * D, device="cuda").half()
 do = torch.randn(B * N, D, device="cuda").half()
 out, lse = mv.attention_fwd(qkv, B, H, N, q_out=(5, 10))
+dbias = torch.zeros(3 * D, device="cuda") if os.environ.get("MV_TRACE_DBIAS") else None     # the fused to_qkv bias gradient, as in the step
 for _ in range(2):
-    mv.attention_bwd(qkv, out, do, lse, B, H, N)
+    mv.attention_bwd(qkv, out, do, lse, B, H, N, dbias=dbias)
 buf = torch.zeros(3 * 3072, dtype=torch.int64, device="cuda")
 mv.lib().mv_debug_set_attn_trace(ctypes.c_void_p(buf.data_ptr()))
-(mv.attention_fwd(qkv, B, H, N, q_out=(5, 10)) if "fwd" in sys.argv else mv.attention_bwd(qkv, out, do, lse, B, H, N))
+(mv.attention_fwd(qkv, B, H, N, q_out=(5, 10)) if "fwd" in sys.argv else mv.attention_bwd(qkv, out, do, lse, B, H, N, dbias=dbias))
 torch.cuda.synchronize()
 mv.lib().mv_debug_set_attn_trace(None)
 t = buf.cpu().view(3, 1024, 3)
