@@ -75,6 +75,27 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, ui
     return 0;
 }
 
+// un-swizzled 2-D boxes (epilogue operands read row by row by the CUDA cores)
+int make_tmap_2d_plain(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint64_t cols,
+                       uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return 1;
+    int esz;
+    CUtensorMapDataType dt = tmap_dtype(dtype, &esz);
+    MV_CHECK(reinterpret_cast<uintptr_t>(ptr) % 16 == 0, "TMA: base pointer not 16-byte aligned");
+    MV_CHECK((ld * esz) % 16 == 0, "TMA: row pitch %llu B not a multiple of 16", (unsigned long long)(ld * esz));
+    MV_CHECK((box_cols * esz) % 16 == 0, "TMA: box inner extent must be a multiple of 16 B");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * esz};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d, plain) failed with %d", int(r));
+    return 0;
+}
+
 int make_tmap_3d(CUtensorMap* map, const void* ptr, int dtype, uint64_t d0, uint64_t d1,
                  uint64_t d2, uint64_t stride1, uint64_t stride2, uint32_t box0, uint32_t box1,
                  uint32_t box2) {

@@ -496,13 +496,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // other epilogue runs faster on 12 spill-free ones (measured per shape, gpurun_out/probe_gemm2*.log).
 constexpr int kStgPitch = 36;                                  // floats per staged row: 32 + 4 pad
 constexpr int kStgBytesPerWarp = 32 * kStgPitch * 4;           // 4608
-template <int BN, int EW> struct Gemm2Cfg {
+// AUX: the gelu' epilogue's second operand (aux, fp16 [M, N]) arrives by TMA, one 32 x 32 chunk per epilogue warp, requested
+// by that warp a chunk ahead (kAuxChunkBytes each): loaded with LDG just before use, its latency was a quarter of all stall
+// samples of that kernel (ncu, r2_gemm_dgelu), and fetching it earlier into registers spills.
+constexpr int kAuxChunkBytes = 32 * 64;
+template <int BN, int EW, bool AUX = false> struct Gemm2Cfg {
     static constexpr int kThreads = 64 + 32 * EW;
     static constexpr int kBHalfBytes = (BN / 2) * 128;
     static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
     static constexpr int kStagingBytes = EW * kStgBytesPerWarp;
-    static constexpr int kStages = (232448 - kStagingBytes - 1024 - 256) / kStageBytes;
-    static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + 256;
+    static constexpr int kAuxBytes = AUX ? EW * kAuxChunkBytes : 0;
+    static constexpr int kBarBytes = 512;
+    static constexpr int kStages = (232448 - kStagingBytes - kAuxBytes - 1024 - kBarBytes) / kStageBytes;
+    static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kAuxBytes + 1024 + kBarBytes;
     static constexpr int kTmemCols = 2 * BN <= 256 ? 256 : 512;
 };
 
@@ -583,7 +589,7 @@ __device__ __forceinline__ void stage_chunk(const EpiWarp& w, uint32_t taddr, ui
 // loop is a few instructions per 4 outputs.  kRes: 0 none, 1 residual[m, n], 2 residual[m % rows_per_img, n].
 template <int kOut, int kEpi, int kRes, int kQO, int kQR, bool kAcc, bool kCS = false>
 __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, uint32_t taddr, uint32_t release,
-                                          int mrow0, int nc0) {
+                                          int mrow0, int nc0, const uint2* aux_pre = nullptr) {
     const int n = nc0 + w.lc;
     const int m_first = mrow0 + w.lr;
     float4 res4[8];
@@ -599,7 +605,8 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
     if (kEpi == MV_EPI_DGELU) {
 #pragma unroll
         for (int it = 0; it < 8; it++)
-            aux2[it] = __ldcs(reinterpret_cast<const uint2*>(p.aux + int64_t(m_first + it * 4) * p.ld_aux + n));
+            aux2[it] = aux_pre != nullptr ? aux_pre[it]
+                                          : __ldcs(reinterpret_cast<const uint2*>(p.aux + int64_t(m_first + it * 4) * p.ld_aux + n));
     }
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!kAcc && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
@@ -734,11 +741,11 @@ __device__ __forceinline__ void epi_chunk_generic(const GemmDev& p, const EpiWar
     __syncwarp();
 }
 
-template <int BN, int EW>
+template <int BN, int EW, bool AUX = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-             const __grid_constant__ GemmDev p) {
-    using Cfg = Gemm2Cfg<BN, EW>;
+             const __grid_constant__ CUtensorMap tmap_aux, const __grid_constant__ GemmDev p) {
+    using Cfg = Gemm2Cfg<BN, EW, AUX>;
     constexpr int kEpi2Warps = EW;
     constexpr int kStages = Cfg::kStages;
     constexpr int kStageBytes = Cfg::kStageBytes;
@@ -754,11 +761,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; offset arithmetic keeps the shared address space
     float* staging = reinterpret_cast<float*>(smem + kStages * kStageBytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + Cfg::kStagingBytes);
+    uint8_t* aux_buf = smem + kStages * kStageBytes + Cfg::kStagingBytes;            // [EW][32 rows][64 B] (AUX)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + Cfg::kStagingBytes + Cfg::kAuxBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* aux_full = tmem_empty + 4;                                             // [EW] (AUX)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -770,6 +779,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         tma_prefetch_desc(&tmap_b);
         for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * kEpi2Warps); }
+        if (AUX) { tma_prefetch_desc(&tmap_aux); for (int e = 0; e < EW; e++) mbar_init(&aux_full[e], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_cg2<Cfg::kTmemCols>(tmem_slot);
@@ -904,6 +914,64 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
             }
         };
+        // AUX: the same walk with this warp's aux chunk requested one chunk ahead (TMA into its 2 KB buffer; the request
+        // for the next chunk — of this tile or of the warp's next tile — goes out as soon as the current one is in registers)
+        [[maybe_unused]] auto walk_aux = [&](auto chunk) {
+            const int wi = warp - 2;
+            uint8_t* abuf = aux_buf + wi * kAuxChunkBytes;
+            uint64_t* abar = &aux_full[wi];
+            uint32_t aphase = 0;
+            constexpr int kStep = kEpi2Warps / 4;
+            auto request = [&](int u, int c) {
+                const int tile = u / p.splits;
+                const int mrow0 = (tile / p.n_tiles) * 256 + rank * 128 + quad * 32;
+                const int nc0 = (tile % p.n_tiles) * BN + c * 32;
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(abar, kAuxChunkBytes);
+                    tma_load_2d(abuf, &tmap_aux, abar, nc0, mrow0);
+                }
+            };
+            if (unit0 < total_units) request(unit0, cg);
+            for (int u = unit0; u < total_units; u += unit_stride) {
+                const int tile = u / p.splits;
+                const int mrow0 = (tile / p.n_tiles) * 256 + rank * 128 + quad * 32;
+                const int n0 = (tile % p.n_tiles) * BN;
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = cg; c < BN / 32; c += kStep) {
+                    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32;
+                    const uint32_t release = (c + kStep >= BN / 32) ? lead_empty0 + acc * 8 : 0u;
+                    const int nc0 = n0 + c * 32;
+                    const bool fast = mrow0 + 32 <= p.M && nc0 + 32 <= p.N;
+                    mbar_wait(abar, aphase);
+                    aphase ^= 1;
+                    uint2 aux2[8];
+#pragma unroll
+                    for (int it = 0; it < 8; it++)
+                        aux2[it] = *reinterpret_cast<const uint2*>(abuf + (it * 4 + w.lr) * 64 + (lane & 7) * 8);
+                    // the buffer is about to be overwritten through the async proxy: without this fence single 64-byte rows of
+                    // the NEXT chunk's box showed up in these (generic-proxy) reads, a few hundred values per launch
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (c + kStep < BN / 32) request(u, c + kStep);
+                    else if (u + unit_stride < total_units) request(u + unit_stride, cg);
+                    if (fast) chunk(taddr, release, mrow0, nc0, aux2);
+                    else epi_chunk_generic(p, w, taddr, release, mrow0, nc0);
+                }
+                if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
+            }
+        };
+        if constexpr (AUX) {
+            if (p.variant == 11)
+                walk_aux([&](uint32_t taddr, uint32_t release, int mrow0, int nc0, const uint2* aux2) {
+                    epi_chunk<MV_F16, MV_EPI_DGELU, 0, 0, 0, false, true>(p, w, taddr, release, mrow0, nc0, aux2);
+                });
+            else
+                walk_aux([&](uint32_t taddr, uint32_t release, int mrow0, int nc0, const uint2* aux2) {
+                    epi_chunk<MV_F16, MV_EPI_DGELU, 0, 0, 0, false>(p, w, taddr, release, mrow0, nc0, aux2);
+                });
+        } else {
 #define MV_EPI_CASE(id, ...)                                                                                   \
     case id:                                                                                                   \
         walk([&](uint32_t taddr, uint32_t release, int mrow0, int nc0) {                                       \
@@ -931,6 +999,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 break;
         }
 #undef MV_EPI_CASE
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -941,15 +1010,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
 }
 
-template <int BN, int EW>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
-    using Cfg = Gemm2Cfg<BN, EW>;
+template <int BN, int EW, bool AUX = false>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st,
+                        const CUtensorMap* taux = nullptr) {
+    using Cfg = Gemm2Cfg<BN, EW, AUX>;
     static bool attr_done = false;
     if (!attr_done) {
-        MV_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+        MV_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, EW, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
         attr_done = true;
     }
-    gemm2_kernel<BN, EW><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, p);
+    gemm2_kernel<BN, EW, AUX><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, taux != nullptr ? *taux : ta, p);
     return 0;
 }
 
@@ -1051,7 +1121,13 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     int rc;
     // 16 epilogue warps only where 12 would be unbalanced: BN = 256 is 8 chunks over 3 column groups (3 / 3 / 2)
     const bool heavy = (a->epilogue == MV_EPI_GELU || a->epilogue == MV_EPI_DGELU) && BN == 256;
+    // gelu' epilogue on 256-wide tiles with a compile-time variant: its aux operand by TMA, a chunk ahead
+    const bool aux_tma = heavy && BN == 256 && (p.variant == 6 || p.variant == 11) && (a->ld_aux & 7) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0;
+    CUtensorMap taux;
+    if (aux_tma && make_tmap_2d_plain(&taux, a->aux, MV_F16, a->M, a->N, a->ld_aux, 32, 32)) return 1;
     if (BN == 384) rc = launch_gemm2<384, 12>(ta, tb, p, grid, st);
+    else if (aux_tma) rc = launch_gemm2<256, 16, true>(ta, tb, p, grid, st, &taux);
     else if (BN == 256) rc = heavy ? launch_gemm2<256, 16>(ta, tb, p, grid, st) : launch_gemm2<256, 12>(ta, tb, p, grid, st);
     else if (BN == 192) rc = heavy ? launch_gemm2<192, 16>(ta, tb, p, grid, st) : launch_gemm2<192, 12>(ta, tb, p, grid, st);
     else rc = heavy ? launch_gemm2<128, 16>(ta, tb, p, grid, st) : launch_gemm2<128, 12>(ta, tb, p, grid, st);
