@@ -191,9 +191,10 @@ __device__ __forceinline__ void sn_load_kv(uint8_t* dst, const CUtensorMap* m128
 }
 
 // dot product of two 64-element fp16 rows held in 128-byte-swizzled tiles (row index selects the XOR)
+// (rolled: it runs once per row and tile, and the forward kernel's code must stay inside the instruction cache)
 __device__ __forceinline__ float sn_dot64(const uint8_t* tile_a, int ra, const uint8_t* tile_b, int rb) {
     float acc = 0.f;
-#pragma unroll
+#pragma unroll 2
     for (int c = 0; c < 8; c++) {
         const uint4 wa = *reinterpret_cast<const uint4*>(tile_a + ra * 128 + ((c ^ (ra & 7)) << 4));
         const uint4 wb = *reinterpret_cast<const uint4*>(tile_b + rb * 128 + ((c ^ (rb & 7)) << 4));
@@ -221,17 +222,18 @@ __device__ __forceinline__ void sn_tail_row_fwd(const SnFwdDev& p, const uint8_t
         sq[2 * lane] = f.x; sq[2 * lane + 1] = f.y;
     }
     __syncwarp();
+    // rolled loops, scores parked in the scratch row: this runs for one row per (image, head) on its own warps, and
+    // unrolled over nine key groups it was a quarter of the kernel's 120 KB of code (no-instruction stalls: 17 %)
     constexpr int kMaxPerLane = (kSnMaxKeys + 31) / 32;
-    float sc[kMaxPerLane];
     float mx = -INFINITY;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < kMaxPerLane; i++) {
         const int j = lane + 32 * i;
         float acc = -INFINITY;
         if (j < p.N) {
             acc = 0.f;
             const uint8_t* krow = sK + j * 128;
-#pragma unroll
+#pragma unroll 2
             for (int c = 0; c < 8; c++) {
                 const uint4 w = *reinterpret_cast<const uint4*>(krow + ((c ^ (j & 7)) << 4));
                 const __half2* hh = reinterpret_cast<const __half2*>(&w);
@@ -245,17 +247,17 @@ __device__ __forceinline__ void sn_tail_row_fwd(const SnFwdDev& p, const uint8_t
                 acc = fmaf(qb.z, k3.x, acc); acc = fmaf(qb.w, k3.y, acc);
             }
         }
-        sc[i] = acc;
+        if (j < p.Nld) sp[j] = acc;
         mx = fmaxf(mx, acc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     const float m = mx * p.scale_log2;
     float sum = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < kMaxPerLane; i++) {
         const int j = lane + 32 * i;
-        const float e = j < p.N ? ex2_fast(fmaf(sc[i], p.scale_log2, -m)) : 0.f;
+        const float e = j < p.N ? ex2_fast(fmaf(sp[j], p.scale_log2, -m)) : 0.f;       // (this lane wrote sp[j] itself)
         sum += e;
         if (j < p.Nld) sp[j] = e;
     }
@@ -265,6 +267,7 @@ __device__ __forceinline__ void sn_tail_row_fwd(const SnFwdDev& p, const uint8_t
     // o[2l], o[2l+1] = sum_j p_j V[j][2l..2l+1]; V row j: 16-byte chunk (l >> 2) sits at position (l >> 2) ^ (j & 7)
     float o0 = 0.f, o1 = 0.f;
     const int cl = lane >> 2, wi = (lane & 3) * 4;
+#pragma unroll 1
     for (int j0 = 0; j0 < p.Nld; j0 += 8) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -631,7 +634,10 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
                 } else {
                     if (mode == 1) {
 #pragma unroll
-                        for (int i = 0; i < 64; i++) o[i] = fq_half_fast(o[i] * inv);
+                        for (int i = 0; i < 16; i++) {                       // four at a time: one range test, rare path out of line
+                            const float4 q4 = fq_half4_f32(make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv));
+                            o[4 * i] = q4.x; o[4 * i + 1] = q4.y; o[4 * i + 2] = q4.z; o[4 * i + 3] = q4.w;
+                        }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 64; i++) o[i] = fq_apply(o[i] * inv, mode, p.q_out);
