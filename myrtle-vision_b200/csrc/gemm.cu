@@ -499,13 +499,14 @@ constexpr int kStgBytesPerWarp = 32 * kStgPitch * 4;           // 4608
 // AUX: the gelu' epilogue's second operand (aux, fp16 [M, N]) arrives by TMA, one 32 x 32 chunk per epilogue warp, requested
 // by that warp a chunk ahead (kAuxChunkBytes each): loaded with LDG just before use, its latency was a quarter of all stall
 // samples of that kernel (ncu, r2_gemm_dgelu), and fetching it earlier into registers spills.
-constexpr int kAuxChunkBytes = 32 * 64;
-template <int BN, int EW, bool AUX = false> struct Gemm2Cfg {
+// AUX = 2: the same for the fp32 residual of the x + Linear(...) epilogues (32 x 32 fp32 = 4 KB per chunk).
+template <int AUX> struct AuxChunk { static constexpr int kBytes = AUX == 2 ? 32 * 128 : 32 * 64; };
+template <int BN, int EW, int AUX = 0> struct Gemm2Cfg {
     static constexpr int kThreads = 64 + 32 * EW;
     static constexpr int kBHalfBytes = (BN / 2) * 128;
     static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
     static constexpr int kStagingBytes = EW * kStgBytesPerWarp;
-    static constexpr int kAuxBytes = AUX ? EW * kAuxChunkBytes : 0;
+    static constexpr int kAuxBytes = AUX ? EW * AuxChunk<AUX>::kBytes : 0;
     static constexpr int kBarBytes = 512;
     static constexpr int kStages = (232448 - kStagingBytes - kAuxBytes - 1024 - kBarBytes) / kStageBytes;
     static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kAuxBytes + 1024 + kBarBytes;
@@ -589,7 +590,7 @@ __device__ __forceinline__ void stage_chunk(const EpiWarp& w, uint32_t taddr, ui
 // loop is a few instructions per 4 outputs.  kRes: 0 none, 1 residual[m, n], 2 residual[m % rows_per_img, n].
 template <int kOut, int kEpi, int kRes, int kQO, int kQR, bool kAcc, bool kCS = false>
 __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, uint32_t taddr, uint32_t release,
-                                          int mrow0, int nc0, const uint2* aux_pre = nullptr) {
+                                          int mrow0, int nc0, const uint2* aux_pre = nullptr, const float4* res_pre = nullptr) {
     const int n = nc0 + w.lc;
     const int m_first = mrow0 + w.lr;
     float4 res4[8];
@@ -599,7 +600,7 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
         for (int it = 0; it < 8; it++) {
             const int m = m_first + it * 4;
             const int64_t rrow = kRes == 2 ? (m % p.rows_per_img) : m;
-            res4[it] = __ldcs(reinterpret_cast<const float4*>(p.residual + rrow * p.ld_res + n));
+            res4[it] = res_pre != nullptr ? res_pre[it] : __ldcs(reinterpret_cast<const float4*>(p.residual + rrow * p.ld_res + n));
         }
     }
     if (kEpi == MV_EPI_DGELU) {
@@ -741,7 +742,7 @@ __device__ __forceinline__ void epi_chunk_generic(const GemmDev& p, const EpiWar
     __syncwarp();
 }
 
-template <int BN, int EW, bool AUX = false>
+template <int BN, int EW, int AUX = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_aux, const __grid_constant__ GemmDev p) {
@@ -918,6 +919,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         // for the next chunk — of this tile or of the warp's next tile — goes out as soon as the current one is in registers)
         [[maybe_unused]] auto walk_aux = [&](auto chunk) {
             const int wi = warp - 2;
+            constexpr int kAuxChunkBytes = AuxChunk<AUX>::kBytes;
             uint8_t* abuf = aux_buf + wi * kAuxChunkBytes;
             uint64_t* abar = &aux_full[wi];
             uint32_t aphase = 0;
@@ -947,29 +949,41 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     mbar_wait(abar, aphase);
                     aphase ^= 1;
                     uint2 aux2[8];
+                    float4 res4[8];
 #pragma unroll
-                    for (int it = 0; it < 8; it++)
-                        aux2[it] = *reinterpret_cast<const uint2*>(abuf + (it * 4 + w.lr) * 64 + (lane & 7) * 8);
+                    for (int it = 0; it < 8; it++) {
+                        if (AUX == 2) res4[it] = *reinterpret_cast<const float4*>(abuf + (it * 4 + w.lr) * 128 + (lane & 7) * 16);
+                        else aux2[it] = *reinterpret_cast<const uint2*>(abuf + (it * 4 + w.lr) * 64 + (lane & 7) * 8);
+                    }
                     // the buffer is about to be overwritten through the async proxy: without this fence single 64-byte rows of
                     // the NEXT chunk's box showed up in these (generic-proxy) reads, a few hundred values per launch
                     fence_proxy_async();
                     __syncwarp();
                     if (c + kStep < BN / 32) request(u, c + kStep);
                     else if (u + unit_stride < total_units) request(u + unit_stride, cg);
-                    if (fast) chunk(taddr, release, mrow0, nc0, aux2);
+                    if (fast) chunk(taddr, release, mrow0, nc0, aux2, res4);
                     else epi_chunk_generic(p, w, taddr, release, mrow0, nc0);
                 }
                 if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
             }
         };
-        if constexpr (AUX) {
+        if constexpr (AUX == 1) {
             if (p.variant == 11)
-                walk_aux([&](uint32_t taddr, uint32_t release, int mrow0, int nc0, const uint2* aux2) {
+                walk_aux([&](uint32_t taddr, uint32_t release, int mrow0, int nc0, const uint2* aux2, const float4*) {
                     epi_chunk<MV_F16, MV_EPI_DGELU, 0, 0, 0, false, true>(p, w, taddr, release, mrow0, nc0, aux2);
                 });
             else
-                walk_aux([&](uint32_t taddr, uint32_t release, int mrow0, int nc0, const uint2* aux2) {
+                walk_aux([&](uint32_t taddr, uint32_t release, int mrow0, int nc0, const uint2* aux2, const float4*) {
                     epi_chunk<MV_F16, MV_EPI_DGELU, 0, 0, 0, false>(p, w, taddr, release, mrow0, nc0, aux2);
+                });
+        } else if constexpr (AUX == 2) {
+            if (p.variant == 4)
+                walk_aux([&](uint32_t taddr, uint32_t release, int mrow0, int nc0, const uint2*, const float4* res4) {
+                    epi_chunk<MV_F32, MV_EPI_NONE, 1, 1, 1, false>(p, w, taddr, release, mrow0, nc0, nullptr, res4);
+                });
+            else
+                walk_aux([&](uint32_t taddr, uint32_t release, int mrow0, int nc0, const uint2*, const float4* res4) {
+                    epi_chunk<MV_F32, MV_EPI_NONE, 1, 0, 0, false>(p, w, taddr, release, mrow0, nc0, nullptr, res4);
                 });
         } else {
 #define MV_EPI_CASE(id, ...)                                                                                   \
@@ -1010,7 +1024,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
 }
 
-template <int BN, int EW, bool AUX = false>
+template <int BN, int EW, int AUX = 0>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st,
                         const CUtensorMap* taux = nullptr) {
     using Cfg = Gemm2Cfg<BN, EW, AUX>;
@@ -1124,10 +1138,17 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     // gelu' epilogue on 256-wide tiles with a compile-time variant: its aux operand by TMA, a chunk ahead
     const bool aux_tma = heavy && BN == 256 && (p.variant == 6 || p.variant == 11) && (a->ld_aux & 7) == 0 &&
                          (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0;
+    // x + Linear(...) epilogues with a row-for-row fp32 residual on 192-wide tiles (proj at D = 384): likewise, where the
+    // epilogue and not the operand stream bounds the tile (short K: 56.5 -> 46.6 us at K = 384; at K = 1536 the two
+    // operand stages it costs lose more than the prefetch gains, 93.3 -> 96.5 us)
+    const bool res_tma = !heavy && BN == 192 && a->K <= 768 && (p.variant == 3 || p.variant == 4) && (a->ld_res & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;
     CUtensorMap taux;
     if (aux_tma && make_tmap_2d_plain(&taux, a->aux, MV_F16, a->M, a->N, a->ld_aux, 32, 32)) return 1;
+    if (res_tma && make_tmap_2d_plain(&taux, a->residual, MV_F32, a->M, a->N, a->ld_res, 32, 32)) return 1;
     if (BN == 384) rc = launch_gemm2<384, 12>(ta, tb, p, grid, st);
-    else if (aux_tma) rc = launch_gemm2<256, 16, true>(ta, tb, p, grid, st, &taux);
+    else if (aux_tma) rc = launch_gemm2<256, 16, 1>(ta, tb, p, grid, st, &taux);
+    else if (res_tma) rc = launch_gemm2<192, 12, 2>(ta, tb, p, grid, st, &taux);
     else if (BN == 256) rc = heavy ? launch_gemm2<256, 16>(ta, tb, p, grid, st) : launch_gemm2<256, 12>(ta, tb, p, grid, st);
     else if (BN == 192) rc = heavy ? launch_gemm2<192, 16>(ta, tb, p, grid, st) : launch_gemm2<192, 12>(ta, tb, p, grid, st);
     else rc = heavy ? launch_gemm2<128, 16>(ta, tb, p, grid, st) : launch_gemm2<128, 12>(ta, tb, p, grid, st);
