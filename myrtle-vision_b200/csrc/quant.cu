@@ -60,18 +60,45 @@ struct FixedParams {
 // four — element i takes half-word (i & 7) of philox(seed, i >> 3, offset) (include/mv_b200.h, "16-bit stream").  Ten
 // Philox rounds per 4 elements were the bound of the stochastic kernel (0.65 - 0.74 of copy bandwidth); a thread now
 // owns two adjacent 16-byte vectors (32 contiguous bytes) per Philox call.
+// Four values with the random half-words (lo, hi) of two Philox words.  One range test for the group, voted over the
+// warp (`valid`: lanes past the end vote yes): when every magnitude in the warp lies between the format's lowest normal and
+// its largest finite value (unsigned compares of the magnitude bits, so NaN / inf fail it), float_quantize's stochastic
+// rounding is "add the tail bits, clear the tail" — three instructions per value; otherwise every value takes the
+// general path (subnormal shift, saturation), as before.  Same results.  Narrow-range tensors (randn: 4.8 -> 5.8 TB/s into
+// the fp16 container) take the short path; with 15 % of the values below the normal range no warp does, and a test per
+// lane instead of the vote makes those warps run both paths (5.7 -> 4.75 TB/s).
+__device__ __forceinline__ float4 float_quantize_stoch4(float4 v, uint32_t w0, uint32_t w1, int exp_bits, int man_bits,
+                                                        uint32_t lo_bits, uint32_t hi_bits, uint32_t mask, bool valid) {
+    const uint32_t tx = __float_as_uint(v.x), ty = __float_as_uint(v.y), tz = __float_as_uint(v.z), tw = __float_as_uint(v.w);
+    const uint32_t mx = tx & 0x7FFFFFFFu, my = ty & 0x7FFFFFFFu, mz = tz & 0x7FFFFFFFu, mw = tw & 0x7FFFFFFFu;
+    const uint32_t mn = min(min(mx, my), min(mz, mw)), mxx = max(max(mx, my), max(mz, mw));
+    if (__all_sync(0xffffffffu, !valid || (mn >= lo_bits && mxx <= hi_bits))) {
+        return make_float4(__uint_as_float((tx + (w0 & mask)) & ~mask), __uint_as_float((ty + ((w0 >> 16) & mask)) & ~mask),
+                           __uint_as_float((tz + (w1 & mask)) & ~mask), __uint_as_float((tw + ((w1 >> 16) & mask)) & ~mask));
+    }
+    return make_float4(float_quantize_elem<true>(v.x, w0 & 0xFFFFu, exp_bits, man_bits),
+                       float_quantize_elem<true>(v.y, w0 >> 16, exp_bits, man_bits),
+                       float_quantize_elem<true>(v.z, w1 & 0xFFFFu, exp_bits, man_bits),
+                       float_quantize_elem<true>(v.w, w1 >> 16, exp_bits, man_bits));
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(kQThreads)
 quant_vec16_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t n, int exp_bits, int man_bits,
                    uint64_t seed, uint64_t offset) {
     const int64_t n8 = n >> 3;
     constexpr int kU = 4;                                   // 4 x 32 B in flight per thread
+    const uint32_t mask = (1u << (23 - man_bits)) - 1u;
+    const uint32_t lo_bits = uint32_t(127 - ((1 << (exp_bits - 1)) - 2)) << 23;                      // lowest normal
+    const uint32_t hi_bits = (uint32_t((1 << (exp_bits - 1)) - 1 + 127) << 23) | (0x007FFFFFu & ~mask);  // largest finite
     const int64_t stride = int64_t(gridDim.x) * kQThreads * kU;
-    for (int64_t base = int64_t(blockIdx.x) * kQThreads * kU + threadIdx.x; base < n8; base += stride) {
+    // warp-uniform trip count (the lanes of a warp hold consecutive indices): the loop body votes over the whole warp
+    for (int64_t base = int64_t(blockIdx.x) * kQThreads * kU + threadIdx.x; base - (threadIdx.x & 31) < n8; base += stride) {
         float4 v[kU][2];
 #pragma unroll
         for (int j = 0; j < kU; j++) {
             const int64_t i = base + int64_t(j) * kQThreads;
+            v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < n8) {
                 v[j][0] = __ldcs(reinterpret_cast<const float4*>(in) + 2 * i);
                 v[j][1] = __ldcs(reinterpret_cast<const float4*>(in) + 2 * i + 1);
@@ -80,18 +107,14 @@ quant_vec16_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t
 #pragma unroll
         for (int j = 0; j < kU; j++) {
             const int64_t i = base + int64_t(j) * kQThreads;
-            if (i >= n8) continue;
+            const bool valid = i < n8;                      // (the whole warp stays in the loop body: warp vote below)
             const uint4 r = philox4x32_10(seed, uint64_t(i), offset);
             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
             float4 o[2];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                o[h].x = float_quantize_elem<true>(v[j][h].x, w[2 * h] & 0xFFFFu, exp_bits, man_bits);
-                o[h].y = float_quantize_elem<true>(v[j][h].y, w[2 * h] >> 16, exp_bits, man_bits);
-                o[h].z = float_quantize_elem<true>(v[j][h].z, w[2 * h + 1] & 0xFFFFu, exp_bits, man_bits);
-                o[h].w = float_quantize_elem<true>(v[j][h].w, w[2 * h + 1] >> 16, exp_bits, man_bits);
-            }
-            Vec8Store<OutT>::st(out + 8 * i, o[0], o[1]);
+            for (int h = 0; h < 2; h++)
+                o[h] = float_quantize_stoch4(v[j][h], w[2 * h], w[2 * h + 1], exp_bits, man_bits, lo_bits, hi_bits, mask, valid);
+            if (valid) Vec8Store<OutT>::st(out + 8 * i, o[0], o[1]);
         }
     }
 }
