@@ -77,7 +77,7 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, ui
 
 // un-swizzled 2-D boxes (epilogue operands read row by row by the CUDA cores)
 int make_tmap_2d_plain(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint64_t cols,
-                       uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+                       uint64_t ld, uint32_t box_rows, uint32_t box_cols, int swizzle64) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return 1;
     int esz;
@@ -90,7 +90,7 @@ int make_tmap_2d_plain(CUtensorMap* map, const void* ptr, int dtype, uint64_t ro
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d, plain) failed with %d", int(r));
     return 0;

@@ -355,7 +355,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int a_fmt, int b_fmt, int a_ma
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint64_t cols,
                  uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 int make_tmap_2d_plain(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint64_t cols,
-                       uint64_t ld, uint32_t box_rows, uint32_t box_cols);      // same, no swizzle, any 16-byte inner extent
+                       uint64_t ld, uint32_t box_rows, uint32_t box_cols, int swizzle64 = 0);  // same, no / 64-byte swizzle, any 16-byte inner extent
 // 3-D: [d2, d1, d0] with d0 contiguous, strides in elements
 int make_tmap_3d(CUtensorMap* map, const void* ptr, int dtype, uint64_t d0, uint64_t d1,
                  uint64_t d2, uint64_t stride1, uint64_t stride2, uint32_t box0, uint32_t box1,

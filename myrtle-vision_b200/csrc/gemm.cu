@@ -500,7 +500,8 @@ constexpr int kStgBytesPerWarp = 32 * kStgPitch * 4;           // 4608
 // by that warp a chunk ahead (kAuxChunkBytes each): loaded with LDG just before use, its latency was a quarter of all stall
 // samples of that kernel (ncu, r2_gemm_dgelu), and fetching it earlier into registers spills.
 // AUX = 2: the same for the fp32 residual of the x + Linear(...) epilogues (32 x 32 fp32 = 4 KB per chunk).
-template <int AUX> struct AuxChunk { static constexpr int kBytes = AUX == 2 ? 32 * 128 : 32 * 64; };
+// AUX = 3: no extra buffer (fp16 outputs leave by TMA store from the warp's staging area, epi_chunk_tma16).
+template <int AUX> struct AuxChunk { static constexpr int kBytes = AUX == 3 ? 0 : (AUX == 2 ? 32 * 128 : 32 * 64); };
 template <int BN, int EW, int AUX = 0> struct Gemm2Cfg {
     static constexpr int kThreads = 64 + 32 * EW;
     static constexpr int kBHalfBytes = (BN / 2) * 128;
@@ -670,6 +671,54 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
     __syncwarp();                                      // staging is rewritten by the next chunk
 }
 
+// fp16 outputs with no second operand (qkv forward, the plain dgrads): the chunk never takes the fp32 staging round trip.
+// Each thread keeps its accumulator row (thread = row, 32 columns), adds the bias, quantises, packs 64 bytes of fp16 into a
+// [32 rows][64 B] tile (64-byte TMA swizzle: 16-byte chunk c of row r sits at c ^ ((r >> 1) & 3), conflict-free) and one
+// TMA store per chunk writes it out — no LDS, no per-lane global stores.  Two tiles per warp inside its staging area: the
+// store of chunk i - 2 must have been read before chunk i overwrites its tile (bulk-group wait by the issuing lane).
+template <int kQO>
+__device__ __forceinline__ void epi_chunk_tma16(const GemmDev& p, const EpiWarp& w, uint32_t taddr, uint32_t release,
+                                                int mrow0, int nc0, const CUtensorMap* tmap_out, int which) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr, r);
+    tmem_ld_wait();
+    if (release != 0u) {
+        tc_fence_before();
+        __syncwarp();
+        if (w.lane == 0) mbar_arrive_cluster(release);
+    }
+    float amax = 0.f;
+    uint32_t h[16];
+#pragma unroll
+    for (int g4 = 0; g4 < 8; g4++) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc0) + g4);
+        float v[4] = {__uint_as_float(r[4 * g4]) + b4.x, __uint_as_float(r[4 * g4 + 1]) + b4.y,
+                      __uint_as_float(r[4 * g4 + 2]) + b4.z, __uint_as_float(r[4 * g4 + 3]) + b4.w};
+        if (kQO == 1) fq_half4<true>(v);
+        else amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))));
+        const uint2 pk = pack4_f16_sat(v);
+        h[2 * g4] = pk.x; h[2 * g4 + 1] = pk.y;
+    }
+    if (kQO == 0) raise_overflow(p.ovf, amax);
+    if (w.lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the tile's previous store has been read
+    __syncwarp();
+    const uint32_t tile = w.stg_s + which * 2048;
+    const uint32_t row = tile + w.lane * 64;
+    const int sw = (w.lane >> 1) & 3;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((c ^ sw) << 4)), "r"(h[4 * c]), "r"(h[4 * c + 1]),
+                     "r"(h[4 * c + 2]), "r"(h[4 * c + 3]) : "memory");
+    fence_proxy_async();
+    __syncwarp();
+    if (w.lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(tmap_out)), "r"(tile), "r"(nc0), "r"(mrow0) : "memory");
+        tma_store_commit();
+    }
+}
+
 // Split-K accumulation into the TRANSPOSED output, out[n, m] += acc[m, n]: the staged 32 x 32 chunk is read
 // column-wise (lane = column, conflict-free with the 36-float pitch), so every lane adds 4 consecutive m of one
 // output row with one red.add.v4.  Lets a wgrad whose natural output is 384 tall and wide (fc2: [384, 1536]) run
@@ -781,6 +830,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * kEpi2Warps); }
         if (AUX) { tma_prefetch_desc(&tmap_aux); for (int e = 0; e < EW; e++) mbar_init(&aux_full[e], 1); }
+        (void)aux_buf;
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_cg2<Cfg::kTmemCols>(tmem_slot);
@@ -909,7 +959,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     if (p.trace != nullptr && blockIdx.x == 0 && warp == 2) { w.tr = p.trace + 3072 + 3 * (trace_n % 1021); trace_n += 3; }
 #endif
                     if (fast) chunk(taddr, release, mrow0, nc0);
-                    else epi_chunk_generic(p, w, taddr, release, mrow0, nc0);
+                    else {
+                        if constexpr (AUX == 3) {          // the generic path stages through the area the TMA tiles live in
+                            if (lane == 0) tma_store_wait_read();
+                            __syncwarp();
+                        }
+                        epi_chunk_generic(p, w, taddr, release, mrow0, nc0);
+                    }
                 }
                 GEMM_TRACE(lane == 0 && (warp == 2 || warp == 17), warp == 2 ? 1 : 2, 7, u);    // this warp's chunks done
                 if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
@@ -976,6 +1032,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 walk_aux([&](uint32_t taddr, uint32_t release, int mrow0, int nc0, const uint2* aux2, const float4*) {
                     epi_chunk<MV_F16, MV_EPI_DGELU, 0, 0, 0, false>(p, w, taddr, release, mrow0, nc0, aux2);
                 });
+        } else if constexpr (AUX == 3) {
+            // fp16 outputs without a second operand: direct TMA-store epilogue (epi_chunk_tma16), tiles alternate per chunk
+            int which = 0;
+            if (p.variant == 2)
+                walk([&](uint32_t taddr, uint32_t release, int mrow0, int nc0) {
+                    epi_chunk_tma16<1>(p, w, taddr, release, mrow0, nc0, &tmap_aux, which); which ^= 1; });
+            else
+                walk([&](uint32_t taddr, uint32_t release, int mrow0, int nc0) {
+                    epi_chunk_tma16<0>(p, w, taddr, release, mrow0, nc0, &tmap_aux, which); which ^= 1; });
+            if (lane == 0) tma_store_wait_all();
         } else if constexpr (AUX == 2) {
             if (p.variant == 4)
                 walk_aux([&](uint32_t taddr, uint32_t release, int mrow0, int nc0, const uint2*, const float4* res4) {
@@ -1146,7 +1212,12 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     CUtensorMap taux;
     if (aux_tma && make_tmap_2d_plain(&taux, a->aux, MV_F16, a->M, a->N, a->ld_aux, 32, 32)) return 1;
     if (res_tma && make_tmap_2d_plain(&taux, a->residual, MV_F32, a->M, a->N, a->ld_res, 32, 32)) return 1;
+    // plain fp16 outputs (variants 1, 2) on 192- / 128-wide tiles: TMA-store epilogue
+    const bool out_tma = !heavy && (BN == 192 || BN == 128) && (p.variant == 1 || p.variant == 2) && (a->ld_out & 7) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a->out) & 15) == 0;
+    if (out_tma && make_tmap_2d_plain(&taux, a->out, MV_F16, a->M, a->N, a->ld_out, 32, 32, 1)) return 1;
     if (BN == 384) rc = launch_gemm2<384, 12>(ta, tb, p, grid, st);
+    else if (out_tma) rc = BN == 192 ? launch_gemm2<192, 12, 3>(ta, tb, p, grid, st, &taux) : launch_gemm2<128, 12, 3>(ta, tb, p, grid, st, &taux);
     else if (aux_tma) rc = launch_gemm2<256, 16, 1>(ta, tb, p, grid, st, &taux);
     else if (res_tma) rc = launch_gemm2<192, 12, 2>(ta, tb, p, grid, st, &taux);
     else if (BN == 256) rc = heavy ? launch_gemm2<256, 16>(ta, tb, p, grid, st) : launch_gemm2<256, 12>(ta, tb, p, grid, st);
