@@ -64,15 +64,22 @@ struct FixedParams {
 // warp (`valid`: lanes past the end vote yes): when every magnitude in the warp lies between the format's lowest normal and
 // its largest finite value (unsigned compares of the magnitude bits, so NaN / inf fail it), float_quantize's stochastic
 // rounding is "add the tail bits, clear the tail" — three instructions per value; otherwise every value takes the
-// general path (subnormal shift, saturation), as before.  Same results.  Narrow-range tensors (randn: 4.8 -> 5.8 TB/s into
-// the fp16 container) take the short path; with 15 % of the values below the normal range no warp does, and a test per
-// lane instead of the vote makes those warps run both paths (5.7 -> 4.75 TB/s).
+// general path (subnormal shift, saturation), as before.  Same results.  Narrow-range tensors (randn: 4.8 -> 6.3 TB/s into
+// the fp16 container) take the short path; with 15 % of the values below the normal range no warp does (a test per lane
+// instead of the vote makes those warps run both paths, 5.7 -> 4.75 TB/s), and even the vote's range test costs them
+// 15 %: a warp whose last vote failed tests again only every eighth iteration (try_short).
 __device__ __forceinline__ float4 float_quantize_stoch4(float4 v, uint32_t w0, uint32_t w1, int exp_bits, int man_bits,
-                                                        uint32_t lo_bits, uint32_t hi_bits, uint32_t mask, bool valid) {
+                                                        uint32_t lo_bits, uint32_t hi_bits, uint32_t mask, bool valid,
+                                                        bool try_short, bool& all_short) {
     const uint32_t tx = __float_as_uint(v.x), ty = __float_as_uint(v.y), tz = __float_as_uint(v.z), tw = __float_as_uint(v.w);
-    const uint32_t mx = tx & 0x7FFFFFFFu, my = ty & 0x7FFFFFFFu, mz = tz & 0x7FFFFFFFu, mw = tw & 0x7FFFFFFFu;
-    const uint32_t mn = min(min(mx, my), min(mz, mw)), mxx = max(max(mx, my), max(mz, mw));
-    if (__all_sync(0xffffffffu, !valid || (mn >= lo_bits && mxx <= hi_bits))) {
+    bool take = false;
+    if (try_short) {                                    // warp-uniform
+        const uint32_t mx = tx & 0x7FFFFFFFu, my = ty & 0x7FFFFFFFu, mz = tz & 0x7FFFFFFFu, mw = tw & 0x7FFFFFFFu;
+        const uint32_t mn = min(min(mx, my), min(mz, mw)), mxx = max(max(mx, my), max(mz, mw));
+        take = __all_sync(0xffffffffu, !valid || (mn >= lo_bits && mxx <= hi_bits));
+        all_short = all_short && take;
+    }
+    if (take) {
         return make_float4(__uint_as_float((tx + (w0 & mask)) & ~mask), __uint_as_float((ty + ((w0 >> 16) & mask)) & ~mask),
                            __uint_as_float((tz + (w1 & mask)) & ~mask), __uint_as_float((tw + ((w1 >> 16) & mask)) & ~mask));
     }
@@ -93,7 +100,11 @@ quant_vec16_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t
     const uint32_t hi_bits = (uint32_t((1 << (exp_bits - 1)) - 1 + 127) << 23) | (0x007FFFFFu & ~mask);  // largest finite
     const int64_t stride = int64_t(gridDim.x) * kQThreads * kU;
     // warp-uniform trip count (the lanes of a warp hold consecutive indices): the loop body votes over the whole warp
-    for (int64_t base = int64_t(blockIdx.x) * kQThreads * kU + threadIdx.x; base - (threadIdx.x & 31) < n8; base += stride) {
+    bool last_short = true;                                 // did every group of this warp's previous iteration take the short path?
+    int iter = 0;
+    for (int64_t base = int64_t(blockIdx.x) * kQThreads * kU + threadIdx.x; base - (threadIdx.x & 31) < n8; base += stride, iter++) {
+        const bool try_short = last_short || (iter & 7) == 0;
+        bool all_short = try_short;
         float4 v[kU][2];
 #pragma unroll
         for (int j = 0; j < kU; j++) {
@@ -113,9 +124,11 @@ quant_vec16_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t
             float4 o[2];
 #pragma unroll
             for (int h = 0; h < 2; h++)
-                o[h] = float_quantize_stoch4(v[j][h], w[2 * h], w[2 * h + 1], exp_bits, man_bits, lo_bits, hi_bits, mask, valid);
+                o[h] = float_quantize_stoch4(v[j][h], w[2 * h], w[2 * h + 1], exp_bits, man_bits, lo_bits, hi_bits, mask, valid,
+                                             try_short, all_short);
             if (valid) Vec8Store<OutT>::st(out + 8 * i, o[0], o[1]);
         }
+        last_short = all_short;
     }
 }
 // scalar companion (tails, unaligned buffers): the same 16-bit stream
