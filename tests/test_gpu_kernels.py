@@ -109,6 +109,49 @@ def test_gemm_wgrad_384_wide_tiles(T, No, Ki):
     assert relmax(out_t - 1.0, ref.t()) < 1e-5
 
 
+@pytest.mark.parametrize("M", [16384, 8192 + 40])
+def test_gemm_epilogue_operands_and_outputs_by_tma(M):
+    """The epilogue paths that move their operand / result by TMA (gemm2_kernel AUX = 1, 2, 3), at sizes where every
+    cluster walks several tiles (the aux buffers are re-filled while the previous chunk is still in registers: a missing
+    proxy fence showed up as a few hundred wrong values only from M ~ 8k upwards), with a ragged row tail.
+      gelu' dgrad (fp16 aux chunk prefetched), with and without the fused bias gradient;
+      x + Linear at K = 384 (fp32 residual chunk prefetched), FP16_32 and FP16_16 flags;
+      plain fp16 outputs (TMA-store epilogue), with bias / with the (5,10) output quantiser."""
+    import mv_native as mv
+    torch.manual_seed(M)
+    K = 384
+    A = (torch.randn(M, K, device=dev) * 0.5).half()
+    for _ in range(2):                                   # twice: different timing, same answer
+        B = (torch.randn(1536, K, device=dev) * 0.1).half()
+        aux = torch.rand(M, 1536, device=dev).half()
+        want = (A.double() @ B.double().t()) * aux.double()
+        for colsum in (False, True):
+            d = torch.full((M, 1536), float("nan"), device=dev, dtype=torch.float16)
+            cs = torch.zeros(1536, device=dev) if colsum else None
+            mv.gemm(A, B, d, aux=aux, epilogue=mv.EPI_DGELU, colsum=cs)
+            assert relmax(d, want) < 2e-3
+            if colsum:
+                assert relmax(cs, want.sum(0)) < 1e-4        # fp32 sums of the values before their fp16 rounding
+        B = (torch.randn(384, K, device=dev) * 0.1).half()
+        bias = torch.randn(384, device=dev); res = torch.randn(M, 384, device=dev)
+        lin = A.double() @ B.double().t() + bias.double()
+        o = torch.full((M, 384), float("nan"), device=dev)
+        mv.gemm(A, B, o, bias=bias, residual=res)
+        assert relmax(o, lin + res.double()) < 1e-5
+        mv.gemm(A, B, o, bias=bias, residual=res, q_out=(5, 10), q_res=(5, 10))
+        wantq = mv.float_quantize(mv.float_quantize(lin.float(), 5, 10) + res, 5, 10)
+        assert ((o - wantq).abs() > 0).float().mean().item() < 6e-3 and relmax(o, wantq) < 1e-3
+        B = (torch.randn(1152, K, device=dev) * 0.1).half()
+        bias = torch.randn(1152, device=dev)
+        lin = (A.double() @ B.double().t() + bias.double()).float()
+        h = torch.full((M, 1152), float("nan"), device=dev, dtype=torch.float16)
+        mv.gemm(A, B, h, bias=bias)
+        assert relmax(h, lin) < 1e-3 and not torch.isnan(h.float()).any()
+        mv.gemm(A, B, h, bias=bias, q_out=(5, 10))
+        wantq = mv.float_quantize(lin, 5, 10)
+        assert ((h.float() - wantq).abs() > 0).float().mean().item() < 6e-3 and relmax(h, wantq) < 1e-3
+
+
 def test_gemm_rejects_mixed_operand_types():
     import mv_native as mv
     A = torch.zeros(128, 64, device=dev).half(); B = torch.zeros(128, 64, device=dev).bfloat16()
@@ -144,6 +187,7 @@ def test_layernorm_q(D):
 @pytest.mark.parametrize("sn", [1, 0])
 @pytest.mark.parametrize("B,H,N", [(1, 1, 64), (1, 1, 128), (2, 2, 257), (2, 3, 197), (1, 2, 1000), (1, 1, 17),
                                    (2, 1, 130), (2, 1, 131), (2, 1, 256), (1, 2, 272), (1, 1, 273), (40, 6, 257),
+                                   (3, 2, 258), (2, 1, 259),      # odd keys: 2 (warp-MMA phase of the backward), 3 (third pass)
                                    (1, 6, 2501)])      # last: BASELINE config 5 (800 x 800 -> N = 2501), both det settings
 def test_attention_fwd_bwd(B, H, N, sn, request):
     """sn=1: short-sequence kernels (attention_sn.cu, N <= 272); sn=0: the general streaming kernels."""
