@@ -157,6 +157,13 @@ int mv_layernorm_q_bwd(const void* dy, int dy_dtype, int64_t ld_dy, const float*
                        float* dx, int64_t ld_dx, void* dx_f16, int64_t ld_lp, float* dgamma,
                        float* dbeta, float* dbias_prev, int rows, int D, int q_in_exp, int q_in_man,
                        void* stream);
+/* Gradient quantiser (QPyTorch's Quantizer(backward_number=FloatingPoint(exp, man), backward_rounding="nearest"),
+ * qtorch/quant/quant_module.py — an option the reference's NumberFormat.quantizer never sets, utils/quantize.py:47-72;
+ * named by the north star).  Process-wide; (0, 0) = off, the default.  When on, mv_layernorm_q_bwd rounds the
+ * LayerNorm-input gradient (the backward of the QuantStub in front of the LayerNorm) before it adds dres; the
+ * stubs in front of the Linears are the q_out of their dgrad mv_gemm, the weight quantisers a mv_float_quantize over
+ * the accumulated weight gradient (the caller passes them: mv_engine.EncoderEngine.backward). */
+int mv_set_grad_format(int exp_bits, int man_bits);
 /* out[c] += sum_r in[r,c]   (bias gradients); in_dtype MV_F16 or MV_F32 */
 int mv_colsum(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out, void* stream);
 /* img NCHW fp32 -> q(patches) [B*(H/P)*(W/P), P*P*C], (ph,pw,c) minor order (models/vit.py:271-275).

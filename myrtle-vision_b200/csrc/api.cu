@@ -10,6 +10,7 @@ namespace mv {
 static thread_local char g_err[512] = "";
 int64_t g_launches = 0;
 int g_opt_attn_sn = 1;          // short-sequence attention kernels (attention_sn.cu) when N fits
+FloatFmt g_grad_fmt = {0, 0};
 int* g_overflow = nullptr;      // device int registered with mv_set_overflow_flag (NULL: no overflow reporting)
 
 void set_error(const char* fmt, ...) {
@@ -122,6 +123,14 @@ int make_tmap_3d(CUtensorMap* map, const void* ptr, int dtype, uint64_t d0, uint
 extern "C" const char* mv_last_error(void) { return mv::g_err; }
 extern "C" int mv_version(void) { return 101; }
 extern "C" int mv_set_overflow_flag(int* flag_dev) { mv::g_overflow = flag_dev; return 0; }
+extern "C" int mv_set_grad_format(int exp_bits, int man_bits) {
+    if (exp_bits != 0 && (exp_bits < 2 || exp_bits > 8 || man_bits < 0 || man_bits > 23)) {
+        mv::set_error("mv_set_grad_format: unsupported format (%d, %d)", exp_bits, man_bits);
+        return 1;
+    }
+    mv::g_grad_fmt = mv::FloatFmt{exp_bits, exp_bits == 0 ? 0 : man_bits};
+    return 0;
+}
 extern "C" int64_t mv_launch_count(void) { return mv::g_launches; }
 
 extern "C" int mv_set_option(const char* name, int value) {

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include "quant_dev.cuh"
 
 namespace mv {
 
@@ -32,6 +33,7 @@ constexpr int kNumSMs = 148;
 // |value| they convert and raise the flag when it would not fit (>= 65520 rounds past 65504: the container
 // saturates; +-inf included.  NaNs are caught by the final un-scale pass, which tests every parameter gradient).
 extern int* g_overflow;
+extern FloatFmt g_grad_fmt;     // mv_set_grad_format: gradient quantiser of the LayerNorm input stubs ({0, 0} = off)
 constexpr float kHalfOverflow = 65520.0f;
 __device__ __forceinline__ void raise_overflow(int* flag, float amax) {
     if (flag != nullptr && amax >= kHalfOverflow) *flag = 1;

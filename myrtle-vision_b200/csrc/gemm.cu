@@ -88,6 +88,51 @@ __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
     dg = fmaf(x, 0.3989422804f * E, cdf);
 }
 
+// The same arithmetic on two values per instruction (fma/mul/add.f32x2 = FFMA2 / FMUL2 / FADD2 on sm_100a: the FP32 pipe
+// does the same lane work, but the epilogue warps issue half as many instructions — the fc1 + GELU kernel is bound
+// by issue slots, not by the FP32 pipe).  Operation order per lane is that of gelu_both: bit-identical results.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t bc2(float c) { return pk2(c, c); }
+__device__ __forceinline__ void gelu_both2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+    const uint64_t X = pk2(x0, x1);
+    float den0, den1, s0, s1;
+    upk2(fma2(pk2(fabsf(x0), fabsf(x1)), bc2(0.2316418882f), bc2(1.0f)), den0, den1);
+    upk2(mul2(mul2(X, X), bc2(-0.7213475204f)), s0, s1);
+    const uint64_t T = pk2(rcp_fast(den0), rcp_fast(den1));
+    const uint64_t E = pk2(ex2_fast(s0), ex2_fast(s1));
+    uint64_t poly = fma2(T, bc2(0.5307027145f), bc2(-0.7265760135f));
+    poly = fma2(poly, T, bc2(0.7107068705f));
+    poly = fma2(poly, T, bc2(-0.142248368f));
+    poly = fma2(poly, T, bc2(0.127414796f));
+    const uint64_t H = mul2(mul2(poly, T), E);                       // 0.5 erfc(|x| / sqrt 2)
+    float h0, h1, u0, u1;
+    upk2(H, h0, h1);
+    upk2(fma2(H, bc2(-1.0f), bc2(1.0f)), u0, u1);                    // 1 - h (the product is exact: same as 1.0f - h)
+    const uint64_t C = pk2(x0 >= 0.f ? u0 : h0, x1 >= 0.f ? u1 : h1);
+    upk2(mul2(X, C), g0, g1);
+    upk2(fma2(X, mul2(E, bc2(0.3989422804f)), C), d0, d1);
+}
+
 // float_quantize(5,10) of four values at once: one range test for the group, then 2 integer
 // instructions per value.  kSatLater: the caller converts with cvt.rn.satfinite.f16, which performs
 // the clip to +-65504 (the rounded value is exactly representable in fp16 otherwise).
@@ -633,13 +678,24 @@ __device__ __forceinline__ void epi_chunk(const GemmDev& p, const EpiWarp& w, ui
             red_add_v4(reinterpret_cast<float*>(p.out) + int64_t(m) * p.ld_out + n, v[0], v[1], v[2], v[3]);
             continue;
         }
-        v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+        if (kEpi == MV_EPI_GELU) {
+            upk2(add2(pk2(v[0], v[1]), pk2(b4.x, b4.y)), v[0], v[1]);
+            upk2(add2(pk2(v[2], v[3]), pk2(b4.z, b4.w)), v[2], v[3]);
+        } else {
+            v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+        }
         if (kQO == 1) fq_half4<false>(v);
         if (kEpi == MV_EPI_GELU) {
             float d[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) gelu_both(v[j], v[j], d[j]);
+            gelu_both2(v[0], v[1], v[0], v[1], d[0], d[1]);
+            gelu_both2(v[2], v[3], v[2], v[3], d[2], d[3]);
             *reinterpret_cast<uint2*>(p.aux + int64_t(m) * p.ld_aux + n) = pack4_f16_sat(d);
+            if (kQR == 1 && kOut == MV_F16 && !kCS) {
+                // fc2's input quantiser: add half an fp16 ulp, convert with RZ (fq_half4_pack) — 1.5 instructions per value
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + int64_t(m) * p.ld_out + n) =
+                    fq_half4_pack(v[0], v[1], v[2], v[3]);
+                continue;
+            }
         } else if (kEpi == MV_EPI_DGELU) {
             const __half2* hh = reinterpret_cast<const __half2*>(&aux2[it]);
             const float2 f0 = __half22float2(hh[0]), f1 = __half22float2(hh[1]);

@@ -162,14 +162,16 @@ __device__ __forceinline__ float4 unpack_dy(const uint2& u) {
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
-template <int NV, typename DyT>
+// kGQ: the gradient quantiser of the LayerNorm's input stub (QPyTorch backward_number; mv_set_grad_format) rounds the
+// LayerNorm-input gradient before the residual gradient is added to it
+template <int NV, typename DyT, bool kGQ = false>
 __global__ void __launch_bounds__(kLnWarps * 32, 2)
 ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x, int64_t ld_x,
               const float* __restrict__ dres, int64_t ld_dres, const float* __restrict__ gamma,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               float* __restrict__ dx, int64_t ld_dx, __half* __restrict__ dx_lp, int64_t ld_lp,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias_prev,
-              int rows, int D, FloatFmt q_in, int* __restrict__ ovf) {
+              int rows, int D, FloatFmt q_in, int* __restrict__ ovf, FloatFmt q_grad = FloatFmt{0, 0}) {
     // Column sums (dgamma, dbeta, previous bias grad) are kept per warp in shared memory — each
     // lane owns its columns, so plain read-modify-write — which frees ~36 registers per thread for
     // occupancy; the next row's loads are issued before the current row is reduced.
@@ -256,6 +258,10 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, const float* __restrict
                 float4 o;
                 o.x = fmaf(gy[i].x, rstd, fmaf(xh[i].x, cb, cc)); o.y = fmaf(gy[i].y, rstd, fmaf(xh[i].y, cb, cc));
                 o.z = fmaf(gy[i].z, rstd, fmaf(xh[i].z, cb, cc)); o.w = fmaf(gy[i].w, rstd, fmaf(xh[i].w, cb, cc));
+                if (kGQ) {
+                    o.x = fq_nearest(o.x, q_grad); o.y = fq_nearest(o.y, q_grad);
+                    o.z = fq_nearest(o.z, q_grad); o.w = fq_nearest(o.w, q_grad);
+                }
                 if (dres != nullptr) {
                     const float4 r = cur.dres[i];
                     o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -504,7 +510,16 @@ static int launch_ln_bwd(const void* dy, int dy_dtype, int64_t ld_dy, const floa
         cudaFuncSetAttribute(ln_bwd_kernel<NV, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnWarps * 3 * 128 * kLnMaxVec * 4);
         attr_done = true;
     }
-    if (dy_dtype == MV_F16)
+    if (g_grad_fmt.exp_bits != 0) {      // gradient quantiser on (never in the shipped configurations): fp16 dy only
+        static bool attr_gq = false;
+        if (!attr_gq) {
+            cudaFuncSetAttribute(ln_bwd_kernel<NV, __half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnWarps * 3 * 128 * kLnMaxVec * 4);
+            attr_gq = true;
+        }
+        if (dy_dtype != MV_F16) { set_error("mv_layernorm_q_bwd: the gradient quantiser (mv_set_grad_format) takes fp16 dy"); return 1; }
+        ln_bwd_kernel<NV, __half, true><<<grid, kLnWarps * 32, smem, st>>>((const __half*)dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx,
+                                                                          (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in, g_overflow, g_grad_fmt);
+    } else if (dy_dtype == MV_F16)
         ln_bwd_kernel<NV, __half><<<grid, kLnWarps * 32, smem, st>>>((const __half*)dy, ld_dy, x, ld_x, dres, ld_dres, gamma, mean, rstd, dx, ld_dx,
                                                                     (__half*)dx_lp, ld_lp, dgamma, dbeta, dbias_prev, rows, D, q_in, g_overflow);
     else

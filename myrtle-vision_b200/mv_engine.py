@@ -82,6 +82,10 @@ class EncoderEngine:
         # hi*hi + lo*hi + hi*lo — and attention / GELU, which have no quantiser to fuse with in this format,
         # use torch's fp32 ops.  This is the reference's "plumbing" configuration, not a performance path.
         self.exact = plan.inp is None
+        # gradient quantiser of the input / weight quantisers (QPyTorch backward_number; QuantPlan.grad)
+        self.gfmt = getattr(plan, "grad", None)
+        if self.gfmt is not None and self.wide:
+            raise NotImplementedError("a gradient format needs the 16-bit operand path (q_format=FP16_32)")
         if cfg.dim != cfg.heads * 64:
             raise ValueError("dim must equal heads * 64 (dim_head is fixed at 64, models/vit.py:178)")
         self.fmt = plan.inp
@@ -200,6 +204,10 @@ class EncoderEngine:
     def _gradient_scale(self, gx):
         """Power-of-two operand scale S chosen on the device: max |gx| * S lands in [target / 2, target]."""
         mv.set_overflow_flag(self.overflow)        # (cleared by the training forward this backward belongs to)
+        if self.gfmt is not None:
+            # the gradient quantisers must see the gradient as autograd presents it (what QPyTorch's would see under
+            # the reference's GradScaler): no rescaling here, loss scaling is the caller's
+            return self._one()
         amax = torch.linalg.vector_norm(gx, float("inf")).clamp_min(1e-30)          # one reduction, no |gx| temporary
         return torch.exp2(torch.floor(torch.log2(self.scaler_state[1] / amax))).clamp(2.0 ** -60, 2.0 ** 60)
 
@@ -291,30 +299,46 @@ class EncoderEngine:
         last = cfg.depth - 1
         mv.colsum(dx, g[2 + PER_LAYER * last + 11].view(-1))               # fc2 bias of the last block
 
+        # Gradient quantiser G (QuantPlan.grad, normally None): the backward of every QuantStub in front of a Linear is
+        # the q_out of that Linear's dgrad GEMM (before the gelu' multiply for fc2's), of every stub in front of a
+        # LayerNorm a rounding inside mv_layernorm_q_bwd (before the residual gradient is added), of every weight
+        # quantiser a pass over the accumulated weight gradient (before the data-parallel reduction, as autograd
+        # would apply it to the local gradient)
+        gq = self.gfmt
+        mv.set_grad_format(gq)
+
+        def wq_grad(i):
+            if gq is not None:
+                mv.float_quantize(g[i], gq[0], gq[1], out=g[i])
+
         for l in range(last, -1, -1):
             b0 = 2 + PER_LAYER * l
             x, xn1, mean1, rstd1, qkv, att, lse, x1, xn2, mean2, rstd2, u, h = saved["layers"][l]
             # ---- FeedForward
             du = torch.empty(M, Mm, dtype=f16, device=dev)
             # fc1's bias gradient (column sums of du) rides in the epilogue
-            mv.gemm(dx_h, wq[b0 + 10][1], du, aux=u, epilogue=mv.EPI_DGELU, colsum=g[b0 + 9].view(-1))
+            mv.gemm(dx_h, wq[b0 + 10][1], du, aux=u, epilogue=mv.EPI_DGELU, colsum=g[b0 + 9].view(-1), q_out=gq)
             # fc2's [D, 4D] gradient as its transpose h^T dx: 256 x 384 tiles over 4D rows instead of 1.5 padded 256-row tiles
             mv.gemm(h, dx_h, g[b0 + 10], a_major=1, b_major=1, accumulate=True, transpose_out=True)
+            wq_grad(b0 + 10)
             dxn2 = torch.empty(M, D, dtype=f16, device=dev)
-            mv.gemm(du, wq[b0 + 8][1], dxn2, tag="dgrad")
+            mv.gemm(du, wq[b0 + 8][1], dxn2, tag="dgrad", q_out=gq)
             mv.gemm(du, xn2, g[b0 + 8], a_major=1, b_major=1, accumulate=True)
+            wq_grad(b0 + 8)
             del du
             dx1, dx1_h = mv.layernorm_q_bwd(dxn2, x1, prm[b0 + 6], mean2, rstd2, dres=dx, q_in=fmt,
                                             dgamma=g[b0 + 6], dbeta=g[b0 + 7], dbias_prev=g[b0 + 5])
             # ---- Attention
             datt = torch.empty(M, D, dtype=f16, device=dev)
-            mv.gemm(dx1_h, wq[b0 + 4][1], datt, tag="dgrad")
+            mv.gemm(dx1_h, wq[b0 + 4][1], datt, tag="dgrad", q_out=gq)
             mv.gemm(dx1_h, att, g[b0 + 4], a_major=1, b_major=1, accumulate=True)
+            wq_grad(b0 + 4)
             dqkv = mv.attention_bwd(qkv, att, datt, lse, B, H, N, scale=0.125,
                                     dbias=g[b0 + 3].view(-1))          # to_qkv's bias gradient fused
             dxn1 = dxn2      # reuse
-            mv.gemm(dqkv, wq[b0 + 2][1], dxn1, tag="dgrad")
+            mv.gemm(dqkv, wq[b0 + 2][1], dxn1, tag="dgrad", q_out=gq)
             mv.gemm(dqkv, xn1, g[b0 + 2], a_major=1, b_major=1, accumulate=True)
+            wq_grad(b0 + 2)
             prev_bias = g[b0 - 1] if l > 0 else None                       # fc2 bias of block l-1
             dx, dx_h = mv.layernorm_q_bwd(dxn1, x, prm[b0], mean1, rstd1, dres=dx1, q_in=fmt,
                                           dgamma=g[b0], dbeta=g[b0 + 1], dbias_prev=prev_bias,
@@ -327,6 +351,8 @@ class EncoderEngine:
                 self.reducer.reduce_slice(self.gflat[lo:hi], 1.0 / S)
         # ---- patch embedding: dW = dx^T patches (cls rows of `patches` are zero)
         mv.gemm(dx_h, saved["patches"], g[0], a_major=1, b_major=1, accumulate=True)
+        wq_grad(0)
+        mv.set_grad_format(None)
         return self._finish_backward(dx, S, B, N, D)
 
     def _finish_backward(self, dx, S, B, N, D):

@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "csrc", "libmv_b200.so")
+_SO = os.path.join(_HERE, "csrc", os.environ.get("MV_ALT_LIB") or "libmv_b200.so")   # MV_ALT_LIB: an experiment build (tools/build_variant.sh)
 _lib = None
 
 F32, F16, BF16 = 0, 1, 2
@@ -137,6 +137,12 @@ def set_overflow_flag(flag):
         _need_cuda(flag)
         assert flag.dtype == torch.int32 and flag.numel() >= 1
     _check(lib().mv_set_overflow_flag(_ptr(flag)), "mv_set_overflow_flag")
+
+
+def set_grad_format(fmt):
+    """Gradient quantiser of the LayerNorm input stubs (mv_set_grad_format); None = off."""
+    e, m = (0, 0) if fmt is None else fmt
+    _check(lib().mv_set_grad_format(int(e), int(m)), "mv_set_grad_format")
 
 
 def overflow_update(flag, state, shared_slot=None, backoff=1.0 / 16, growth=2.0, growth_interval=2000,

@@ -96,19 +96,23 @@ class DetectionDecoder(nn.Module):
 
 
 class _STEQuant(torch.autograd.Function):
-    """float_quantize (nearest) on the GPU with a straight-through backward."""
+    """float_quantize (nearest) on the GPU; backward straight-through, or float_quantize (nearest) of the incoming
+    gradient with the plan's gradient format (QPyTorch's backward_number; utils.quantize.QuantPlan.grad)."""
 
     @staticmethod
-    def forward(ctx, x, exp, man):
+    def forward(ctx, x, exp, man, gfmt):
+        ctx.gfmt = gfmt
         return mv_native.float_quantize(x.detach(), exp, man).to(x.dtype)
 
     @staticmethod
     def backward(ctx, g):
-        return g, None, None
+        if ctx.gfmt is not None:
+            g = mv_native.float_quantize(g, ctx.gfmt[0], ctx.gfmt[1]).to(g.dtype)
+        return g, None, None, None
 
 
-def _fq(x, fmt):
-    return x if fmt is None else _STEQuant.apply(x, fmt[0], fmt[1])
+def _fq(x, fmt, gfmt=None):
+    return x if fmt is None else _STEQuant.apply(x, fmt[0], fmt[1], gfmt)
 
 
 def _unwrap(module):
@@ -139,6 +143,7 @@ class ViT(nn.Module):
         num_det_tokens: int = 100,
         profile: bool = False,
         q_format: Optional[Union[str, QFormat]] = None,
+        backward_format=None,      # extension: (exp, man) gradient format, see ModelQuantizer.prepare_qat
     ):
         super().__init__()
         assert image_size % patch_size == 0, "Image dimensions must be divisible by the patch size."
@@ -173,7 +178,7 @@ class ViT(nn.Module):
 
         self._engine = None
         self.quantizer = ModelQuantizer(self)
-        self.quantizer.prepare_qat(q_format if q_format is not None else QFormat.FP32)
+        self.quantizer.prepare_qat(q_format if q_format is not None else QFormat.FP32, backward_format=backward_format)
 
     # ------------------------------------------------------------------ plumbing
     def _invalidate_engine(self):
@@ -228,13 +233,13 @@ class ViT(nn.Module):
     def _linear(self, holder, x):
         plan = self.quantizer.plan
         lin = _unwrap(holder)
-        y = F.linear(_fq(x, plan.inp), _fq(lin.weight, plan.inp), lin.bias)
+        y = F.linear(_fq(x, plan.inp, plan.grad), _fq(lin.weight, plan.inp, plan.grad), lin.bias)
         return _fq(y, plan.out)
 
     def _norm(self, holder, x):
         plan = self.quantizer.plan
         ln = _unwrap(holder)
-        y = F.layer_norm(_fq(x, plan.inp), ln.normalized_shape, ln.weight, ln.bias, ln.eps)
+        y = F.layer_norm(_fq(x, plan.inp, plan.grad), ln.normalized_shape, ln.weight, ln.bias, ln.eps)
         return _fq(y, plan.out)
 
     def _decode(self, x, img_hw):

@@ -109,7 +109,9 @@ _FLOAT_FMT = {
 #   out : output observer of Linear / LayerNorm
 #   ff  : FloatFunctional outputs (residual adds, cls/pos cat and add)
 #   gelu: QuantStub in front of GELU
-QuantPlan = namedtuple("QuantPlan", ["inp", "out", "ff", "gelu"])
+#   grad: gradient format of the `inp` quantisers (QPyTorch's backward_number; None = straight-through, the only
+#         thing the reference configures, utils/quantize.py:47-72 — see ModelQuantizer.prepare_qat)
+QuantPlan = namedtuple("QuantPlan", ["inp", "out", "ff", "gelu", "grad"], defaults=[None])
 
 _PLANS = {
     QFormat.FP32: QuantPlan(None, None, None, None),
@@ -153,8 +155,15 @@ class ModelQuantizer:
     def __init__(self, model):
         self.model = model
 
-    def prepare_qat(self, q_format):
-        """Make the model simulate `q_format`."""
+    def prepare_qat(self, q_format, backward_format=None):
+        """Make the model simulate `q_format`.
+
+        backward_format (extension; the reference builds every QPyTorch quantiser without a backward_number):
+        (exp_bits, man_bits) of a float format that every input / weight quantiser of the plan also applies, with
+        nearest rounding, to the gradient flowing back through it — qtorch.quant.Quantizer(forward_number,
+        backward_number) at the QuantStubs in front of Linear / LayerNorm and at the weight fake-quant.  The
+        quantiser sees the gradient as autograd presents it (loss scaling is the caller's, as with the reference's
+        GradScaler): the engine's own power-of-two operand scale is switched off.  FP16_32 only."""
         if hasattr(self, "q_format") and self.q_format != QFormat.FP32:
             raise ValueError("model already quantized")
         if isinstance(q_format, str):
@@ -165,6 +174,14 @@ class ModelQuantizer:
         if q_format not in _PLANS:
             raise NotImplementedError(f"unknown q_format={q_format}")
         plan = _PLANS[q_format]
+        if backward_format is not None:
+            if q_format != QFormat.FP16_32:
+                raise NotImplementedError("backward_format is implemented for q_format=FP16_32 (quantisers in front of "
+                                          "Linear / LayerNorm and on the weights); got %s" % (q_format,))
+            e, m = (int(v) for v in backward_format)
+            if not (2 <= e <= 8 and 0 <= m <= 23):
+                raise ValueError("backward_format must be (exp_bits in 2..8, man_bits in 0..23)")
+            plan = plan._replace(grad=(e, m))
         if q_format != QFormat.FP32:
             self._wrap_modules(plan)
         self.plan = plan

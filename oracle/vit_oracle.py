@@ -59,27 +59,42 @@ def convert_params(P, q_format):
         return {k: (fq(v, fmt) if k.endswith(".weight") else v) for k, v in P.items()}
 
 
+def _fq_np(t, exp, man):
+    a = t.detach().contiguous().float().numpy()
+    if a.size > 4096:
+        o = _qo.float_quantize_nearest_np(a, exp, man)
+    else:
+        o = _qo.float_quantize(a, exp, man, "nearest")
+    return torch.from_numpy(o.reshape(a.shape)).to(t.dtype)
+
+
 class _STEQuant(torch.autograd.Function):
-    """forward: float_quantize nearest on x.data; backward: identity."""
+    """forward: float_quantize nearest on x.data; backward: identity (utils/quantize.py:87-89) — or, with a gradient
+    format (an option the reference never sets: QPyTorch's quantizer(forward_number, backward_number), whose backward
+    is float_quantize(grad_output) with backward_rounding, qtorch/quant/quant_module.py), float_quantize nearest of
+    the incoming gradient."""
 
     @staticmethod
-    def forward(ctx, x, exp, man):
-        a = x.detach().contiguous().float().numpy()
-        if a.size > 4096:
-            o = _qo.float_quantize_nearest_np(a, exp, man)
-        else:
-            o = _qo.float_quantize(a, exp, man, "nearest")
-        return torch.from_numpy(o.reshape(a.shape)).to(x.dtype)
+    def forward(ctx, x, exp, man, gfmt):
+        ctx.gfmt = gfmt
+        return _fq_np(x, exp, man)
 
     @staticmethod
     def backward(ctx, g):
-        return g, None, None
+        if ctx.gfmt is not None:
+            g = _fq_np(g, ctx.gfmt[0], ctx.gfmt[1])
+        return g, None, None, None
 
 
-def fq(x, fmt):
+# gradient format of the input / weight quantisers (the QuantStubs in front of Linear / LayerNorm and the weight
+# fake-quant); None = the reference's straight-through backward.  Set by vit_forward(grad_format=...).
+_GRAD_FMT = None
+
+
+def fq(x, fmt, gfmt=None):
     if fmt is None:
         return x
-    return _STEQuant.apply(x, fmt[0], fmt[1])
+    return _STEQuant.apply(x, fmt[0], fmt[1], gfmt)
 
 
 _WRAPPED = re.compile(r"^(.*)\.1\.(weight|bias)$")
@@ -99,20 +114,23 @@ def canonical_params(state_dict):
 
 def _linear(x, P, name, fin, fout):
     """Sequential(QuantStub, qat.Linear): q(x) @ q(W).T + b, then the output observer."""
-    y = F.linear(fq(x, fin), fq(P[name + ".weight"], fin), P[name + ".bias"])
+    y = F.linear(fq(x, fin, _GRAD_FMT), fq(P[name + ".weight"], fin, _GRAD_FMT), P[name + ".bias"])
     return fq(y, fout)
 
 
 def _layernorm(x, P, name, fin, fout):
-    xq = fq(x, fin)
+    xq = fq(x, fin, _GRAD_FMT)
     y = F.layer_norm(xq, (xq.shape[-1],), P[name + ".weight"], P[name + ".bias"], 1e-5)
     return fq(y, fout)
 
 
 def vit_forward(P, img, *, decoder, patch_size=16, heads, q_format="FP32", num_det_tokens=100,
-                image_size=None, dim_head=64, converted=False):
+                image_size=None, dim_head=64, converted=False, grad_format=None):
     """P: canonical parameter dict.  Returns what ViT.forward returns.  converted=True: the quantiser set that is
-    left after ModelQuantizer.convert() (pass convert_params(P, q_format) as P)."""
+    left after ModelQuantizer.convert() (pass convert_params(P, q_format) as P).  grad_format: (exp, man) applied by
+    the input / weight quantisers to the gradient in backward (None: the reference's straight-through)."""
+    global _GRAD_FMT
+    _GRAD_FMT = grad_format
     fin, fout, ffn, fgelu = (CONVERTED if converted else PLACEMENT)[str(q_format)]
     b, c, h, w = img.shape
     p = patch_size
@@ -216,20 +234,24 @@ def init_params(*, decoder, num_classes, dim, depth, heads, mlp_dim, patch_size=
     return P
 
 
-def train_step(P, img, target, *, decoder, heads, q_format, patch_size=16, num_det_tokens=100):
+def train_step(P, img, target, *, decoder, heads, q_format, patch_size=16, num_det_tokens=100, grad_format=None,
+               loss_scale=1.0):
     """zero_grad -> forward -> CrossEntropy -> backward (classification/train.py:239-264,
     segmentation/train.py:254-275).  Detection uses a fixed surrogate loss (sum of CE on
     pred_logits vs target['labels'] and L1 on pred_boxes vs target['boxes']) because the
     Hungarian criterion is host-side and out of scope.
+    grad_format / loss_scale: the gradient-quantiser option (vit_forward) and the factor the loss is multiplied by
+    before backward (the reference's GradScaler, classification/train.py:259-264); the returned gradients are those
+    of loss * loss_scale.
     Returns (output, loss, grads dict)."""
     params = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
     out = vit_forward(params, img, decoder=decoder, heads=heads, q_format=q_format,
-                      patch_size=patch_size, num_det_tokens=num_det_tokens)
+                      patch_size=patch_size, num_det_tokens=num_det_tokens, grad_format=grad_format)
     if decoder == "detection":
         loss = (F.cross_entropy(out["pred_logits"].flatten(0, 1), target["labels"].flatten())
                 + (out["pred_boxes"] - target["boxes"]).abs().mean())
     else:
         loss = F.cross_entropy(out, target)
-    loss.backward()
+    (loss * loss_scale).backward()
     grads = {k: v.grad for k, v in params.items()}
     return out, loss.detach(), grads

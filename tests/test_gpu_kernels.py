@@ -184,6 +184,48 @@ def test_layernorm_q(D):
     assert relmax(dg, gr.grad) < 1e-5 and relmax(db, br.grad) < 1e-5 and relmax(dp, want.sum(0)) < 1e-5
 
 
+def test_gradient_quantiser_sites_of_the_kernels():
+    """QPyTorch's backward_number at the QuantStubs (mv_set_grad_format / the dgrad GEMM's q_out), kernel by kernel
+    against fp64 references: the fp32 arithmetic is within 1e-6 of them, so apart from a handful of near-tie flips the
+    quantised values must be EQUAL (the model-level test can only bound the flips that fp16 containers add)."""
+    import mv_native as mv
+    torch.manual_seed(5)
+    G = (5, 2)                                                   # E5M2 gradients
+    rows, D = 2000, 384
+    x = torch.randn(rows, D, device=dev) * 2
+    g = 1 + 0.1 * torch.randn(D, device=dev); b = 0.1 * torch.randn(D, device=dev)
+    _, mean, rstd = mv.layernorm_q_fwd(x, g, b, q_in=(5, 10), q_post=(5, 10))
+    xq = mv.float_quantize(x, 5, 10)
+    dy = torch.randn(rows, D, device=dev).half(); dres = torch.randn(rows, D, device=dev)
+    xr = xq.double().requires_grad_(True)
+    F.layer_norm(xr, (D,), g.double(), b.double(), 1e-5).backward(dy.double())
+    dp = torch.zeros(D, device=dev)
+    mv.set_grad_format(G)
+    try:
+        dx, dx16 = mv.layernorm_q_bwd(dy, x, g, mean, rstd, dres=dres, q_in=(5, 10), dbias_prev=dp)
+    finally:
+        mv.set_grad_format(None)
+    want = mv.float_quantize(xr.grad.float(), *G).double() + dres.double()       # the stub rounds BEFORE the residual add
+    assert ((dx.double() - want).abs() > 1e-6 * want.abs().max()).float().mean().item() < 1e-3
+    assert relmax(dp, want.sum(0)) < 1e-3
+    plain, _ = mv.layernorm_q_bwd(dy, x, g, mean, rstd, dres=dres, q_in=(5, 10))  # and the option is off again
+    assert relmax(plain, xr.grad + dres.double()) < 1e-6
+    # dgrad GEMMs: plain (stub in front of qkv / proj / fc1) and gelu' (stub in front of fc2: rounded BEFORE the multiply)
+    M, N, K = 1000, 1536, 384
+    A = (torch.randn(M, K, device=dev) * 0.5).half(); B = (torch.randn(N, K, device=dev) * 0.1).half()
+    aux = torch.rand(M, N, device=dev).half()
+    lin = (A.double() @ B.double().t())
+    q = mv.float_quantize(lin.float(), *G).double()
+    d = torch.empty(M, N, device=dev, dtype=torch.float16)
+    mv.gemm(A, B, d, q_out=G)
+    assert ((d.double() - q).abs() > 0).float().mean().item() < 1e-3
+    cs = torch.zeros(N, device=dev)
+    mv.gemm(A, B, d, aux=aux, epilogue=mv.EPI_DGELU, colsum=cs, q_out=G)
+    want = q * aux.double()
+    assert ((d.double() - want).abs() > 1e-3 * want.abs().max()).float().mean().item() < 1e-3
+    assert relmax(cs, want.sum(0)) < 3e-2          # a flipped rounding moves a column sum by a whole E5M2 step
+
+
 @pytest.mark.parametrize("sn", [1, 0])
 @pytest.mark.parametrize("B,H,N", [(1, 1, 64), (1, 1, 128), (2, 2, 257), (2, 3, 197), (1, 2, 1000), (1, 1, 17),
                                    (2, 1, 130), (2, 1, 131), (2, 1, 256), (1, 2, 272), (1, 1, 273), (40, 6, 257),

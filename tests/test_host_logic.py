@@ -230,3 +230,23 @@ def test_box_average_precision():
                  "boxes": torch.tensor([[30., 30, 35, 35], [0, 0, 10, 10]])}]
     assert abs(box_average_precision(fp_first, gt, 3)["per_class"][0] - 0.5) < 1e-9
     assert abs(float(pairwise_iou(torch.tensor([[0., 0, 10, 10]]), torch.tensor([[0., 0, 10, 8]]))) - 0.8) < 1e-6
+
+
+def test_backward_format_is_an_fp16_32_option_of_prepare_qat():
+    """ModelQuantizer.prepare_qat(q_format, backward_format=(exp, man)): the plan carries the gradient format;
+    formats with more quantiser sites than FP16_32's are refused rather than half-done."""
+    import torch.nn as nn
+    from myrtle_vision.utils.quantize import ModelQuantizer, QFormat
+    net = nn.Sequential(nn.LayerNorm(8), nn.Linear(8, 8))
+    mq = ModelQuantizer(net)
+    mq.prepare_qat(QFormat.FP16_32, backward_format=(5, 10))
+    assert mq.plan.inp == (5, 10) and mq.plan.grad == (5, 10)
+    assert ModelQuantizer(nn.Sequential(nn.Linear(4, 4))).__class__ is ModelQuantizer
+    mq2 = ModelQuantizer(nn.Sequential(nn.Linear(4, 4)))
+    mq2.prepare_qat("FP16_32")
+    assert mq2.plan.grad is None
+    for fmt in ("FP16_16", "TF32", "FP32"):
+        with pytest.raises(NotImplementedError):
+            ModelQuantizer(nn.Sequential(nn.Linear(4, 4))).prepare_qat(fmt, backward_format=(5, 10))
+    with pytest.raises(ValueError):
+        ModelQuantizer(nn.Sequential(nn.Linear(4, 4))).prepare_qat("FP16_32", backward_format=(9, 3))

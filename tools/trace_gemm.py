@@ -9,10 +9,11 @@ import mv_native as mv
 N, K, mode = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 M, dev, h = 65792, "cuda", torch.float16
 torch.manual_seed(0)
-A = (torch.randn(M, K, device=dev) * 0.05).to(h); B = (torch.randn(N, K, device=dev)).to(h)
+A = (torch.randn(M, K, device=dev) * (1.0 if mode == "gelu" else 0.05)).to(h)
+B = (torch.randn(N, K, device=dev) * (0.4 / K ** 0.5 if mode == "gelu" else 1.0)).to(h)      # gelu: u with the benchmark's spread
 out = torch.empty(M, N, device=dev, dtype=torch.float32 if mode == "res" else h)
 aux = (torch.rand(M, N, device=dev)).to(h); res = torch.randn(M, N, device=dev) if mode == "res" else None
-bias = torch.randn(N, device=dev)
+bias = torch.randn(N, device=dev) * (0.02 if mode == "gelu" else 1.0)
 def run():
     if mode == "gelu": mv.gemm(A, B, out, bias=bias, aux=aux, epilogue=mv.EPI_GELU, q_res=(5, 10))
     elif mode == "dgelu": mv.gemm(A, B, out, aux=aux, epilogue=mv.EPI_DGELU)
