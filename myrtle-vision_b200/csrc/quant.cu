@@ -68,6 +68,17 @@ struct FixedParams {
 // the fp16 container) take the short path; with 15 % of the values below the normal range no warp does (a test per lane
 // instead of the vote makes those warps run both paths, 5.7 -> 4.75 TB/s), and even the vote's range test costs them
 // 15 %: a warp whose last vote failed tests again only every eighth iteration (try_short).
+// float_quantize_elem<true> with both of its branches evaluated and selected (no divergence: on a wide-range tensor nearly
+// every warp holds values below the lowest normal binade next to normal ones).  lo_bits / hi_bits / mask as below.
+__device__ __forceinline__ float float_quantize_stoch_bf(float a, uint32_t r, uint32_t lo_bits, uint32_t hi_bits, uint32_t mask) {
+    const uint32_t t = __float_as_uint(a), sign = t & 0x80000000u, rm = r & mask;
+    uint32_t q = (t + rm) & ~mask;                                     // normal range: add the tail bits, clear the tail
+    q = (q & 0x7FFFFFFFu) > hi_bits ? (sign | hi_bits) : q;            // clip_exponent: saturate to +-max
+    const float shift = __uint_as_float(lo_bits | sign);               // below it: shift up to the lowest normal binade,
+    const uint32_t vb = __float_as_uint(__fadd_rn(a, shift));          // round there, shift back
+    const float sub = __fsub_rn(__uint_as_float((vb + rm) & ~mask), shift);
+    return (t & 0x7FFFFFFFu) < lo_bits ? sub : __uint_as_float(q);
+}
 __device__ __forceinline__ float4 float_quantize_stoch4(float4 v, uint32_t w0, uint32_t w1, int exp_bits, int man_bits,
                                                         uint32_t lo_bits, uint32_t hi_bits, uint32_t mask, bool valid,
                                                         bool try_short, bool& all_short) {
@@ -83,10 +94,15 @@ __device__ __forceinline__ float4 float_quantize_stoch4(float4 v, uint32_t w0, u
         return make_float4(__uint_as_float((tx + (w0 & mask)) & ~mask), __uint_as_float((ty + ((w0 >> 16) & mask)) & ~mask),
                            __uint_as_float((tz + (w1 & mask)) & ~mask), __uint_as_float((tw + ((w1 >> 16) & mask)) & ~mask));
     }
+#ifdef MV_QUANT_BRANCHY
     return make_float4(float_quantize_elem<true>(v.x, w0 & 0xFFFFu, exp_bits, man_bits),
                        float_quantize_elem<true>(v.y, w0 >> 16, exp_bits, man_bits),
                        float_quantize_elem<true>(v.z, w1 & 0xFFFFu, exp_bits, man_bits),
                        float_quantize_elem<true>(v.w, w1 >> 16, exp_bits, man_bits));
+#else
+    return make_float4(float_quantize_stoch_bf(v.x, w0, lo_bits, hi_bits, mask), float_quantize_stoch_bf(v.y, w0 >> 16, lo_bits, hi_bits, mask),
+                       float_quantize_stoch_bf(v.z, w1, lo_bits, hi_bits, mask), float_quantize_stoch_bf(v.w, w1 >> 16, lo_bits, hi_bits, mask));
+#endif
 }
 
 template <typename OutT>
@@ -148,6 +164,11 @@ quant_vec_kernel(const float* __restrict__ in, OutT* __restrict__ out, uint8_t* 
                  uint64_t offset) {
     const int64_t n4 = n >> 2;
     const int64_t stride = int64_t(gridDim.x) * kQThreads * kQUnroll;
+    // MODE 0: the format's tail mask, half a step of it, its lowest normal and largest finite magnitudes
+    const int mb = MODE == 0 ? man_bits : 10, eb = MODE == 0 ? exp_bits : 5;
+    const uint32_t tail_mask = (1u << (23 - mb)) - 1u, half_step = (tail_mask + 1u) >> 1;
+    const uint32_t lo_bits = uint32_t(127 - ((1 << (eb - 1)) - 2)) << 23;
+    const uint32_t hi_bits = (uint32_t((1 << (eb - 1)) - 1 + 127) << 23) | (0x007FFFFFu & ~tail_mask);
     for (int64_t base = int64_t(blockIdx.x) * kQThreads * kQUnroll + threadIdx.x; base < n4;
          base += stride) {
         float4 v[kQUnroll];
@@ -164,10 +185,19 @@ quant_vec_kernel(const float* __restrict__ in, OutT* __restrict__ out, uint8_t* 
             if (STOCH) r = philox4x32_10(seed, uint64_t(i), offset);
             float4 o;
             if (MODE == 0) {
+#ifdef MV_QUANT_BRANCHY
                 o.x = float_quantize_elem<STOCH>(v[j].x, r.x, exp_bits, man_bits);
                 o.y = float_quantize_elem<STOCH>(v[j].y, r.y, exp_bits, man_bits);
                 o.z = float_quantize_elem<STOCH>(v[j].z, r.z, exp_bits, man_bits);
                 o.w = float_quantize_elem<STOCH>(v[j].w, r.w, exp_bits, man_bits);
+#else
+                // both branches of float_quantize_elem evaluated and selected (float_quantize_stoch_bf); nearest rounding
+                // adds half a step of the tail where stochastic rounding adds random tail bits
+                o.x = float_quantize_stoch_bf(v[j].x, STOCH ? r.x : half_step, lo_bits, hi_bits, tail_mask);
+                o.y = float_quantize_stoch_bf(v[j].y, STOCH ? r.y : half_step, lo_bits, hi_bits, tail_mask);
+                o.z = float_quantize_stoch_bf(v[j].z, STOCH ? r.z : half_step, lo_bits, hi_bits, tail_mask);
+                o.w = float_quantize_stoch_bf(v[j].w, STOCH ? r.w : half_step, lo_bits, hi_bits, tail_mask);
+#endif
             } else {
                 const bool cl = fp.clamp != 0 && mask == nullptr;
                 float4 u;
