@@ -9,6 +9,7 @@ namespace mv {
 
 static thread_local char g_err[512] = "";
 int64_t g_launches = 0;
+int g_opt_quant_ctas = 8;       // grid cap of the elementwise quant kernels, CTAs per SM
 int g_opt_attn_sn = 1;          // short-sequence attention kernels (attention_sn.cu) when N fits
 FloatFmt g_grad_fmt = {0, 0};
 int* g_overflow = nullptr;      // device int registered with mv_set_overflow_flag (NULL: no overflow reporting)
@@ -124,7 +125,7 @@ extern "C" const char* mv_last_error(void) { return mv::g_err; }
 extern "C" int mv_version(void) { return 101; }
 extern "C" int mv_set_overflow_flag(int* flag_dev) { mv::g_overflow = flag_dev; return 0; }
 extern "C" int mv_set_grad_format(int exp_bits, int man_bits) {
-    if (exp_bits != 0 && (exp_bits < 2 || exp_bits > 8 || man_bits < 0 || man_bits > 23)) {
+    if (exp_bits != 0 && (exp_bits < 2 || exp_bits > 8 || man_bits < 1 || man_bits > 22)) {
         mv::set_error("mv_set_grad_format: unsupported format (%d, %d)", exp_bits, man_bits);
         return 1;
     }
@@ -135,6 +136,7 @@ extern "C" int64_t mv_launch_count(void) { return mv::g_launches; }
 
 extern "C" int mv_set_option(const char* name, int value) {
     if (name != nullptr && strcmp(name, "attn_sn") == 0) { mv::g_opt_attn_sn = value; return 0; }
+    if (name != nullptr && strcmp(name, "quant_ctas") == 0 && value >= 1 && value <= 16) { mv::g_opt_quant_ctas = value; return 0; }
     mv::set_error("mv_set_option: unknown option '%s'", name ? name : "(null)");
     return 1;
 }

@@ -79,7 +79,7 @@ __device__ __forceinline__ float float_quantize_stoch_bf(float a, uint32_t r, ui
     const float sub = __fsub_rn(__uint_as_float((vb + rm) & ~mask), shift);
     return (t & 0x7FFFFFFFu) < lo_bits ? sub : __uint_as_float(q);
 }
-__device__ __forceinline__ float4 float_quantize_stoch4(float4 v, uint32_t w0, uint32_t w1, int exp_bits, int man_bits,
+__device__ __forceinline__ float4 float_quantize_stoch4(float4 v, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, int exp_bits, int man_bits,
                                                         uint32_t lo_bits, uint32_t hi_bits, uint32_t mask, bool valid,
                                                         bool try_short, bool& all_short) {
     const uint32_t tx = __float_as_uint(v.x), ty = __float_as_uint(v.y), tz = __float_as_uint(v.z), tw = __float_as_uint(v.w);
@@ -91,21 +91,17 @@ __device__ __forceinline__ float4 float_quantize_stoch4(float4 v, uint32_t w0, u
         all_short = all_short && take;
     }
     if (take) {
-        return make_float4(__uint_as_float((tx + (w0 & mask)) & ~mask), __uint_as_float((ty + ((w0 >> 16) & mask)) & ~mask),
-                           __uint_as_float((tz + (w1 & mask)) & ~mask), __uint_as_float((tw + ((w1 >> 16) & mask)) & ~mask));
+        return make_float4(__uint_as_float((tx + (r0 & mask)) & ~mask), __uint_as_float((ty + (r1 & mask)) & ~mask),
+                           __uint_as_float((tz + (r2 & mask)) & ~mask), __uint_as_float((tw + (r3 & mask)) & ~mask));
     }
-#ifdef MV_QUANT_BRANCHY
-    return make_float4(float_quantize_elem<true>(v.x, w0 & 0xFFFFu, exp_bits, man_bits),
-                       float_quantize_elem<true>(v.y, w0 >> 16, exp_bits, man_bits),
-                       float_quantize_elem<true>(v.z, w1 & 0xFFFFu, exp_bits, man_bits),
-                       float_quantize_elem<true>(v.w, w1 >> 16, exp_bits, man_bits));
-#else
-    return make_float4(float_quantize_stoch_bf(v.x, w0, lo_bits, hi_bits, mask), float_quantize_stoch_bf(v.y, w0 >> 16, lo_bits, hi_bits, mask),
-                       float_quantize_stoch_bf(v.z, w1, lo_bits, hi_bits, mask), float_quantize_stoch_bf(v.w, w1 >> 16, lo_bits, hi_bits, mask));
-#endif
+    return make_float4(float_quantize_stoch_bf(v.x, r0, lo_bits, hi_bits, mask), float_quantize_stoch_bf(v.y, r1, lo_bits, hi_bits, mask),
+                       float_quantize_stoch_bf(v.z, r2, lo_bits, hi_bits, mask), float_quantize_stoch_bf(v.w, r3, lo_bits, hi_bits, mask));
 }
 
-template <typename OutT>
+// kStoch = false: nearest rounding on the same access pattern (a thread owns 32 contiguous input bytes, four such
+// groups in flight): every tail word is half a step of the tail, no Philox (5.57 -> TB/s on randn against
+// 16 bytes per thread and load in quant_vec_kernel)
+template <typename OutT, bool kStoch = true>
 __global__ void __launch_bounds__(kQThreads)
 quant_vec16_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t n, int exp_bits, int man_bits,
                    uint64_t seed, uint64_t offset) {
@@ -135,13 +131,17 @@ quant_vec16_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t
         for (int j = 0; j < kU; j++) {
             const int64_t i = base + int64_t(j) * kQThreads;
             const bool valid = i < n8;                      // (the whole warp stays in the loop body: warp vote below)
-            const uint4 r = philox4x32_10(seed, uint64_t(i), offset);
+            const uint32_t half_step = (mask + 1u) >> 1;
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (kStoch) r = philox4x32_10(seed, uint64_t(i), offset);
             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
             float4 o[2];
 #pragma unroll
             for (int h = 0; h < 2; h++)
-                o[h] = float_quantize_stoch4(v[j][h], w[2 * h], w[2 * h + 1], exp_bits, man_bits, lo_bits, hi_bits, mask, valid,
-                                             try_short, all_short);
+                o[h] = kStoch ? float_quantize_stoch4(v[j][h], w[2 * h], w[2 * h] >> 16, w[2 * h + 1], w[2 * h + 1] >> 16, exp_bits, man_bits,
+                                                      lo_bits, hi_bits, mask, valid, try_short, all_short)
+                              : float_quantize_stoch4(v[j][h], half_step, half_step, half_step, half_step, exp_bits, man_bits,
+                                                      lo_bits, hi_bits, mask, valid, try_short, all_short);
             if (valid) Vec8Store<OutT>::st(out + 8 * i, o[0], o[1]);
         }
         last_short = all_short;
@@ -250,9 +250,10 @@ __global__ void quant_scalar_kernel(const float* __restrict__ in, OutT* __restri
     }
 }
 
+extern int g_opt_quant_ctas;
 static inline int grid_for(int64_t work_items, int per_block) {
     int64_t blocks = (work_items + per_block - 1) / per_block;
-    const int64_t cap = int64_t(kNumSMs) * 8;   // 8 resident CTAs of 256 threads per SM
+    const int64_t cap = int64_t(kNumSMs) * g_opt_quant_ctas;   // resident CTAs of 256 threads per SM (8; option "quant_ctas")
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return int(blocks);
@@ -272,6 +273,26 @@ static int launch_quant16(const float* in, OutT* out, int64_t n, int exp_bits, i
     }
     if (done < n) {
         quant_scalar16_kernel<OutT><<<grid_for(n - done, 256), 256, 0, st>>>(in, out, done, n, exp_bits, man_bits, seed, offset);
+        g_launches++;
+    }
+    return check_cuda(cudaGetLastError(), "quant launch");
+}
+
+// float_quantize, nearest: eight values per thread (quant_vec16_kernel<OutT, false>), scalar tail
+template <typename OutT>
+static int launch_quant_nearest8(const float* in, OutT* out, int64_t n, int exp_bits, int man_bits, cudaStream_t st) {
+    if (n == 0) return 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    int64_t done = 0;
+    if (aligned && n >= 8) {
+        const int64_t n8 = n >> 3;
+        quant_vec16_kernel<OutT, false><<<grid_for(n8, kQThreads * 4), kQThreads, 0, st>>>(in, out, n, exp_bits, man_bits, 0, 0);
+        g_launches++;
+        done = n8 << 3;
+    }
+    if (done < n) {
+        quant_scalar_kernel<0, false, OutT><<<grid_for(n - done, 256), 256, 0, st>>>(in, out, nullptr, done, n, exp_bits, man_bits,
+                                                                                    FixedParams{}, 0, 0);
         g_launches++;
     }
     return check_cuda(cudaGetLastError(), "quant launch");
@@ -488,7 +509,7 @@ extern "C" int mv_float_quantize(const float* in, void* out, int out_dtype, int6
         if (s16) return launch_quant16<float>(in, (float*)out, n, exp_bits, man_bits, seed, offset, st);
         return rounding == MV_ROUND_STOCHASTIC
                    ? launch_quant<0, true, float>(in, (float*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st)
-                   : launch_quant<0, false, float>(in, (float*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st);
+                   : launch_quant_nearest8<float>(in, (float*)out, n, exp_bits, man_bits, st);
     }
     MV_CHECK(out_dtype == MV_F16, "mv_float_quantize: unsupported out_dtype %d", out_dtype);
     MV_CHECK(exp_bits <= 5 && man_bits <= 10,
@@ -497,7 +518,7 @@ extern "C" int mv_float_quantize(const float* in, void* out, int out_dtype, int6
     if (s16) return launch_quant16<__half>(in, (__half*)out, n, exp_bits, man_bits, seed, offset, st);
     return rounding == MV_ROUND_STOCHASTIC
                ? launch_quant<0, true, __half>(in, (__half*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st)
-               : launch_quant<0, false, __half>(in, (__half*)out, nullptr, n, exp_bits, man_bits, fp, seed, offset, st);
+               : launch_quant_nearest8<__half>(in, (__half*)out, n, exp_bits, man_bits, st);
 }
 
 extern "C" int mv_fixed_point_quantize(const float* in, float* out, uint8_t* mask, int64_t n, int wl,

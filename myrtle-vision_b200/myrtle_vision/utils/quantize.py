@@ -179,8 +179,8 @@ class ModelQuantizer:
                 raise NotImplementedError("backward_format is implemented for q_format=FP16_32 (quantisers in front of "
                                           "Linear / LayerNorm and on the weights); got %s" % (q_format,))
             e, m = (int(v) for v in backward_format)
-            if not (2 <= e <= 8 and 0 <= m <= 23):
-                raise ValueError("backward_format must be (exp_bits in 2..8, man_bits in 0..23)")
+            if not (2 <= e <= 8 and 1 <= m <= 22):
+                raise ValueError("backward_format must be (exp_bits in 2..8, man_bits in 1..22)")
             plan = plan._replace(grad=(e, m))
         if q_format != QFormat.FP32:
             self._wrap_modules(plan)
