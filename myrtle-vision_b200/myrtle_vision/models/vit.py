@@ -111,6 +111,33 @@ class _STEQuant(torch.autograd.Function):
         return g, None, None, None
 
 
+class _FusedNorm(torch.autograd.Function):
+    """Decoder LayerNorm with its quantisers on the library's kernels: y = q_out(LN(q_in(x))) in one pass
+    (mv_layernorm_q_fwd, fp32 output) and dx, dgamma, dbeta in one pass (mv_layernorm_q_bwd) — in place of ATen's
+    layer_norm + three standalone quantiser passes + GammaBetaBackward (0.85 ms per step on the segmentation head's
+    [65 536, 384] input).  Straight-through quantisers, as everywhere (utils/quantize.py:87-89)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, q_in, q_out, eps):
+        x2 = x.detach().reshape(-1, x.shape[-1]).contiguous()
+        y, mean, rstd = mv_native.layernorm_q_fwd(x2, gamma.detach(), beta.detach(), q_in=q_in, q_post=q_out,
+                                                  out_dtype=torch.float32, eps=eps)
+        ctx.save_for_backward(x2, gamma, mean, rstd)
+        ctx.q_in, ctx.shape = q_in, x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, gamma, mean, rstd = ctx.saved_tensors
+        D = x2.shape[-1]
+        dy2 = dy.reshape(-1, D).contiguous().float()
+        dgamma = torch.zeros(D, dtype=torch.float32, device=dy.device)
+        dbeta = torch.zeros(D, dtype=torch.float32, device=dy.device)
+        dx, _ = mv_native.layernorm_q_bwd(dy2, x2, gamma.detach(), mean, rstd, q_in=ctx.q_in, dgamma=dgamma, dbeta=dbeta,
+                                          want_f16=False)
+        return dx.view(ctx.shape), dgamma, dbeta, None, None, None
+
+
 def _fq(x, fmt, gfmt=None):
     return x if fmt is None else _STEQuant.apply(x, fmt[0], fmt[1], gfmt)
 
@@ -239,6 +266,10 @@ class ViT(nn.Module):
     def _norm(self, holder, x):
         plan = self.quantizer.plan
         ln = _unwrap(holder)
+        d = x.shape[-1]
+        if (x.is_cuda and x.dtype == torch.float32 and plan.grad is None and ln.elementwise_affine and d % 4 == 0
+                and d <= 1024 and len(ln.normalized_shape) == 1):
+            return _FusedNorm.apply(x, ln.weight, ln.bias, plan.inp, plan.out, ln.eps)
         y = F.layer_norm(_fq(x, plan.inp, plan.grad), ln.normalized_shape, ln.weight, ln.bias, ln.eps)
         return _fq(y, plan.out)
 

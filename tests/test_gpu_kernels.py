@@ -296,7 +296,8 @@ def test_patchify_and_colsum():
     assert relmax(o, a.double().sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize("B,C,g,S", [(2, 17, 16, 256), (3, 4, 5, 80), (1, 24, 3, 48), (2, 32, 2, 32), (2, 7, 14, 224)])
+@pytest.mark.parametrize("B,C,g,S", [(2, 17, 16, 256), (3, 4, 5, 80), (1, 24, 3, 48), (2, 32, 2, 32), (2, 7, 14, 224),
+                                     (2, 19, 8, 64)])       # last: 8 pixels per cell (a warp spans six coarse cells), the 20-class tier
 def test_fused_upsample_cross_entropy(B, C, g, S):
     """mv_upsample_ce against nn.Upsample(bilinear) + CrossEntropyLoss in fp64, incl. ignore_index."""
     from myrtle_vision.models.losses import upsampled_cross_entropy

@@ -26,6 +26,7 @@ ap.add_argument("--arch", default="small")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--unfused-seg-loss", action="store_true", help="segmentation: upsample + CrossEntropyLoss in PyTorch")
 ap.add_argument("--no-graph", action="store_true")
+ap.add_argument("--profile", action="store_true", help="print the 30 largest CUDA kernels of three eager steps (torch profiler) and exit")
 ap.add_argument("--host-matcher", action="store_true",
                 help="detection: SciPy assignment on the host between two captured graphs (the round-1e path)")
 args = ap.parse_args()
@@ -63,6 +64,18 @@ def eager(img, tgt):
 for i in range(3):
     eager(*batches[i % 2])
 torch.cuda.synchronize()
+if args.profile:
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(3):
+            eager(*batches[i % 2])
+        torch.cuda.synchronize()
+    rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+    tot = sum(e.device_time_total for e in rows)
+    print("total device time per step %.3f ms" % (tot / 3e3))
+    for e in rows[:30]:
+        print("%8.3f ms/step  n=%4d  %s" % (e.device_time_total / 3e3, e.count // 3, e.key[:110]))
+    sys.exit(0)
 mv_native.enable_timing(True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
