@@ -10,6 +10,7 @@ namespace mv {
 static thread_local char g_err[512] = "";
 int64_t g_launches = 0;
 int g_opt_quant_ctas = 8;       // grid cap of the elementwise quant kernels, CTAs per SM
+int g_opt_sm_limit = 148, g_opt_sm_limit_launches = 0;   // see persistent_sms() (common.cuh)
 int g_opt_attn_sn = 1;          // short-sequence attention kernels (attention_sn.cu) when N fits
 FloatFmt g_grad_fmt = {0, 0};
 int* g_overflow = nullptr;      // device int registered with mv_set_overflow_flag (NULL: no overflow reporting)
@@ -136,6 +137,8 @@ extern "C" int64_t mv_launch_count(void) { return mv::g_launches; }
 
 extern "C" int mv_set_option(const char* name, int value) {
     if (name != nullptr && strcmp(name, "attn_sn") == 0) { mv::g_opt_attn_sn = value; return 0; }
+    if (name != nullptr && strcmp(name, "sm_limit") == 0 && value >= 16 && value <= mv::kNumSMs) { mv::g_opt_sm_limit = value; return 0; }
+    if (name != nullptr && strcmp(name, "sm_limit_launches") == 0 && value >= 0) { mv::g_opt_sm_limit_launches = value; return 0; }
     if (name != nullptr && strcmp(name, "quant_ctas") == 0 && value >= 1 && value <= 16) { mv::g_opt_quant_ctas = value; return 0; }
     mv::set_error("mv_set_option: unknown option '%s'", name ? name : "(null)");
     return 1;

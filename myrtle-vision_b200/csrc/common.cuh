@@ -28,6 +28,17 @@ int check_cuda(cudaError_t e, const char* what);
     } while (0)
 
 constexpr int kNumSMs = 148;
+// SMs the persistent kernels (CTA-pair GEMM, short-sequence attention, LayerNorm backward) size their grids for.  Normally
+// all 148.  Data-parallel training lowers it for the few launches that run beside a gradient all-reduce (options
+// "sm_limit" + "sm_limit_launches"): a persistent kernel strides a FIXED share of the work per CTA, so when NCCL's CTAs hold
+// some SMs its last CTAs run as a second wave and the kernel takes twice as long; sized for the SMs that are free, it loses
+// only their share.
+extern int g_opt_sm_limit, g_opt_sm_limit_launches;
+inline int persistent_sms() {
+    if (g_opt_sm_limit_launches <= 0) return kNumSMs;
+    g_opt_sm_limit_launches--;
+    return g_opt_sm_limit < kNumSMs ? (g_opt_sm_limit & ~1) : kNumSMs;
+}
 
 // Overflow sink (mv_set_overflow_flag): kernels that round gradient values into fp16 containers keep the largest
 // |value| they convert and raise the flag when it would not fit (>= 65520 rounds past 65504: the container

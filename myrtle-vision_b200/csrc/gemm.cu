@@ -1195,11 +1195,12 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     p.m_tiles = (a->M + 255) / 256;
     p.n_tiles = (a->N + BN - 1) / BN;
     p.kb_total = (a->K + BK - 1) / BK;
+    const int sms = persistent_sms();
     int splits = 1;
     if (a->accumulate) {
         // split K so that the work units fill whole rounds of the 74 clusters: the split count (at most two
         // rounds' worth) with the best units / (rounds * clusters); ties go to fewer splits (fewer red.adds)
-        const int tiles = p.m_tiles * p.n_tiles, clusters = kNumSMs / 2;
+        const int tiles = p.m_tiles * p.n_tiles, clusters = sms / 2;
         double best = -1.0;
         for (int sp = 1; sp <= p.kb_total && sp * tiles <= 2 * clusters; sp++) {
             const int units = sp * tiles;
@@ -1252,7 +1253,7 @@ static int gemm2_host(const mv_gemm_args* a, void* stream) {
     }
 
     const int units = p.m_tiles * p.n_tiles * p.splits;
-    const int grid = 2 * (units < kNumSMs / 2 ? units : kNumSMs / 2);
+    const int grid = 2 * (units < sms / 2 ? units : sms / 2);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
     // 16 epilogue warps only where 12 would be unbalanced: BN = 256 is 8 chunks over 3 column groups (3 / 3 / 2)

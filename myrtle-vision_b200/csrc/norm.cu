@@ -501,7 +501,7 @@ static int launch_ln_bwd(const void* dy, int dy_dtype, int64_t ld_dy, const floa
                          float* dx, int64_t ld_dx, void* dx_lp, int64_t ld_lp, float* dgamma, float* dbeta,
                          float* dbias_prev, int rows, int D, FloatFmt q_in, cudaStream_t st) {
     int grid = (rows + kLnWarps - 1) / kLnWarps;
-    const int cap = kNumSMs * 2;
+    const int cap = persistent_sms() * 2;
     if (grid > cap) grid = cap;
     const size_t smem = size_t(kLnWarps) * 3 * D * sizeof(float);
     static bool attr_done = false;

@@ -19,7 +19,7 @@ from myrtle_vision.utils.trainer import build_criterion, to_device  # noqa: E402
 
 ARCHS = {"small": dict(dim=384, depth=12, heads=6, mlp_dim=1536), "tiny": dict(dim=192, depth=12, heads=3, mlp_dim=768)}
 ap = argparse.ArgumentParser()
-ap.add_argument("task", choices=["segmentation", "detection"])
+ap.add_argument("task", choices=["classification", "segmentation", "detection"])
 ap.add_argument("--batch", type=int, default=None)
 ap.add_argument("--q-format", default="FP16_32")
 ap.add_argument("--arch", default="small")
@@ -30,7 +30,7 @@ ap.add_argument("--profile", action="store_true", help="print the 30 largest CUD
 ap.add_argument("--host-matcher", action="store_true",
                 help="detection: SciPy assignment on the host between two captured graphs (the round-1e path)")
 args = ap.parse_args()
-size, classes, batch = (256, 17, 256) if args.task == "segmentation" else (800, 20, 8)
+size, classes, batch = {"classification": (256, 45, 256), "segmentation": (256, 17, 256), "detection": (800, 20, 8)}[args.task]
 batch = args.batch or batch
 dev = torch.device("cuda")
 torch.manual_seed(1234)
@@ -41,7 +41,7 @@ items = [ds[i] for i in range(2 * batch)]
 if args.task == "detection":
     batches = [detection_collate(items[:batch]), detection_collate(items[batch:])]
 else:
-    batches = [(torch.stack([a for a, _ in part]), torch.stack([b for _, b in part])) for part in (items[:batch], items[batch:])]
+    batches = [(torch.stack([a for a, _ in part]), torch.stack([torch.as_tensor(b) for _, b in part])) for part in (items[:batch], items[batch:])]
 if args.task == "detection" and not args.host_matcher:
     from myrtle_vision.models.matcher import pad_targets
     cap = -(-max(int(t["boxes"].shape[0]) for _, ts in batches for t in ts) // 16) * 16
