@@ -194,7 +194,11 @@ int mv_widen_transpose(const void* in, int in_dtype, int64_t ld, int rows, int c
 int mv_split_tf32(const float* in, int64_t ld, int rows, int cols, float* out, int mode, void* stream);
 
 /* Library-wide switches (testing / A-B measurement).  "attn_sn": 1 (default) = sequences of at most
- * 272 keys use the resident-K/V short-sequence attention kernels, 0 = always the blocked kernels. */
+ * 272 keys use the resident-K/V short-sequence attention kernels, 0 = always the blocked kernels.
+ * "quant_ctas" (1..16, default 8): grid cap of the elementwise quantiser kernels, CTAs per SM.
+ * "sm_limit" (16..148) with "sm_limit_launches" (n >= 0): the next n launches of the persistent kernels (CTA-pair
+ * mv_gemm, short-sequence attention, mv_layernorm_q_bwd) size their grids for that many SMs — for launches that run
+ * beside a gradient all-reduce (measured no gain on B200 / NVSwitch; default: no limit). */
 int mv_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------- attention (tcgen05, flash-style)
