@@ -308,7 +308,7 @@ def _fmt(f):
 
 
 def layernorm_q_fwd(x, gamma, beta, *, q_in=None, q_post=None, out_dtype=torch.float16, eps=1e-5,
-                    save_stats=True):
+                    save_stats=True, tag=None):
     _need_cuda(x, gamma, beta)
     D = x.shape[-1]
     x2 = x.reshape(-1, D)
@@ -318,7 +318,7 @@ def layernorm_q_fwd(x, gamma, beta, *, q_in=None, q_post=None, out_dtype=torch.f
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     qi, qp = _fmt(q_in), _fmt(q_post)
-    with _timed("ln_fwd", 0.0, rows * D * (4 + y.element_size())):
+    with _timed(tag or "ln_fwd", 0.0, rows * D * (4 + y.element_size())):
         rc = lib().mv_layernorm_q_fwd(_ptr(x2), ctypes.c_int64(x2.stride(0)), _ptr(gamma), _ptr(beta),
                                       _ptr(y), ctypes.c_int64(D), _DT[out_dtype], _ptr(mean), _ptr(rstd),
                                       rows, D, ctypes.c_float(eps), qi[0], qi[1], qp[0], qp[1], _stream())
@@ -327,7 +327,7 @@ def layernorm_q_fwd(x, gamma, beta, *, q_in=None, q_post=None, out_dtype=torch.f
 
 
 def layernorm_q_bwd(dy, x, gamma, mean, rstd, *, dres=None, q_in=None, dgamma=None, dbeta=None,
-                    dbias_prev=None, want_f16=True, dx=None, dx_f16=None):
+                    dbias_prev=None, want_f16=True, dx=None, dx_f16=None, tag=None):
     _need_cuda(dy, x)
     D = x.shape[-1]
     x2, dy2 = x.reshape(-1, D), dy.reshape(-1, D)
@@ -340,7 +340,7 @@ def layernorm_q_bwd(dy, x, gamma, mean, rstd, *, dres=None, q_in=None, dgamma=No
     dres2 = dres.reshape(-1, D) if dres is not None else None
     qi = _fmt(q_in)
     # x 4 + dy + dres 4 read, dx 4 + fp16 copy 2 written
-    with _timed("ln_bwd", 0.0, rows * D * (4 + dy2.element_size() + (4 if dres is not None else 0) + 4
+    with _timed(tag or "ln_bwd", 0.0, rows * D * (4 + dy2.element_size() + (4 if dres is not None else 0) + 4
                                             + (2 if dx_f16 is not None else 0))):
         rc = lib().mv_layernorm_q_bwd(_ptr(dy2), _DT[dy2.dtype], ctypes.c_int64(dy2.stride(0)), _ptr(x2),
                                       ctypes.c_int64(x2.stride(0)), _ptr(dres2),

@@ -121,7 +121,7 @@ class _FusedNorm(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, q_in, q_out, eps):
         x2 = x.detach().reshape(-1, x.shape[-1]).contiguous()
         y, mean, rstd = mv_native.layernorm_q_fwd(x2, gamma.detach(), beta.detach(), q_in=q_in, q_post=q_out,
-                                                  out_dtype=torch.float32, eps=eps)
+                                                  out_dtype=torch.float32, eps=eps, tag="ln_fwd_head")
         ctx.save_for_backward(x2, gamma, mean, rstd)
         ctx.q_in, ctx.shape = q_in, x.shape
         return y.view(x.shape)
@@ -134,7 +134,7 @@ class _FusedNorm(torch.autograd.Function):
         dgamma = torch.zeros(D, dtype=torch.float32, device=dy.device)
         dbeta = torch.zeros(D, dtype=torch.float32, device=dy.device)
         dx, _ = mv_native.layernorm_q_bwd(dy2, x2, gamma.detach(), mean, rstd, q_in=ctx.q_in, dgamma=dgamma, dbeta=dbeta,
-                                          want_f16=False)
+                                          want_f16=False, tag="ln_bwd_head")
         return dx.view(ctx.shape), dgamma, dbeta, None, None, None
 
 

@@ -1,10 +1,11 @@
-"""Profiling driver: a few launches of attention fwd (+bwd) at the flagship shape.  usage: prof_attn_one.py [bwd]"""
+"""Profiling driver: a few launches of attention fwd (+bwd) at the flagship shape (or, with `long`, at config 5's:
+B = 8, N = 2501).  usage: prof_attn_one.py [bwd] [long]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "myrtle-vision_b200")); sys.path.insert(0, ROOT)
 import torch
 import mv_native as mv
-B, H, N = 256, 6, 257
+B, H, N = (8, 6, 2501) if "long" in sys.argv else (256, 6, 257)
 D = H * 64
 torch.manual_seed(0)
 qkv = torch.randn(B * N, 3 * D, device="cuda").half()
