@@ -543,8 +543,10 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_co
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTile);
     float* sStg = reinterpret_cast<float*>(smem + 5 * kTile + 256);      // [4 math warps][32 rows][kStgPitchF]
     uint64_t* res_full = bars;
-    uint64_t* ring_full = bars + 1;
-    uint64_t* ring_empty = bars + 2;
+    uint64_t* ring_full = bars + 1;            // Q_i landed
+    uint64_t* ring_empty = bars + 2;           // Q_i consumed (dK MMAs done)
+    uint64_t* do_full = bars + 9;              // dO_i landed / consumed (dV MMAs done): its own pair of barriers, so that the
+    uint64_t* do_empty = bars + 10;            // next dO is on its way while the dK MMAs still run
     uint64_t* sdp_full = bars + 3;
     uint64_t* pds_full = bars + 4;
     uint64_t* pds_empty = bars + 5;
@@ -560,6 +562,7 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_co
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q128); tma_prefetch_desc(&tmap_kv64); tma_prefetch_desc(&tmap_do);
         mbar_init(res_full, 1); mbar_init(ring_full, 1); mbar_init(ring_empty, 1);
+        mbar_init(do_full, 1); mbar_init(do_empty, 1);
         mbar_init(sdp_full, 1); mbar_init(pds_full, 4); mbar_init(pds_empty, 1);
         mbar_init(dq_full, 1); mbar_init(dq_done, 4);
         fence_barrier_init();
@@ -578,10 +581,12 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_co
             tma_load_3d(sK, &tmap_kv64, res_full, p.D + h * 64, blk0, b);
             tma_load_3d(sV, &tmap_kv64, res_full, 2 * p.D + h * 64, blk0, b);
             for (int it = 0; it < nblk; it++) {
+                mbar_wait(do_empty, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(do_full, kTile);
+                tma_load_3d(sdO, &tmap_do, do_full, h * 64, it * 128, b);
                 mbar_wait(ring_empty, (it & 1) ^ 1);
-                mbar_arrive_expect_tx(ring_full, 2 * kTile);
+                mbar_arrive_expect_tx(ring_full, kTile);
                 tma_load_3d(sQ, &tmap_q128, ring_full, h * 64, it * 128, b);
-                tma_load_3d(sdO, &tmap_do, ring_full, h * 64, it * 128, b);
             }
         }
     } else if (warp == 1) {
@@ -592,30 +597,35 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_co
             mbar_wait(res_full, 0);
             for (int it = 0; it < nblk; it++) {
                 const int nq16 = (min(128, p.N - it * 128) + 15) & ~15;
+                // dP first: dO arrives first, and its TMEM columns are not the ones the previous dQ tile is still read from
+                mbar_wait(do_full, it & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    umma_f16(tdP, make_smem_desc_sw128(aDO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), idesc_s, k > 0);
                 mbar_wait(ring_full, it & 1);
                 if (it > 0) mbar_wait(dq_done, (it - 1) & 1);        // dQ tile (aliasing S) has been read
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     umma_f16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k > 0);
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    umma_f16(tdP, make_smem_desc_sw128(aDO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), idesc_s, k > 0);
                 umma_commit(sdp_full);
                 mbar_wait(pds_full, it & 1);
                 tc_fence_after();
-                // dV[keys, d] += P^T dO ; dK[keys, d] += dS^T Q   (M = 128: rows 64..127 are don't-care)
-                for (int k = 0; k < (nq16 >> 4); k++)
-                    umma_f16(tdV, make_smem_desc_sw128(aP + k * 2048, kTile, 1024),
-                             make_smem_desc_sw128(aDO + k * 2048, 8192, 1024), kIdescTT64, (it > 0 || k > 0));
-                for (int k = 0; k < (nq16 >> 4); k++)
-                    umma_f16(tdK, make_smem_desc_sw128(adS + k * 2048, kTile, 1024),
-                             make_smem_desc_sw128(aQ + k * 2048, 8192, 1024), kIdescTT64, (it > 0 || k > 0));
-                // dQ_i contribution of this key block = dS K_j
+                // dQ_i contribution of this key block = dS K_j — first, with its own commit: the math warps read it out
+                // and red.add it while the dV / dK MMAs below run
                 for (int k = 0; k < (nk16 >> 4); k++)
                     umma_f16(tdQ, make_smem_desc_sw128(adS + k * 32, 16, 1024),
                              make_smem_desc_sw128(aK + k * 2048, 8192, 1024), kIdescPV, k > 0);
                 umma_commit(dq_full);
+                // dV[keys, d] += P^T dO ; dK[keys, d] += dS^T Q   (M = 128: rows 64..127 are don't-care)
+                for (int k = 0; k < (nq16 >> 4); k++)
+                    umma_f16(tdV, make_smem_desc_sw128(aP + k * 2048, kTile, 1024),
+                             make_smem_desc_sw128(aDO + k * 2048, 8192, 1024), kIdescTT64, (it > 0 || k > 0));
+                umma_commit(do_empty);
+                for (int k = 0; k < (nq16 >> 4); k++)
+                    umma_f16(tdK, make_smem_desc_sw128(adS + k * 2048, kTile, 1024),
+                             make_smem_desc_sw128(aQ + k * 2048, 8192, 1024), kIdescTT64, (it > 0 || k > 0));
                 umma_commit(ring_empty);
                 umma_commit(pds_empty);
             }
