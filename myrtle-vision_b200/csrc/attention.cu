@@ -174,15 +174,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdDev p
                 // pass 1: row max of the scaled scores
                 float mx = -INFINITY;
                 const bool full_blk = kbase + 128 <= p.N;       // only the last block needs key masking
-#pragma unroll 1
-                for (int c = 0; c < nchunk; c++) {
-                    uint32_t s[32];
-                    tmem_ld_32x32(tS + lane_off + c * 32, s);
+                if (full_blk) {
+                    // 128 live keys: the next 32 columns are in flight while the current ones are reduced
+                    uint32_t sa[32], sb[32];
+                    float mx1 = -INFINITY;
+                    tmem_ld_32x32(tS + lane_off, sa);
                     tmem_ld_wait();
-                    if (full_blk) {
 #pragma unroll
-                        for (int t = 0; t < 32; t++) mx = fmaxf(mx, __uint_as_float(s[t]));
-                    } else {
+                    for (int c = 0; c < 4; c += 2) {
+                        tmem_ld_32x32(tS + lane_off + (c + 1) * 32, sb);
+#pragma unroll
+                        for (int t = 0; t < 16; t++) {
+                            mx = fmaxf(mx, __uint_as_float(sa[2 * t])); mx1 = fmaxf(mx1, __uint_as_float(sa[2 * t + 1]));
+                        }
+                        tmem_ld_wait();
+                        if (c + 2 < 4) tmem_ld_32x32(tS + lane_off + (c + 2) * 32, sa);
+#pragma unroll
+                        for (int t = 0; t < 16; t++) {
+                            mx = fmaxf(mx, __uint_as_float(sb[2 * t])); mx1 = fmaxf(mx1, __uint_as_float(sb[2 * t + 1]));
+                        }
+                        tmem_ld_wait();
+                    }
+                    mx = fmaxf(mx, mx1);
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < nchunk; c++) {
+                        uint32_t s[32];
+                        tmem_ld_32x32(tS + lane_off + c * 32, s);
+                        tmem_ld_wait();
 #pragma unroll
                         for (int t = 0; t < 32; t++)
                             if (kbase + c * 32 + t < p.N) mx = fmaxf(mx, __uint_as_float(s[t]));

@@ -512,8 +512,34 @@ attn_fwd_sn_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_con
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
             for (int e = 0; e < kSnExtraMax; e++) mx0 = fmaxf(mx0, sx[e]);
+            // whole 64-key steps inside [0, N): the next 32 columns are in flight while the current ones are reduced
+            int k_pipe = 0;
+            if (p.Nk >= 64 && p.Nk <= p.N) {
+                const int kend = p.Nk & ~63;
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(tS, va);
+                tmem_ld_wait();
 #pragma unroll 1
-            for (int k0 = 0; k0 < p.Nk; k0 += 32) {
+                for (int k0 = 0; k0 < kend; k0 += 64) {
+                    tmem_ld_32x32(tS + k0 + 32, vb);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        mx0 = fmaxf(mx0, __uint_as_float(va[2 * i]));
+                        mx1 = fmaxf(mx1, __uint_as_float(va[2 * i + 1]));
+                    }
+                    tmem_ld_wait();
+                    if (k0 + 64 < kend) tmem_ld_32x32(tS + k0 + 64, va);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        mx0 = fmaxf(mx0, __uint_as_float(vb[2 * i]));
+                        mx1 = fmaxf(mx1, __uint_as_float(vb[2 * i + 1]));
+                    }
+                    tmem_ld_wait();
+                }
+                k_pipe = kend;
+            }
+#pragma unroll 1
+            for (int k0 = k_pipe; k0 < p.Nk; k0 += 32) {
                 if (k0 + 32 <= p.Nk) {
                     uint32_t v[32];
                     tmem_ld_32x32(tS + k0, v);
